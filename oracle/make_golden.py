@@ -1,0 +1,230 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference.
+
+TEST INFRASTRUCTURE.  Run in the build container only (needs /root/reference):
+
+    python oracle/make_golden.py
+
+The reference is imported from /root/reference with the stand-ins under
+oracle/standins (astropy, flatstar are absent from the image).  Every array
+stored here is an output of the reference's own functions, never of the oracle or
+of the CUDA engine.  The fixtures travel to the GPU box; /root/reference does not.
+"""
+import os
+import sys
+import warnings
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import refloader  # noqa: E402
+
+refloader.load()
+import astropy.units as u  # noqa: E402  (stand-in)
+from p_winds import parker, hydrogen, helium, transit, tools, lines  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(HERE), 'tests', 'golden')
+DATA = os.path.join(refloader.REFERENCE_ROOT, 'data')
+
+R_PL, M_PL = 1.39, 0.73
+M_STAR, A_AU = 1.07, 0.04634
+R = np.logspace(0, np.log10(20), 100)
+M_HE = 4 * 1.67262192369e-27
+TIGHT_H = dict(rtol=1e-10, atol=1e-13)
+TIGHT_HE = dict(method='LSODA', rtol=1e-10, atol=1e-16)
+
+
+def spectrum_dict():
+    units = {'wavelength': u.angstrom,
+             'flux': u.erg / u.s / u.cm ** 2 / u.angstrom}
+    return tools.make_spectrum_from_file(
+        os.path.join(DATA, 'solar_spectrum_scaled_lambda.dat'), units)
+
+
+def one_model(sp, geom, T0, mdot, h, tidal, tight):
+    """The docs' cascading model (quickstart.ipynb cells 4-12)."""
+    he_h = (1 - h) / h
+    mu_0 = (1 + 4 * he_h) / (1 + he_h + 0.0)
+    kw = dict(star_mass=M_STAR, semimajor_axis=A_AU) if tidal else {}
+    o = dict(status=0, f_r=np.full(100, np.nan), mu_bar=np.nan,
+             v=np.full(100, np.nan), rho=np.full(100, np.nan),
+             f_1=np.full(100, np.nan), f_3=np.full(100, np.nan),
+             spectrum=np.full(200, np.nan), vs=np.nan, rs=np.nan, rhos=np.nan)
+    try:
+        f_r, mu = hydrogen.ion_fraction(
+            R, R_PL, T0, h, mdot, M_PL, mu_0, spectrum_at_planet=sp,
+            exact_phi=True, initial_f_ion=0.0, relax_solution=True,
+            return_mu=True, **kw, **(TIGHT_H if tight else {}))
+    except RuntimeError:
+        o['status'] = 1
+        return o
+    vs = parker.sound_speed(T0, mu)
+    if tidal:
+        rs = parker.radius_sonic_point_tidal(M_PL, vs, M_STAR, A_AU)
+        rhos = parker.density_sonic_point(mdot, rs, vs)
+        v, rho = parker.structure_tidal(R * R_PL / rs, vs, rs, M_PL, M_STAR, A_AU)
+    else:
+        rs = parker.radius_sonic_point(M_PL, vs)
+        rhos = parker.density_sonic_point(mdot, rs, vs)
+        v, rho = parker.structure(R * R_PL / rs)
+    o.update(f_r=f_r, mu_bar=mu, v=v, rho=rho, vs=vs, rs=rs, rhos=rhos)
+    try:
+        with warnings.catch_warnings(record=True) as w:
+            warnings.simplefilter('always')
+            f1, f3 = helium.population_fraction(
+                R, v, rho, f_r, R_PL, T0, h, vs, rs, rhos, sp,
+                initial_state=np.array([1.0, 0.0]), relax_solution=True,
+                **(TIGHT_HE if tight else {}))
+        if any('odeint' in str(x.message).lower() or 'lsoda' in str(x.message).lower()
+               or 'Excess' in str(x.message) for x in w):
+            o['status'] = 3
+    except RuntimeError:
+        o['status'] = 2
+        return o
+    o.update(f_1=f1, f_3=f3)
+    he_fraction = 1 - h
+    n_he = rho * rhos * he_fraction / (h + 4 * he_fraction) / 1.67262192369e-24
+    w0, w1, w2, f0, f1_, f2, a_ij = lines.he_3_properties()
+    wl = np.linspace(1.0827, 1.0832, 200) * 1E-6
+    i0, r_map = geom
+    o['spectrum'] = transit.radiative_transfer_2d(
+        i0, r_map, R * R_PL * 71492000, f3 * n_he * 1E6, v * vs * 1000,
+        np.array([w0, w1, w2]), np.array([f0, f1_, f2]), np.array([a_ij] * 3),
+        wl, float(T0), M_HE, wind_broadening_method='average')
+    return o
+
+
+def stack(models):
+    keys = models[0].keys()
+    return {k: np.array([m[k] for m in models]) for k in keys}
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    sp = spectrum_dict()
+
+    # ---- data fixtures (the SED and the He 2^3S profile the reference tests use)
+    np.savez_compressed(os.path.join(OUT, 'solar_sed.npz'),
+                        wavelength=sp['wavelength'], flux_lambda=sp['flux_lambda'])
+    prof = np.loadtxt(os.path.join(DATA, 'he_3_profile.dat'))
+    np.savez_compressed(os.path.join(OUT, 'he_3_profile.npz'), r=prof[:, 0],
+                        v=prof[:, 1], n=prof[:, 2])
+
+    # ---- SED scalars
+    phi, a0 = hydrogen.radiative_processes(sp)
+    he = helium.radiative_processes(sp)
+    np.savez(os.path.join(OUT, 'sed_scalars.npz'), h=np.array([phi, a0]),
+             he=np.array(he), he_collision_9100=np.array(helium.collision(9100.)),
+             he_recomb_9100=np.array(helium.recombination(9100.)),
+             h_recomb_9100=hydrogen.recombination(9100.))
+
+    # ---- geometry (quickstart: k=0.12086, b=0.499, G=100, ss=10) + the test geometry
+    i0, depth, r_map = transit.draw_transit(0.12086, R_PL * 71492000, 0.499, 0.0,
+                                            supersampling=10, grid_size=100)
+    t0, td, tr = transit.draw_transit(0.12086, R_PL * 71492000, 0.0, 0.0,
+                                      supersampling=10, grid_size=101)
+    ld = {}
+    for law, c in (('linear', 0.5), ('quadratic', [0.3, 0.2]),
+                   ('square-root', [0.3, 0.2]), ('log', [0.3, 0.2]),
+                   ('exp', [0.3, 0.01]), ('s3', [0.3, 0.2, 0.1]),
+                   ('c4', [0.3, 0.2, 0.1, 0.05])):
+        m, d, rm = transit.draw_transit(0.1, 1.0, 0.3, -0.2, supersampling=4,
+                                        grid_size=40, limb_darkening_law=law,
+                                        ld_coefficient=c)
+        ld['ld_%s_map' % law] = m
+        ld['ld_%s_depth' % law] = d
+        ld['ld_%s_rmap' % law] = rm
+    np.savez_compressed(os.path.join(OUT, 'geometry.npz'), i0=i0, depth=depth,
+                        r_map=r_map, test_i0=t0, test_depth=td, test_r_map=tr, **ld)
+
+    # ---- RT known-answer fixture (tests/test_transit.py:42-48 inputs)
+    w0, w1, w2, f0, f1, f2, a_ij = lines.he_3_properties()
+    wl = np.linspace(1.0827, 1.0832, 150) * 1E-6
+    args = (prof[:, 0], prof[:, 2], prof[:, 1], np.array([w0, w1, w2]),
+            np.array([f0, f1, f2]), np.array([a_ij] * 3))
+    s_avg = transit.radiative_transfer_2d(t0, tr, *args, wl, 9E3, M_HE,
+                                          bulk_los_velocity=-2E3)
+    tau_avg = transit.optical_depth_2d(*args, wl, 9E3, M_HE, 200, -2E3)
+    s_turb = transit.radiative_transfer_2d(t0, tr, *args, wl, 9E3, M_HE,
+                                           bulk_los_velocity=-2E3,
+                                           planet_radial_velocity=1.5E3,
+                                           turbulence_broadening=True)
+    s_formal = transit.radiative_transfer_2d(t0, tr, *args, wl[::6], 9E3, M_HE,
+                                             bulk_los_velocity=-2E3,
+                                             wind_broadening_method='formal')
+    tprof = np.linspace(9E3, 7E3, len(prof))
+    s_tprof = transit.radiative_transfer_2d(t0, tr, *args, wl, tprof, M_HE,
+                                            bulk_los_velocity=-2E3)
+    s_formal_t = transit.radiative_transfer_2d(t0, tr, *args, wl[::6], tprof, M_HE,
+                                               bulk_los_velocity=-2E3,
+                                               wind_broadening_method='formal')
+    s_single = transit.radiative_transfer_2d(1.0, tr, *args[:3], w1, f1, a_ij, wl,
+                                             9E3, M_HE)
+    np.savez_compressed(os.path.join(OUT, 'rt_known_answer.npz'), wl=wl,
+                        spectrum_average=s_avg, tau_average=tau_avg,
+                        spectrum_turbulence_rv=s_turb, spectrum_formal=s_formal,
+                        spectrum_tprofile=s_tprof, spectrum_formal_tprofile=s_formal_t,
+                        tprofile=tprof, spectrum_single_line_scalar_i0=s_single)
+
+    # ---- Parker structure
+    rr = np.concatenate((np.logspace(-1.2, 0, 40), np.logspace(0, 1.2, 40)[1:]))
+    v, rho = parker.structure(rr)
+    cs = parker.sound_speed(9100., 0.8)
+    rs = parker.radius_sonic_point_tidal(M_PL, cs, M_STAR, A_AU)
+    vt, rhot = parker.structure_tidal(rr, cs, rs, M_PL, M_STAR, A_AU)
+    np.savez(os.path.join(OUT, 'parker.npz'), r=rr, v=v, rho=rho, cs=cs, rs_tidal=rs,
+             rs_plain=parker.radius_sonic_point(M_PL, cs),
+             rhos=parker.density_sonic_point(1e11, rs, cs), v_tidal=vt, rho_tidal=rhot,
+             v_at_1=np.array(parker.structure(1.0)),
+             cs_1e4=parker.sound_speed(1e4, 1.0))
+
+    # ---- hydrogen-stage goldens incl. the reference's own test configuration
+    r500 = np.linspace(1, 15, 500)
+    f_apx = hydrogen.ion_fraction(r500, R_PL, 9E3, 0.9, 8E10, M_PL, 0.7,
+                                  spectrum_at_planet=sp, relax_solution=True)
+    f_ex = hydrogen.ion_fraction(r500, R_PL, 9E3, 0.9, 8E10, M_PL, 0.7,
+                                 spectrum_at_planet=sp, relax_solution=True,
+                                 exact_phi=True)
+    f_mono = hydrogen.ion_fraction(np.linspace(1.0, 20, 500), R_PL, 9100., 0.9,
+                                   10 ** 10.27, M_PL, 0.7613, flux_euv=1000.,
+                                   initial_f_ion=0.0, relax_solution=True)
+    f_norelax, mu_norelax = hydrogen.ion_fraction(
+        R, R_PL, 9100., 0.9, 10 ** 10.27, M_PL, 1.3, spectrum_at_planet=sp,
+        exact_phi=True, return_mu=True)
+    np.savez_compressed(os.path.join(OUT, 'hydrogen.npz'), r500=r500, f_approx=f_apx,
+                        f_exact=f_ex, f_mono=f_mono, f_norelax=f_norelax,
+                        mu_norelax=mu_norelax)
+
+    # ---- anchor models through the whole chain
+    geom = (i0, r_map)
+    sets = {
+        # defaults (reference tolerances): includes failing models (T0 <= 8000)
+        'anchors_default': [(T, 10 ** lm, 0.9, False, False)
+                            for T in (6000., 8000., 9100., 10000., 11500., 13000.)
+                            for lm in (9.5, 10.27, 11.0, 11.6, 12.0)],
+        'anchors_default_tidal': [(T, 10 ** lm, h, True, False)
+                                  for T in (7000., 9000., 10500., 12500.)
+                                  for lm in (9.7, 10.6, 11.5) for h in (0.85, 0.95)],
+        # tight tolerances: the tier where 1e-6 / 1e-5 is enforceable per model
+        'anchors_tight': [(T, 10 ** lm, 0.9, False, True)
+                          for T in (9100., 10500., 12500.)
+                          for lm in (9.7, 10.27, 11.0, 11.7)],
+        'anchors_tight_tidal': [(T, 10 ** lm, h, True, True)
+                                for T in (9100., 11500.) for lm in (10.0, 11.3)
+                                for h in (0.85, 0.95)],
+    }
+    for name, plist in sets.items():
+        models = []
+        for (T, md, h, tidal, tight) in plist:
+            m = one_model(sp, geom, T, md, h, tidal, tight)
+            m.update(T0=T, mdot=md, h_fraction=h)
+            models.append(m)
+            print(name, T, '%.3e' % md, h, 'status', m['status'], flush=True)
+        d = stack(models)
+        d['tidal'] = plist[0][3]
+        d['tight'] = plist[0][4]
+        np.savez_compressed(os.path.join(OUT, name + '.npz'), **d)
+
+
+if __name__ == '__main__':
+    main()
