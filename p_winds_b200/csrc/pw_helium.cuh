@@ -1,0 +1,314 @@
+// pw_helium.cuh -- He singlet / triplet population profile of one model
+// (reference: p_winds/helium.py:413-785 `population_fraction`, :270-292
+// `recombination`, :317-380 `collision`).  Oklopcic & Hirata 2018 Eq. 15 in
+// sonic-point units, integrated with the LSODA replica (method='odeint', the
+// reference default), LSODA at user tolerances, or the RK45 replica.
+//
+// One *thread* integrates one model: the solve is ~10^3 dependent implicit
+// steps, there is nothing to share between lanes, and a retrieval grid supplies
+// thousands of independent models.
+#pragma once
+#include "pw_common.cuh"
+#include "pw_lsoda.cuh"
+#include "pw_rk45.cuh"
+
+namespace pw {
+
+enum { PW_HE_ODEINT = 0, PW_HE_LSODA = 1, PW_HE_RK45 = 2 };
+
+struct HeParams {
+  double T, h_fraction, vs, rs, rhos;  // per model
+  double r_pl;
+  double y0[2];
+  int relax, max_n_relax;
+  double convergence;
+  double rates[6];  // phi_1, phi_3, a_1, a_3, a_h_1, a_h_3 (cgs; helium.radiative_processes[_mono])
+  int method;
+  double rtol, atol;  // for PW_HE_LSODA / PW_HE_RK45
+  double first_step, max_step;
+};
+
+// helium.collision (helium.py:317-380)
+PW_HD void he_collision(double T, double* q13, double* q31a, double* q31b, double* bq_he, double* bq_hep) {
+  const double lt[9] = {3.75, 4.00, 4.25, 4.50, 4.75, 5.00, 5.25, 5.50, 5.75};
+  const double g13[9] = {6.198E-2, 6.458E-2, 6.387E-2, 6.157E-2, 5.832E-2, 5.320E-2, 4.787E-2, 4.018E-2, 3.167E-2};
+  const double g31a[9] = {2.389, 2.456, 2.275, 1.916, 1.496, 1.111, 8.003E-1, 5.660E-1, 3.944E-1};
+  const double g31b[9] = {7.965E-1, 9.579E-1, 1.042, 1.015, 8.950E-1, 7.265E-1, 5.516E-1, 3.948E-1, 2.677E-1};
+  double tt[9];
+  for (int i = 0; i < 9; ++i) tt[i] = pow(10.0, lt[i]);
+  const int j = bracket(tt, 9, T, 0);
+  const double G13 = np_interp_at(tt, g13, 9, T, j);
+  const double G31a = np_interp_at(tt, g31a, 9, T, j);
+  const double G31b = np_interp_at(tt, g31b, 9, T, j);
+  const double kt = 8.617333262145179e-05 * T;
+  const double k1 = 2.10E-8 * sqrt(13.6 / kt);
+  *q13 = k1 * G13 * exp(-19.81 / kt);
+  *q31a = k1 * G31a / 3 * exp(-0.80 / kt);
+  *q31b = k1 * G31b / 3 * exp(-1.40 / kt);
+  *bq_he = 1.75E-11 * pow(300 / T, 0.75) * exp(-128E3 / T);
+  *bq_hep = 1.25E-15 * pow(300 / T, -0.25);
+}
+
+// Right-hand side helium.py:624-686.  The eight density-weighted rate
+// coefficients and the two attenuation factors depend on the radius only, so they
+// are cached per abscissa: the corrector iterations and the finite-difference
+// Jacobian of one LSODA step all evaluate at the same x.
+struct HeRhs {
+  const double *rn, *v, *rho, *fh, *tau1, *tau3;
+  int n;
+  double lk1;         // log(k1)
+  double lc[8];       // log of alpha_rec_1, alpha_rec_3, q_13, q_31a, q_31b, Q_31, Q_He, Q_He+
+  double phi1, phi3, ba31;
+  // cache
+  int j;
+  double xc;
+  double c[8], e1, e3, vv;
+  double sl[5], x0, b0[5];
+  int jc;
+
+  PW_HD void coeffs(double x) {
+    const int jj = bracket(rn, n, x, j);
+    j = jj;
+    double v_, rho_, fh_, t1, t3;
+    if (jj < 0 || jj >= n - 1 || rn[jj] == x) {
+      v_ = np_interp_at(rn, v, n, x, jj);
+      rho_ = np_interp_at(rn, rho, n, x, jj);
+      fh_ = np_interp_at(rn, fh, n, x, jj);
+      t1 = np_interp_at(rn, tau1, n, x, jj);
+      t3 = np_interp_at(rn, tau3, n, x, jj);
+    } else {
+      if (jj != jc) {  // slopes exactly as numpy forms them, kept while x stays in the cell
+        jc = jj;
+        x0 = rn[jj];
+        const double dx = rn[jj + 1] - x0;
+        b0[0] = v[jj]; sl[0] = (v[jj + 1] - b0[0]) / dx;
+        b0[1] = rho[jj]; sl[1] = (rho[jj + 1] - b0[1]) / dx;
+        b0[2] = fh[jj]; sl[2] = (fh[jj + 1] - b0[2]) / dx;
+        b0[3] = tau1[jj]; sl[3] = (tau1[jj + 1] - b0[3]) / dx;
+        b0[4] = tau3[jj]; sl[4] = (tau3[jj + 1] - b0[4]) / dx;
+      }
+      const double d = x - x0;
+      v_ = sl[0] * d + b0[0];
+      rho_ = sl[1] * d + b0[1];
+      fh_ = sl[2] * d + b0[2];
+      t1 = sl[3] * d + b0[3];
+      t3 = sl[4] * d + b0[4];
+    }
+    const double lr = lk1 + log(rho_);
+    // exp(log(k1) + log(rho) + log(coef)) * f_h_ion   (helium.py:637-652)
+    c[0] = exp(lr + lc[0]) * fh_;
+    c[1] = exp(lr + lc[1]) * fh_;
+    c[2] = exp(lr + lc[2]) * fh_;
+    c[3] = exp(lr + lc[3]) * fh_;
+    c[4] = exp(lr + lc[4]) * fh_;
+    c[5] = exp(lr + lc[5]) * (1 - fh_);
+    c[6] = exp(lr + lc[6]) * fh_;
+    c[7] = exp(lr + lc[7]) * (1 - fh_);
+    e1 = exp(-t1);
+    e3 = exp(-t3);
+    vv = v_;
+    xc = x;
+  }
+
+  // terms[11] in the reference's order (helium.py:684-686) when `terms` != null
+  PW_HD void eval(const double* y, double* dydx, double* terms) const {
+    const double f_1 = y[0], f_3 = y[1];
+    const double term_11 = (1 - f_1 - f_3) * c[0];
+    const double term_12 = f_3 * ba31;
+    const double term_13 = f_1 * phi1 * e1;
+    const double term_14 = f_1 * c[2];
+    const double term_15 = f_3 * c[3];
+    const double term_16 = f_3 * c[4];
+    const double term_17 = f_3 * c[5];
+    const double term_18 = f_1 * c[6];
+    const double term_19 = (1 - f_1 - f_3) * c[7];
+    const double term_31 = (1 - f_1 - f_3) * c[1];
+    const double term_33 = f_3 * phi3 * e3;
+    if (dydx) {
+      dydx[0] = (term_11 + term_12 - term_13 - term_14 + term_15 + term_16 + term_17 - term_18 + term_19) / vv;
+      dydx[1] = (term_31 - term_12 - term_33 + term_14 - term_15 - term_16 - term_17) / vv;
+    }
+    if (terms) {
+      terms[0] = term_13; terms[1] = term_33; terms[2] = term_11; terms[3] = term_31;
+      terms[4] = term_12; terms[5] = term_14; terms[6] = term_15; terms[7] = term_16;
+      terms[8] = term_17; terms[9] = term_18; terms[10] = term_19;
+    }
+  }
+
+  PW_HD void operator()(double x, const double* y, double* dydx) {
+    if (!(x == xc)) coeffs(x);
+    eval(y, dydx, nullptr);
+  }
+};
+
+// Per-model scratch (global memory on the device), Nr doubles each.
+struct HeWork {
+  double *rn, *tau1, *tau3, *tau1h, *tau3h;
+  double* w;  // 5*Nr: [0,Nr) dr*density, [Nr,3Nr) previous profiles, [3Nr,5Nr) RK45 output staging
+};
+
+struct HeOut {
+  double* f1;      // [Nr]
+  double* f3;      // [Nr]
+  double* scal;    // [4]: n_relax, nfe_total, nst_total, nje_total
+  double* rates;   // [11][Nr] or null (helium.py:770-784)
+  int* status;
+};
+
+// Integrate once over the radius grid; returns false when the reference's solver
+// would have reported a problem (odeint warning / solve_ivp short output).
+PW_HD bool he_solve(const HeParams& p, HeRhs& rhs, const LsodaTables& tab, int nr, double* f1, double* f3,
+                    double* ytmp, int* nfe, int* nst, int* nje) {
+  const double* rn = rhs.rn;
+  rhs.j = 0; rhs.jc = -2; rhs.xc = nan("");
+  if (p.method == PW_HE_RK45) {
+    // solve_ivp(method='RK45', t_eval=r) (helium.py:702-710); interleaved (f1, f3)
+    // samples go to the spare scratch and are split afterwards
+    Rk45Opts o{p.rtol, p.atol, p.first_step, p.max_step};
+    Rk45Stats st{0, 0, 0};
+    const int got = rk45_solve<2>(rhs, rn, nr, p.y0, o, ytmp, &st);
+    for (int k = 0; k < got; ++k) { f1[k] = ytmp[2 * k]; f3[k] = ytmp[2 * k + 1]; }
+    *nfe += st.nfev; *nst += st.naccept;
+    return got == nr;
+  }
+  LsodaOpts lo;
+  if (p.method == PW_HE_ODEINT) { lo.rtol = 1.49012e-8; lo.atol = 1.49012e-8; }
+  else { lo.rtol = p.rtol; lo.atol = p.atol; }
+  // odeint: mxstep = 500 per output interval.  solve_ivp's LSODA wrapper advances one
+  // internal step per call (itask = 5), so no such limit applies there.
+  lo.mxstep = (p.method == PW_HE_ODEINT) ? 500 : 2000000000;
+  lo.hmax = (p.max_step > 0.) ? p.max_step : 0.;
+  lo.h0 = (p.first_step > 0.) ? p.first_step : 0.;
+  Lsoda<2, HeRhs> s(rhs, tab, lo);
+  f1[0] = p.y0[0];
+  f3[0] = p.y0[1];
+  bool ok = true;
+  for (int k = 1; k < nr; ++k) {
+    double yo[2];
+    const int istate = s.call(rn[0], p.y0, rn[k], yo);
+    if (istate < 0) {
+      // odeint stops at the first failing output point (ODEintWarning) and leaves
+      // the remaining rows of its zero-initialised result array untouched
+      ok = false;
+      for (int q = k; q < nr; ++q) { f1[q] = 0.0; f3[q] = 0.0; }
+      break;
+    }
+    f1[k] = yo[0];
+    f3[k] = yo[1];
+  }
+  *nfe += s.nfe; *nst += s.nst; *nje += s.nje;
+  return ok;
+}
+
+// `r` radius profile in planetary radii (shared), v / rho / f_h per model.
+PW_HD void he_population_model(const HeParams& p, const LsodaTables& tab, const double* __restrict__ r,
+                               const double* __restrict__ v, const double* __restrict__ rho,
+                               const double* __restrict__ f_h, int nr, const HeWork& w, const HeOut& out) {
+  const double rs_cm = p.rs * 7.1492E+09;
+  const double alpha_unit = (rs_cm * rs_cm) * p.vs * 1E5;                 // helium.py:553
+  const double a_r1 = 1.54E-13 * pow(p.T / 1E4, -0.486) / alpha_unit;     // :290, :555
+  const double a_r3 = 2.10E-13 * pow(p.T / 1E4, -0.778) / alpha_unit;     // :291, :556
+  const double m_h = 1.67262192E-24 / (p.rhos * (rs_cm * rs_cm * rs_cm)); // :559-560
+  const double phi_unit = p.vs * 1E5 / p.rs / 7.1492E+09;                 // :570
+  const double phi_1 = p.rates[0] / phi_unit, phi_3 = p.rates[1] / phi_unit;
+  const double a_1 = p.rates[2] / (rs_cm * rs_cm), a_3 = p.rates[3] / (rs_cm * rs_cm);
+  const double a_h_1 = p.rates[4] / (rs_cm * rs_cm), a_h_3 = p.rates[5] / (rs_cm * rs_cm);
+  double q13, q31a, q31b, bq_he, bq_hep;
+  he_collision(p.T, &q13, &q31a, &q31b, &bq_he, &bq_hep);
+  q13 /= alpha_unit; q31a /= alpha_unit; q31b /= alpha_unit; bq_he /= alpha_unit; bq_hep /= alpha_unit;
+  const double bq31 = 5E-10 / alpha_unit;      // :598
+  const double ba31 = 1.272E-4 / phi_unit;     // :599
+  const double he_fraction = 1 - p.h_fraction;
+  const double k1 = p.h_fraction / (p.h_fraction + 4 * he_fraction) / m_h;   // :616
+  const double k2 = he_fraction / (p.h_fraction + 4 * he_fraction) / m_h;    // :617
+
+  // r, dr in sonic units; total and neutral-H column densities, rectangle rule with
+  // the local cell included (:604-621)
+  for (int i = 0; i < nr; ++i) w.rn[i] = r[i] * p.r_pl / p.rs;
+  {
+    double c = 0.0, ch = 0.0;
+    for (int i = nr - 1; i >= 0; --i) {
+      const double dr = (i < nr - 1) ? (w.rn[i + 1] - w.rn[i]) : (w.rn[nr - 1] - w.rn[nr - 2]);
+      w.w[i] = dr * rho[i];
+      c += w.w[i];
+      ch += w.w[i] * (1 - f_h[i]);
+      w.tau1h[i] = k1 * a_h_1 * ch;
+      w.tau3h[i] = k1 * a_h_3 * ch;
+      w.tau1[i] = (p.y0[0] * k2 * a_1 * c + w.tau1h[i]);
+      w.tau3[i] = (p.y0[1] * k2 * a_3 * c + w.tau3h[i]);
+    }
+  }
+  HeRhs rhs;
+  rhs.rn = w.rn; rhs.v = v; rhs.rho = rho; rhs.fh = f_h; rhs.tau1 = w.tau1; rhs.tau3 = w.tau3;
+  rhs.n = nr;
+  rhs.lk1 = log(k1);
+  rhs.lc[0] = log(a_r1); rhs.lc[1] = log(a_r3); rhs.lc[2] = log(q13); rhs.lc[3] = log(q31a);
+  rhs.lc[4] = log(q31b); rhs.lc[5] = log(bq31); rhs.lc[6] = log(bq_he); rhs.lc[7] = log(bq_hep);
+  rhs.phi1 = phi_1; rhs.phi3 = phi_3; rhs.ba31 = ba31;
+
+  int nfe = 0, nst = 0, nje = 0, n_relax = 0, status = PW_OK;
+  double* f1 = out.f1;
+  double* f3 = out.f3;
+  auto clamp = [&]() {  // helium.py:715-718
+    for (int i = 0; i < nr; ++i) {
+      if (f1[i] < 0) f1[i] = 1E-15;
+      if (f3[i] < 0) f3[i] = 1E-15;
+      if (f1[i] > 1.0) f1[i] = 1.0;
+      if (f3[i] > 1.0) f3[i] = 1.0;
+    }
+  };
+  double* p1 = w.w + nr;
+  double* p3 = w.w + 2 * nr;
+  double* ytmp = w.w + 3 * nr;
+  bool ok = he_solve(p, rhs, tab, nr, f1, f3, ytmp, &nfe, &nst, &nje);
+  if (!ok) {
+    status = PW_FAIL_HE_SOLVER;  // helium.py:693-697, :708-710
+  } else {
+    clamp();
+    if (p.relax) {
+      for (int it = 0; it < p.max_n_relax; ++it) {
+        ++n_relax;
+        // new optical depths from the current populations (:729-732); keep the sums
+        // of the previous profiles for the convergence test (:753-756)
+        double c1 = 0.0, c3 = 0.0, s1 = 0.0, s3 = 0.0;
+        for (int i = nr - 1; i >= 0; --i) {
+          c1 += w.w[i] * f1[i];
+          c3 += w.w[i] * f3[i];
+          w.tau1[i] = k2 * a_1 * c1 + w.tau1h[i];
+          w.tau3[i] = k2 * a_3 * c3 + w.tau3h[i];
+        }
+        for (int i = 0; i < nr; ++i) { s1 += f1[i]; s3 += f3[i]; p1[i] = f1[i]; p3[i] = f3[i]; }
+        ok = he_solve(p, rhs, tab, nr, f1, f3, ytmp, &nfe, &nst, &nje);
+        if (!ok) {
+          if (p.method == PW_HE_ODEINT) {
+            status = PW_WARN_HE_RELAX;  // helium.py:736 is outside the warnings->error guard
+          } else {
+            status = PW_FAIL_HE_SOLVER;  // solve_ivp returned a short array -> shape error downstream
+            break;
+          }
+        }
+        clamp();
+        double d1 = 0.0, d3 = 0.0;
+        for (int i = 0; i < nr; ++i) { d1 += f1[i] - p1[i]; d3 += f3[i] - p3[i]; }
+        const double rel1 = fabs(d1) / s1, rel3 = fabs(d3) / s3;
+        if (rel1 < p.convergence && rel3 < p.convergence) break;
+      }
+    }
+  }
+  if (status == PW_FAIL_HE_SOLVER) {
+    const double nan_ = nan("");
+    for (int i = 0; i < nr; ++i) { f1[i] = nan_; f3[i] = nan_; }
+  } else if (out.rates) {
+    // _fun(r, [f_1_r, f_3_r], rates=True) * phi_unit  (:770-773, :684-686)
+    for (int i = 0; i < nr; ++i) {
+      double y[2] = {f1[i], f3[i]}, t[11];
+      rhs.coeffs(w.rn[i]);
+      rhs.eval(y, nullptr, t);
+      for (int k = 0; k < 11; ++k) out.rates[k * nr + i] = t[k] * phi_unit;
+    }
+  }
+  out.scal[0] = (double)n_relax; out.scal[1] = (double)nfe; out.scal[2] = (double)nst; out.scal[3] = (double)nje;
+  *out.status = status;
+}
+
+}  // namespace pw

@@ -1,0 +1,244 @@
+// pw_hydrogen.cuh -- H+ fraction profile of one model, evaluated by one CTA
+// (reference: p_winds/hydrogen.py:227-573 `ion_fraction`, :22-114
+// `radiative_processes_exact`).
+//
+// Data-parallel pieces (Parker structure over radii, the Nr x N_lambda
+// photoionisation integrals) are spread over the CTA; the adaptive RK45 solve and
+// the five mu-bar quadratures are inherently serial and run on thread 0 while the
+// other warps wait at the barrier.
+#pragma once
+#include "pw_common.cuh"
+#include "pw_parker.cuh"
+#include "pw_rk45.cuh"
+#include "pw_sed.cuh"
+
+namespace pw {
+
+struct HParams {
+  // per model
+  double T, mdot, h_fraction, mu0;
+  // per batch
+  double r_pl, m_pl, m_star, a_au;
+  double initial_f_ion, convergence;
+  int max_n_relax, relax, exact_phi;
+  double phi_abs, a0;   // used when !exact_phi: hydrogen.radiative_processes[_mono] scalars
+  Rk45Opts ivp;
+  // the Parker structure handed to the helium stage uses parker.structure
+  // (plain) or parker.structure_tidal (docs/source/tidal_effects.ipynb)
+  int out_tidal;
+};
+
+// Shared-memory work arrays of one CTA, Nr doubles each.
+struct HWork {
+  double *rn, *v, *rho, *phi, *tau, *f, *fprev, *colh, *colhe, *rcm;
+  double* red;  // 40 doubles: block reduction scratch + broadcast slots
+};
+
+struct HOut {
+  double* f_r;     // [Nr]
+  double* v;       // [Nr] final structure for the helium stage (sonic units)
+  double* rho;     // [Nr]
+  double* scal;    // [8]: mu_bar, vs, rs, rhos, n_relax, nfev_total, n_solves, -
+  int* status;
+};
+
+#if defined(__CUDA_ARCH__)
+#define PW_LANE ((int)(threadIdx.x & 31))
+#define PW_WARP ((int)(threadIdx.x >> 5))
+#define PW_NWARP ((int)(blockDim.x >> 5))
+#define PW_NLANE 32
+#else
+#define PW_LANE 0
+#define PW_WARP 0
+#define PW_NWARP 1
+#define PW_NLANE 1
+#endif
+
+// hydrogen.radiative_processes_exact for all radii; f_h == nullptr means the
+// scalar f_h_r = 0.0 of the first pass (hydrogen.py:359-363).
+PW_HD void phi_exact(const SedTables& t, const HWork& w, int nr, const double* rho_abs_scale,
+                     double rhos, const double* f_h, double h_fraction) {
+  const double he_to_h = (1 - h_fraction) / h_fraction;
+  // number densities (hydrogen.py:84-94); staged in tau/phi as scratch
+  double* n_h = w.tau;
+  double* n_he = w.phi;
+  for (int i = PW_TID; i < nr; i += PW_NT) {
+    const double f = f_h ? f_h[i] : 0.0;
+    const double rho = rho_abs_scale[i] * rhos;
+    const double mu = (1 + 4 * he_to_h) / (1 + f + he_to_h);
+    const double n_tot = rho / mu / kMH;
+    const double n_htot = 1 / (1 + f + he_to_h) * n_tot;
+    n_h[i] = n_htot * (1 - f);
+    n_he[i] = (n_htot * he_to_h) * (1 - f);
+  }
+  PW_SYNC();
+  // column densities: cumulative_trapezoid on the reversed arrays, sign flipped
+  // (hydrogen.py:96-106); sequential like numpy.cumsum
+  if (PW_TID == 0) {
+    double ch = 0.0, che = 0.0;
+    w.colh[nr - 1] = 0.0;
+    w.colhe[nr - 1] = 0.0;
+    for (int i = nr - 2; i >= 0; --i) {
+      const double d = w.rcm[i] - w.rcm[i + 1];
+      ch += d * (n_h[i] + n_h[i + 1]) / 2.0;
+      che += d * (n_he[i] + n_he[i + 1]) / 2.0;
+      w.colh[i] = -ch;
+      w.colhe[i] = -che;
+    }
+  }
+  PW_SYNC();
+  // phi'(r_i) = | sum_j w_j F_j sigma_j / E_j exp(-tau_ij) |  (hydrogen.py:111-112):
+  // one warp per radius, lanes over wavelength bins, shuffle-tree reduction
+  for (int i = PW_WARP; i < nr; i += PW_NWARP) {
+    const double ch = w.colh[i], che = w.colhe[i];
+    double acc = 0.0;
+    for (int j = PW_LANE; j < t.n_h; j += PW_NLANE) {
+      const double tau = ch * t.s_h[j] + che * t.s_he[j];
+      acc += t.gw[j] * exp(-tau);
+    }
+    acc = warp_sum(acc);
+    if (PW_LANE == 0) w.phi[i] = fabs(acc);
+  }
+  PW_SYNC();
+}
+
+struct HRhs {
+  const double *rn, *phi, *v, *rho, *tau;
+  int n, exact, hint;
+  double k2, phi0;
+  // hydrogen.py:431-448
+  PW_HD void operator()(double x, const double* y, double* dydx) {
+    const int j = bracket(rn, n, x, hint);
+    hint = j;
+    double pp;
+    if (exact) pp = np_interp_at(rn, phi, n, x, j);
+    else pp = exp(-np_interp_at(rn, tau, n, x, j)) * phi0;
+    const double v_ = np_interp_at(rn, v, n, x, j);
+    const double rho_ = np_interp_at(rn, rho, n, x, j);
+    const double f = y[0];
+    const double term1 = (1. - f) / v_ * pp;
+    const double term2 = k2 * rho_ * (f * f) / v_;
+    dydx[0] = term1 - term2;
+  }
+};
+
+// One model, one CTA.  `r` is the radius profile in planetary radii (global).
+PW_HD void h_ion_fraction_model(const HParams& p, const SedTables& sed, const double* __restrict__ r,
+                                int nr, const HWork& w, const HOut& out) {
+  const double alpha_rec = 2.59E-13 * pow(p.T / 1E4, -0.7);  // hydrogen.py:207-223
+  const double he_fraction = 1 - p.h_fraction;
+  const double he_h = he_fraction / p.h_fraction;
+  const double a_0 = p.exact_phi ? 0. : p.a0;
+  const double k1_abs = p.h_fraction * a_0 / (p.h_fraction + 4 * he_fraction) / kMH;
+  const double k2_abs = p.h_fraction / (p.h_fraction + 4 * he_fraction) * alpha_rec / kMH;
+
+  for (int i = PW_TID; i < nr; i += PW_NT)
+    w.rcm[i] = r[i] * p.r_pl * (7.1492e7 / 1e-2);  // (r * R_pl * u.Rjup).to(u.cm)
+
+  double mu = p.mu0;
+  double vs_amw = sound_speed(p.T, p.mu0);  // `vs` of hydrogen.py:351, rebound at :480 only if exact
+  double mu_bar = 0.0;
+  int n_relax = 0, nfev_total = 0, n_solves = 0, status = PW_OK;
+  const int n_pass = p.relax ? p.max_n_relax + 1 : 1;
+
+  for (int pass = 0; pass < n_pass; ++pass) {
+    // ---- _normalize(phi_abs, k1_abs, k2_abs, r, mu)  (hydrogen.py:387-412)
+    const double vs = sound_speed(p.T, mu);
+    const double rs = radius_sonic_point_tidal(p.m_pl, vs, p.m_star, p.a_au);
+    const double rhos = density_sonic_point(p.mdot, rs, vs);
+    if (p.exact_phi) vs_amw = vs;
+    const double phi_unit = vs * 1E5 / rs / 7.1492E+09;
+    const double k1_unit = 1 / (rhos * rs * 7.1492E+09);
+    const double k2_unit = vs * 1E5 / rs / 7.1492E+09 / rhos;
+    const double k1 = k1_abs / k1_unit, k2 = k2_abs / k2_unit;
+    const TidalCoef tc = tidal_coef(vs, rs, p.m_pl, p.m_star, p.a_au);
+    for (int i = PW_TID; i < nr; i += PW_NT) {
+      const double x = r[i] * p.r_pl / rs;
+      w.rn[i] = x;
+      parker_point_tidal(tc, x, &w.v[i], &w.rho[i]);
+    }
+    PW_SYNC();
+    if (p.exact_phi) {
+      // hydrogen.py:355-363 (pass 0, f = 0) and :480-490 (relax passes, f = f_r)
+      phi_exact(sed, w, nr, w.rho, rhos, pass == 0 ? nullptr : w.f, p.h_fraction);
+      for (int i = PW_TID; i < nr; i += PW_NT) w.phi[i] = w.phi[i] / phi_unit;
+    } else if (PW_TID == 0) {
+      // rectangle-rule column density, local cell included (hydrogen.py:424-425, :499-501)
+      double c = 0.0;
+      for (int i = nr - 1; i >= 0; --i) {
+        const double dr = (i < nr - 1) ? (w.rn[i + 1] - w.rn[i]) : (w.rn[nr - 1] - w.rn[nr - 2]);
+        const double wgt = (pass == 0) ? dr * w.rho[i] : dr * w.rho[i] * (1 - w.f[i]);
+        c += wgt;
+        w.tau[i] = k1 * c;
+      }
+    }
+    PW_SYNC();
+    // ---- solve_ivp(_fun, (r[0], r[-1]), [initial_f_ion], t_eval=r)  (:451, :504)
+    if (PW_TID == 0) {
+      for (int i = 0; i < nr; ++i) w.fprev[i] = w.f[i];
+      HRhs rhs{w.rn, w.phi, w.v, w.rho, w.tau, nr, p.exact_phi, 0, k2, p.phi_abs / phi_unit};
+      Rk45Stats st{0, 0, 0};
+      const double y0 = p.initial_f_ion;
+      const int got = rk45_solve<1>(rhs, w.rn, nr, &y0, p.ivp, w.f, &st);
+      nfev_total += st.nfev;
+      ++n_solves;
+      int flag = 0;  // 0 continue relaxing, 1 converged/stop, 2 failed
+      if (got != nr) {
+        flag = 2;  // len(f_r) != len(r) -> RuntimeError (:458-460, :511-513)
+      } else {
+        mu_bar = average_molecular_weight(w.f, r, p.r_pl, w.v, vs_amw, nr, p.m_pl, p.T, he_h);
+        if (pass > 0) {
+          double sd = 0.0, sp = 0.0;
+          for (int i = 0; i < nr; ++i) { sd += w.f[i] - w.fprev[i]; sp += w.fprev[i]; }
+          if (fabs(sd / sp) < p.convergence) flag = 1;
+        }
+      }
+      w.red[34] = (double)flag;
+      w.red[35] = mu_bar;
+      w.red[36] = (double)nfev_total;
+      w.red[37] = (double)n_solves;
+    }
+    PW_SYNC();
+    const int flag = (int)w.red[34];
+    mu_bar = w.red[35];
+    nfev_total = (int)w.red[36];
+    n_solves = (int)w.red[37];
+    PW_SYNC();
+    if (pass > 0) n_relax = pass;
+    if (flag == 2) { status = PW_FAIL_H_SOLVER; break; }
+    if (flag == 1) break;
+    mu = mu_bar;
+  }
+
+  // ---- outputs + the structure the helium stage needs (quickstart.ipynb cell 7)
+  const double vs_f = sound_speed(p.T, mu_bar);
+  double rs_f, rhos_f;
+  if (status == PW_OK && !(mu_bar == mu_bar)) status = PW_FAIL_NAN;
+  if (p.out_tidal) rs_f = radius_sonic_point_tidal(p.m_pl, vs_f, p.m_star, p.a_au);
+  else rs_f = radius_sonic_point(p.m_pl, vs_f);
+  rhos_f = density_sonic_point(p.mdot, rs_f, vs_f);
+  const TidalCoef tcf = tidal_coef(vs_f, rs_f, p.m_pl, p.m_star, p.a_au);
+  const double nan_ = nan("");
+  for (int i = PW_TID; i < nr; i += PW_NT) {
+    if (status == PW_OK) {
+      const double x = r[i] * p.r_pl / rs_f;
+      double vv, rr;
+      if (p.out_tidal) parker_point_tidal(tcf, x, &vv, &rr);
+      else parker_point(x, &vv, &rr);
+      out.f_r[i] = w.f[i];
+      out.v[i] = vv;
+      out.rho[i] = rr;
+    } else {
+      out.f_r[i] = nan_; out.v[i] = nan_; out.rho[i] = nan_;
+    }
+  }
+  if (PW_TID == 0) {
+    out.scal[0] = (status == PW_OK) ? mu_bar : nan_;
+    out.scal[1] = vs_f; out.scal[2] = rs_f; out.scal[3] = rhos_f;
+    out.scal[4] = (double)n_relax; out.scal[5] = (double)nfev_total; out.scal[6] = (double)n_solves;
+    out.scal[7] = 0.0;
+    *out.status = status;
+  }
+}
+
+}  // namespace pw

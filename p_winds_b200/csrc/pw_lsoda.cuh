@@ -1,0 +1,704 @@
+// pw_lsoda.cuh -- LSODA (Petzold & Hindmarsh, ODEPACK) restated for small systems,
+// used where the reference calls `scipy.integrate.odeint` (helium.py:694, :736).
+//
+// scipy's odeint drives ODEPACK's LSODA (scipy/integrate/_odepack: lsoda, stoda,
+// cfode, prja, solsy, intdy, ewset, vmnorm, fnorm) with itask = 1, itol = 1,
+// rtol = atol = 1.49012e-8, jt = 2 (internally generated full Jacobian),
+// mxstep = 500, mxordn = 12, mxords = 5, h0 = hmax = hmin = 0.  No LSODA source
+// exists in this image (only scipy's compiled extension), so this is a
+// restatement of the published algorithm: Nordsieck history array, variable-order
+// Adams (1..12) / BDF (1..5) with automatic stiffness switching, chord iteration
+// with a finite-difference Jacobian, step/order selection from the three error
+// estimates, output by interpolation (intdy).  tests/test_hostsim_lsoda.py holds
+// the host build to scipy's own `odeint(full_output=True)` step/feval/jacobian
+// counters and to its solution on the anchor models.
+#pragma once
+#include "pw_common.cuh"
+
+namespace pw {
+
+constexpr int kLsodaMaxOrdN = 12;  // Adams
+constexpr int kLsodaMaxOrdS = 5;   // BDF
+
+// Method coefficients (ODEPACK cfode): elco[meth][nq][i], tesco[meth][nq][k], 1-based.
+struct LsodaTables {
+  double elco[2][13][14];
+  double tesco[2][13][4];
+  double cm1[13], cm2[6];
+};
+
+PW_HD void lsoda_tables_init(LsodaTables* t) {
+  for (int m = 0; m < 2; ++m)
+    for (int a = 0; a < 13; ++a) {
+      for (int b = 0; b < 14; ++b) t->elco[m][a][b] = 0.0;
+      for (int b = 0; b < 4; ++b) t->tesco[m][a][b] = 0.0;
+    }
+  double pc[13];
+  {  // meth = 1: Adams-Moulton, orders 1..12
+    double (*elco)[14] = t->elco[0];
+    double (*tesco)[4] = t->tesco[0];
+    elco[1][1] = 1.; elco[1][2] = 1.;
+    tesco[1][1] = 0.; tesco[1][2] = 2.; tesco[2][1] = 1.; tesco[12][3] = 0.;
+    pc[1] = 1.;
+    double rqfac = 1.;
+    for (int nq = 2; nq <= 12; ++nq) {
+      const double rq1fac = rqfac;
+      rqfac = rqfac / (double)nq;
+      const int nqm1 = nq - 1, nqp1 = nq + 1;
+      const double fnqm1 = (double)nqm1;
+      pc[nq] = 0.;
+      for (int i = nq; i >= 2; --i) pc[i] = pc[i - 1] + fnqm1 * pc[i];
+      pc[1] = fnqm1 * pc[1];
+      double pint = pc[1], xpin = pc[1] / 2., tsign = 1.;
+      for (int i = 2; i <= nq; ++i) {
+        tsign = -tsign;
+        pint += tsign * pc[i] / (double)i;
+        xpin += tsign * pc[i] / (double)(i + 1);
+      }
+      elco[nq][1] = pint * rq1fac;
+      elco[nq][2] = 1.;
+      for (int i = 2; i <= nq; ++i) elco[nq][i + 1] = rq1fac * pc[i] / (double)i;
+      const double agamq = rqfac * xpin;
+      const double ragq = 1. / agamq;
+      tesco[nq][2] = ragq;
+      if (nq < 12) tesco[nqp1][1] = ragq * rqfac / (double)nqp1;
+      tesco[nqm1][3] = ragq;
+    }
+  }
+  {  // meth = 2: BDF, orders 1..5
+    double (*elco)[14] = t->elco[1];
+    double (*tesco)[4] = t->tesco[1];
+    pc[1] = 1.;
+    double rq1fac = 1.;
+    for (int nq = 1; nq <= 5; ++nq) {
+      const double fnq = (double)nq;
+      const int nqp1 = nq + 1;
+      pc[nqp1] = 0.;
+      for (int i = nq + 1; i >= 2; --i) pc[i] = pc[i - 1] + fnq * pc[i];
+      pc[1] *= fnq;
+      for (int i = 1; i <= nqp1; ++i) elco[nq][i] = pc[i] / pc[2];
+      elco[nq][2] = 1.;
+      tesco[nq][1] = rq1fac;
+      tesco[nq][2] = ((double)nqp1) / elco[nq][1];
+      tesco[nq][3] = ((double)(nq + 2)) / elco[nq][1];
+      rq1fac /= fnq;
+    }
+  }
+  for (int i = 1; i <= 5; ++i) t->cm2[i] = t->tesco[1][i][2] * t->elco[1][i][i + 1];
+  for (int i = 1; i <= 12; ++i) t->cm1[i] = t->tesco[0][i][2] * t->elco[0][i][i + 1];
+}
+
+struct LsodaOpts {
+  double rtol, atol;
+  int mxstep;   // per output interval (odeint default 500)
+  double hmax;  // <= 0: none
+  double h0;    // <= 0: automatic
+};
+
+// istate values on return from call(): 2 ok, < 0 failure (ODEPACK numbering)
+//  -1 excess work (mxstep), -2 excess accuracy, -3 illegal input, -4 repeated
+//  error-test failures, -5 repeated convergence failures, -6 ewt <= 0
+template <int N, class RHS>
+struct Lsoda {
+  RHS& f;
+  const LsodaTables& tab;
+  LsodaOpts o;
+  // Nordsieck array: yh[j][i], j = 1..lmax (+1 scratch column)
+  double yh[kLsodaMaxOrdN + 3][N];
+  double y[N], ewt[N], savf[N], acor[N];
+  double wm[N][N];
+  int ipvt[N];
+  double el[kLsodaMaxOrdN + 2];
+  double tn, h, hu, hold, rc, el0, crate, conit, rmax, pdnorm, pdest, pdlast, ratio, hmxi, tsw;
+  int nq, l, lmax, meth, mused, meth_tab, miter, jtyp, maxord, mxordn, mxords;
+  int ialth, ipup, nslp, icount, irflag, jstart, kflag, jcur, ierpj, iersl;
+  int nst, nfe, nje, nqu, nslast, nhnil;
+  bool started;
+
+  PW_HD Lsoda(RHS& f_, const LsodaTables& t_, const LsodaOpts& o_) : f(f_), tab(t_), o(o_), started(false) {}
+
+  PW_HD double vmnorm(const double* v) const {
+    double vm = 0.0;
+    for (int i = 0; i < N; ++i) vm = fmax(vm, fabs(v[i]) * ewt[i]);
+    return vm;
+  }
+  PW_HD bool ewset(const double* yc) {
+    for (int i = 0; i < N; ++i) {
+      const double e = o.rtol * fabs(yc[i]) + o.atol;
+      if (!(e > 0.0)) return false;
+      ewt[i] = 1.0 / e;
+    }
+    return true;
+  }
+  // ODEPACK keeps ONE elco/tesco table in common storage and reloads it (cfode) only when
+  // stoda is re-entered with jstart = -1 after a method switch; until then the old
+  // method's coefficients stay in force (e.g. tesco(2,nqu) at label 700).
+  PW_HD double elco(int q, int i) const { return tab.elco[meth_tab - 1][q][i]; }
+  PW_HD double tesco(int q, int k) const { return tab.tesco[meth_tab - 1][q][k]; }
+  PW_HD static double sm1(int q) {
+    const double s[13] = {0., 0.5, 0.575, 0.55, 0.45, 0.35, 0.25, 0.2, 0.15, 0.1, 0.075, 0.05, 0.025};
+    return s[q];
+  }
+
+  PW_HD void resetcoeff() {  // stoda label 150
+    for (int i = 1; i <= l; ++i) el[i] = elco(nq, i);
+    rc = rc * el[1] / el0;
+    el0 = el[1];
+    conit = 0.5 / (double)(nq + 2);
+  }
+  PW_HD void scaleh(double* rh, double* pdh) {  // stoda labels 175-180
+    *rh = fmin(*rh, rmax);
+    *rh = *rh / fmax(1., fabs(h) * hmxi * (*rh));
+    if (meth == 1) {
+      irflag = 0;
+      *pdh = fmax(fabs(h) * pdlast, 0.000001);
+      if ((*rh * *pdh * 1.00001) >= sm1(nq)) {
+        *rh = sm1(nq) / *pdh;
+        irflag = 1;
+      }
+    }
+    double r = 1.;
+    for (int j = 2; j <= l; ++j) {
+      r *= *rh;
+      for (int i = 0; i < N; ++i) yh[j][i] *= r;
+    }
+    h *= *rh;
+    rc *= *rh;
+    ialth = l;
+  }
+  PW_HD void predict() {
+    for (int j = nq; j >= 1; --j)
+      for (int i1 = j; i1 <= nq; ++i1)
+        for (int i = 0; i < N; ++i) yh[i1][i] += yh[i1 + 1][i];
+  }
+  PW_HD void retract() {
+    for (int j = nq; j >= 1; --j)
+      for (int i1 = j; i1 <= nq; ++i1)
+        for (int i = 0; i < N; ++i) yh[i1][i] -= yh[i1 + 1][i];
+  }
+
+  // prja, miter = 2: finite-difference Jacobian, P = I - h*el0*J, LU (dgefa)
+  PW_HD void prja() {
+    ++nje;
+    ierpj = 0;
+    jcur = 1;
+    const double hl0 = h * el0;
+    double fac = vmnorm(savf);
+    double r0 = 1000. * fabs(h) * kEps * ((double)N) * fac;
+    if (r0 == 0.) r0 = 1.;
+    const double srur = sqrt(kEps);
+    double ftem[N];
+    for (int j = 0; j < N; ++j) {
+      const double yj = y[j];
+      const double r = fmax(srur * fabs(yj), r0 / ewt[j]);
+      y[j] += r;
+      fac = -hl0 / r;
+      f(tn, y, ftem);
+      for (int i = 0; i < N; ++i) wm[i][j] = (ftem[i] - savf[i]) * fac;
+      y[j] = yj;
+    }
+    nfe += N;
+    // pdnorm = fnorm(wm, ewt) / |hl0| ; fnorm = max_i w_i sum_j |a_ij| / w_j
+    double an = 0.;
+    for (int i = 0; i < N; ++i) {
+      double sum = 0.;
+      for (int j = 0; j < N; ++j) sum += fabs(wm[i][j]) / ewt[j];
+      an = fmax(an, sum * ewt[i]);
+    }
+    pdnorm = an / fabs(hl0);
+    for (int i = 0; i < N; ++i) wm[i][i] += 1.;
+    // dgefa: Gaussian elimination with partial pivoting, multipliers stored negated
+    for (int k = 0; k < N - 1; ++k) {
+      int lp = k;
+      double amax = fabs(wm[k][k]);
+      for (int i = k + 1; i < N; ++i)
+        if (fabs(wm[i][k]) > amax) { amax = fabs(wm[i][k]); lp = i; }
+      ipvt[k] = lp;
+      if (wm[lp][k] == 0.) { ierpj = 1; continue; }
+      if (lp != k) { const double t = wm[lp][k]; wm[lp][k] = wm[k][k]; wm[k][k] = t; }
+      const double t = -1. / wm[k][k];
+      for (int i = k + 1; i < N; ++i) wm[i][k] *= t;
+      for (int j = k + 1; j < N; ++j) {
+        double tj = wm[lp][j];
+        if (lp != k) { wm[lp][j] = wm[k][j]; wm[k][j] = tj; }
+        for (int i = k + 1; i < N; ++i) wm[i][j] += tj * wm[i][k];
+      }
+    }
+    ipvt[N - 1] = N - 1;
+    if (wm[N - 1][N - 1] == 0.) ierpj = 1;
+  }
+  // solsy -> dgesl (job = 0)
+  PW_HD void solsy(double* b) {
+    iersl = 0;
+    for (int k = 0; k < N - 1; ++k) {
+      const int lp = ipvt[k];
+      double t = b[lp];
+      if (lp != k) { b[lp] = b[k]; b[k] = t; }
+      for (int i = k + 1; i < N; ++i) b[i] += t * wm[i][k];
+    }
+    for (int kb = 0; kb < N; ++kb) {
+      const int k = N - 1 - kb;
+      b[k] /= wm[k][k];
+      const double t = -b[k];
+      for (int i = 0; i < k; ++i) b[i] += t * wm[i][k];
+    }
+  }
+
+  // stoda corrector loop (labels 220-450).  Returns corflag: 0 converged,
+  // 1 retry with smaller h (rh set), 2 give up (kflag = -2).
+  PW_HD int correction(double pnorm, double* del_out, double told, int* ncf, double* rh, int* m_out) {
+    int m = 0;
+    double rate = 0., del = 0., delp = 0.;
+    for (int i = 0; i < N; ++i) y[i] = yh[1][i];
+    f(tn, y, savf);
+    ++nfe;
+    for (;;) {
+      if (m == 0) {
+        if (ipup > 0) {
+          prja();
+          ipup = 0;
+          rc = 1.;
+          nslp = nst;
+          crate = 0.7;
+          if (ierpj != 0) return corfailure(told, ncf, rh);
+        }
+        for (int i = 0; i < N; ++i) acor[i] = 0.;
+      }
+      if (miter == 0) {
+        for (int i = 0; i < N; ++i) {
+          savf[i] = h * savf[i] - yh[2][i];
+          y[i] = savf[i] - acor[i];
+        }
+        del = vmnorm(y);
+        for (int i = 0; i < N; ++i) {
+          y[i] = yh[1][i] + el[1] * savf[i];
+          acor[i] = savf[i];
+        }
+      } else {
+        for (int i = 0; i < N; ++i) y[i] = h * savf[i] - (yh[2][i] + acor[i]);
+        solsy(y);
+        del = vmnorm(y);
+        for (int i = 0; i < N; ++i) {
+          acor[i] += y[i];
+          y[i] = yh[1][i] + el[1] * acor[i];
+        }
+      }
+      // convergence test (label 400)
+      bool conv = false;
+      if (del <= 100. * pnorm * kEps) {
+        conv = true;
+      } else if (m != 0 || meth != 1) {
+        if (m != 0) {
+          double rm = 1024.;
+          if (del <= (1024. * delp)) rm = del / delp;
+          rate = fmax(rate, rm);
+          crate = fmax(0.2 * crate, rm);
+        }
+        const double dcon = del * fmin(1., 1.5 * crate) / (tesco(nq, 2) * conit);
+        if (dcon <= 1.) {
+          pdest = fmax(pdest, rate / fabs(h * el[1]));
+          if (pdest != 0.) pdlast = pdest;
+          conv = true;
+        }
+      }
+      if (conv) { *del_out = del; *m_out = m; return 0; }
+      ++m;
+      if (m == 3 /*maxcor*/ || (m >= 2 && del > 2. * delp)) {
+        if (miter == 0 || jcur == 1) return corfailure(told, ncf, rh);
+        ipup = miter;
+        // restart the corrector with a fresh Jacobian (label 220)
+        m = 0; rate = 0.; del = 0.;
+        for (int i = 0; i < N; ++i) y[i] = yh[1][i];
+        f(tn, y, savf);
+        ++nfe;
+      } else {
+        delp = del;
+        f(tn, y, savf);
+        ++nfe;
+      }
+    }
+  }
+  PW_HD int corfailure(double told, int* ncf, double* rh) {  // label 430
+    ++(*ncf);
+    rmax = 2.;
+    tn = told;
+    retract();
+    if (fabs(h) <= 0.0 /*hmin*/ * 1.00001 || *ncf == 10 /*mxncf*/) return 2;
+    *rh = 0.25;
+    ipup = miter;
+    return 1;
+  }
+
+  PW_HD void methodswitch(double dsm, double pnorm, double* pdh, double* rh) {
+    if (meth == 1) {
+      int nqm2;
+      double rh2;
+      if (nq > 5) return;
+      if (dsm <= (100. * pnorm * kEps) || pdest == 0.) {
+        if (irflag == 0) return;
+        rh2 = 2.;
+        nqm2 = nq < mxords ? nq : mxords;
+      } else {
+        const double exsm = 1. / (double)l;
+        double rh1 = 1. / (1.2 * pow(dsm, exsm) + 0.0000012);
+        double rh1it = 2. * rh1;
+        *pdh = pdlast * fabs(h);
+        if ((*pdh * rh1) > 0.00001) rh1it = sm1(nq) / *pdh;
+        rh1 = fmin(rh1, rh1it);
+        if (nq > mxords) {
+          nqm2 = mxords;
+          const int lm2 = mxords + 1;
+          const double exm2 = 1. / (double)lm2;
+          const double dm2 = vmnorm(yh[lm2 + 1]) / tab.cm2[mxords];
+          rh2 = 1. / (1.2 * pow(dm2, exm2) + 0.0000012);
+        } else {
+          const double dm2 = dsm * (tab.cm1[nq] / tab.cm2[nq]);
+          rh2 = 1. / (1.2 * pow(dm2, exsm) + 0.0000012);
+          nqm2 = nq;
+        }
+        if (rh2 < ratio * rh1) return;
+      }
+      *rh = rh2;
+      icount = 20;
+      meth = 2;
+      miter = jtyp;
+      pdlast = 0.;
+      nq = nqm2;
+      l = nq + 1;
+      return;
+    }
+    // currently BDF: consider Adams
+    const double exsm = 1. / (double)l;
+    int nqm1;
+    double rh1, dm1, exm1;
+    if (mxordn < nq) {
+      nqm1 = mxordn;
+      const int lm1 = mxordn + 1;
+      exm1 = 1. / (double)lm1;
+      dm1 = vmnorm(yh[lm1 + 1]) / tab.cm1[mxordn];
+      rh1 = 1. / (1.2 * pow(dm1, exm1) + 0.0000012);
+    } else {
+      dm1 = dsm * (tab.cm2[nq] / tab.cm1[nq]);
+      rh1 = 1. / (1.2 * pow(dm1, exsm) + 0.0000012);
+      nqm1 = nq;
+      exm1 = exsm;
+    }
+    double rh1it = 2. * rh1;
+    *pdh = pdnorm * fabs(h);
+    if ((*pdh * rh1) > 0.00001) rh1it = sm1(nqm1) / *pdh;
+    rh1 = fmin(rh1, rh1it);
+    const double rh2 = 1. / (1.2 * pow(dsm, exsm) + 0.0000012);
+    if ((rh1 * ratio) < (5. * rh2)) return;
+    const double alpha = fmax(0.001, rh1);
+    dm1 *= pow(alpha, exm1);
+    if (dm1 <= 1000. * kEps * pnorm) return;
+    *rh = rh1;
+    icount = 20;
+    meth = 1;
+    miter = 0;
+    pdlast = 0.;
+    nq = nqm1;
+    l = nq + 1;
+  }
+
+  // labels 540-630.  orderflag: 0 no change, 1 h changes, 2 h and nq change
+  PW_HD void orderswitch(double rhup, double dsm, double* pdh, double* rh, int* orderflag) {
+    *orderflag = 0;
+    const double exsm = 1. / (double)l;
+    double rhsm = 1. / (1.2 * pow(dsm, exsm) + 0.0000012);
+    double rhdn = 0.;
+    if (nq != 1) {
+      const double ddn = vmnorm(yh[l]) / tesco(nq, 1);
+      const double exdn = 1. / (double)nq;
+      rhdn = 1. / (1.3 * pow(ddn, exdn) + 0.0000013);
+    }
+    if (meth == 1) {
+      *pdh = fmax(fabs(h) * pdlast, 0.000001);
+      if (l < lmax) rhup = fmin(rhup, sm1(l) / *pdh);
+      rhsm = fmin(rhsm, sm1(nq) / *pdh);
+      if (nq > 1) rhdn = fmin(rhdn, sm1(nq - 1) / *pdh);
+      pdest = 0.;
+    }
+    int newq;
+    if (rhsm >= rhup) {
+      if (rhsm >= rhdn) {
+        newq = nq;
+        *rh = rhsm;
+      } else {
+        newq = nq - 1;
+        *rh = rhdn;
+        if (kflag < 0 && *rh > 1.) *rh = 1.;
+      }
+    } else {
+      if (rhup <= rhdn) {
+        newq = nq - 1;
+        *rh = rhdn;
+        if (kflag < 0 && *rh > 1.) *rh = 1.;
+      } else {
+        *rh = rhup;
+        if (*rh >= 1.1) {
+          const double r = el[l] / (double)l;
+          nq = l;
+          l = nq + 1;
+          for (int i = 0; i < N; ++i) yh[l][i] = acor[i] * r;
+          *orderflag = 2;
+          return;
+        }
+        ialth = 3;
+        return;
+      }
+    }
+    if (meth == 1) {
+      if ((*rh * *pdh * 1.00001) < sm1(newq))
+        if (kflag == 0 && *rh < 1.1) { ialth = 3; return; }
+    } else {
+      if (kflag == 0 && *rh < 1.1) { ialth = 3; return; }
+    }
+    if (kflag <= -2) *rh = fmin(*rh, 0.2);
+    if (newq == nq) { *orderflag = 1; return; }
+    nq = newq;
+    l = nq + 1;
+    *orderflag = 2;
+  }
+
+  PW_HD void endstoda() {  // labels 700-720
+    const double r = 1. / tesco(nqu, 2);
+    for (int i = 0; i < N; ++i) acor[i] *= r;
+    hold = h;
+    jstart = 1;
+  }
+
+  // One step of the core integrator (DSTODA).
+  PW_HD void stoda() {
+    kflag = 0;
+    const double told = tn;
+    int ncf = 0;
+    ierpj = 0; iersl = 0; jcur = 0;
+    double rh = 0., pdh = 0., del = 0., dsm = 0.;
+    int m = 0;
+    if (jstart == 0) {
+      lmax = maxord + 1;
+      nq = 1; l = 2; ialth = 2; rmax = 10000.; rc = 0.; el0 = 1.; crate = 0.7;
+      hold = h; nslp = 0; ipup = miter;
+      icount = 20; irflag = 0; pdest = 0.; pdlast = 0.; ratio = 5.;
+      meth_tab = 1;
+      resetcoeff();
+    }
+    if (jstart == -1) {
+      ipup = miter;
+      lmax = maxord + 1;
+      if (ialth == 1) ialth = 2;
+      if (meth != mused) {
+        meth_tab = meth;  // call dcfode(meth, elco, tesco)
+        ialth = l;
+        resetcoeff();
+      }
+      if (h != hold) {
+        rh = h / hold;
+        h = hold;
+        scaleh(&rh, &pdh);
+      }
+    }
+    for (;;) {
+      // prediction + corrector, retried while the corrector fails
+      double pnorm;
+      for (;;) {
+        if (fabs(rc - 1.) > 0.3 /*ccmax*/) ipup = miter;
+        if (nst >= nslp + 20 /*msbp*/) ipup = miter;
+        tn += h;
+        predict();
+        pnorm = vmnorm(yh[1]);
+        const int corflag = correction(pnorm, &del, told, &ncf, &rh, &m);
+        if (corflag == 0) break;
+        if (corflag == 1) {
+          rh = fmax(rh, 0.0 /*hmin*/ / fabs(h));
+          scaleh(&rh, &pdh);
+          continue;
+        }
+        kflag = -2;
+        hold = h;
+        jstart = 1;
+        return;
+      }
+      jcur = 0;
+      if (m == 0) dsm = del / tesco(nq, 2);
+      if (m > 0) dsm = vmnorm(acor) / tesco(nq, 2);
+      if (dsm <= 1.) {
+        // successful step
+        kflag = 0;
+        ++nst;
+        hu = h;
+        nqu = nq;
+        mused = meth;
+        for (int j = 1; j <= l; ++j) {
+          const double r = el[j];
+          for (int i = 0; i < N; ++i) yh[j][i] += r * acor[i];
+        }
+        --icount;
+        if (icount < 0) {
+          methodswitch(dsm, pnorm, &pdh, &rh);
+          if (meth != mused) {
+            rh = fmax(rh, 0.0 / fabs(h));
+            scaleh(&rh, &pdh);
+            rmax = 10.;
+            endstoda();
+            return;
+          }
+        }
+        --ialth;
+        if (ialth == 0) {
+          double rhup = 0.;
+          if (l != lmax) {
+            for (int i = 0; i < N; ++i) savf[i] = acor[i] - yh[lmax][i];
+            const double dup = vmnorm(savf) / tesco(nq, 3);
+            const double exup = 1. / (double)(l + 1);
+            rhup = 1. / (1.4 * pow(dup, exup) + 0.0000014);
+          }
+          int orderflag;
+          orderswitch(rhup, dsm, &pdh, &rh, &orderflag);
+          if (orderflag == 0) { endstoda(); return; }
+          if (orderflag == 2) resetcoeff();
+          rh = fmax(rh, 0.0 / fabs(h));
+          scaleh(&rh, &pdh);
+          rmax = 10.;
+          endstoda();
+          return;
+        }
+        if (ialth > 1 || l == lmax) { endstoda(); return; }
+        for (int i = 0; i < N; ++i) yh[lmax][i] = acor[i];
+        endstoda();
+        return;
+      }
+      // error test failed (label 500)
+      --kflag;
+      tn = told;
+      retract();
+      rmax = 2.;
+      if (fabs(h) <= 0.0 /*hmin*/ * 1.00001) {
+        kflag = -1; hold = h; jstart = 1;
+        return;
+      }
+      if (kflag > -3) {
+        int orderflag;
+        orderswitch(0., dsm, &pdh, &rh, &orderflag);
+        if (orderflag == 0) {
+          // label 610 reached from a failed step: "ialth = 3; go to 700" cannot
+          // happen here because kflag < 0 skips the 10 percent test
+          rh = fmin(rh, 0.2);
+        }
+        if (orderflag == 2) resetcoeff();
+        rh = fmax(rh, 0.0 / fabs(h));
+        scaleh(&rh, &pdh);
+        continue;
+      }
+      // three or more failures: reset to order 1 (label 640)
+      if (kflag == -10) {
+        kflag = -1; hold = h; jstart = 1;
+        return;
+      }
+      rh = 0.1;
+      rh = fmax(0.0 / fabs(h), rh);
+      h *= rh;
+      for (int i = 0; i < N; ++i) y[i] = yh[1][i];
+      f(tn, y, savf);
+      ++nfe;
+      for (int i = 0; i < N; ++i) yh[2][i] = h * savf[i];
+      ipup = miter;
+      ialth = 5;
+      if (nq == 1) continue;
+      nq = 1;
+      l = 2;
+      resetcoeff();
+    }
+  }
+
+  // DINTDY with k = 0
+  PW_HD int intdy(double t, double* dky) const {
+    const double tp = tn - hu - 100. * kEps * copysign(fabs(tn) + fabs(hu), hu);
+    if ((t - tp) * (t - tn) > 0.) return -2;
+    const double s = (t - tn) / h;
+    for (int i = 0; i < N; ++i) dky[i] = yh[l][i];
+    for (int j = nq - 1; j >= 0; --j)
+      for (int i = 0; i < N; ++i) dky[i] = yh[j + 1][i] + s * dky[i];
+    return 0;
+  }
+
+  // One `lsoda(..., itask = 1)` call: advance to tout and interpolate.
+  // First call initialises from (t0, y0).  Returns istate.
+  PW_HD int call(double t0, const double* y0, double tout, double* yout) {
+    if (!started) {
+      started = true;
+      mxordn = kLsodaMaxOrdN; mxords = kLsodaMaxOrdS;
+      hmxi = (o.hmax > 0.) ? 1. / o.hmax : 0.;
+      tn = t0; tsw = t0; maxord = mxordn;
+      jstart = 0; nhnil = 0; nst = 0; nje = 0; nslast = 0; hu = 0.; nqu = 0; mused = 0; miter = 0;
+      meth = 1; jtyp = 2;
+      for (int i = 0; i < N; ++i) { y[i] = y0[i]; yh[1][i] = y0[i]; }
+      f(tn, y, yh[2]);
+      nfe = 1;
+      nq = 1;
+      h = 1.;
+      if (!ewset(yh[1])) return -3;
+      double h0 = o.h0;
+      if (!(h0 > 0.)) {
+        const double tdist = fabs(tout - t0);
+        const double w0 = fmax(fabs(t0), fabs(tout));
+        if (tdist < 2. * kEps * w0) return -3;
+        double tol = o.rtol;
+        if (tol <= 0.)
+          for (int i = 0; i < N; ++i) {
+            const double ayi = fabs(y[i]);
+            if (ayi != 0.) tol = fmax(tol, o.atol / ayi);
+          }
+        tol = fmax(tol, 100. * kEps);
+        tol = fmin(tol, 0.001);
+        double sum = vmnorm(yh[2]);
+        sum = 1. / (tol * w0 * w0) + tol * sum * sum;
+        h0 = 1. / sqrt(sum);
+        h0 = fmin(h0, tdist);
+        h0 = copysign(h0, tout - t0);
+      }
+      const double rh = fabs(h0) * hmxi;
+      if (rh > 1.) h0 /= rh;
+      h = h0;
+      for (int i = 0; i < N; ++i) yh[2][i] *= h0;
+    } else {
+      nslast = nst;
+      if ((tn - tout) * h >= 0.) {
+        if (intdy(tout, yout) != 0) return -3;
+        return 2;
+      }
+    }
+    for (;;) {
+      if (nst != 0 || jstart != 0) {  // label 250 (skipped on the very first pass)
+        if ((nst - nslast) >= o.mxstep) {
+          for (int i = 0; i < N; ++i) yout[i] = yh[1][i];
+          return -1;
+        }
+        if (!ewset(yh[1])) { for (int i = 0; i < N; ++i) yout[i] = yh[1][i]; return -6; }
+      }
+      double tolsf = kEps * vmnorm(yh[1]);
+      if (tolsf > 1.) {
+        for (int i = 0; i < N; ++i) yout[i] = yh[1][i];
+        return (nst == 0) ? -3 : -2;
+      }
+      if ((tn + h) == tn) ++nhnil;
+      stoda();
+      if (kflag == 0) {
+        if (meth != mused) {
+          tsw = tn;
+          maxord = mxordn;
+          if (meth == 2) maxord = mxords;
+          jstart = -1;
+        }
+        if ((tn - tout) * h < 0.) continue;
+        if (intdy(tout, yout) != 0) return -3;
+        return 2;
+      }
+      for (int i = 0; i < N; ++i) yout[i] = yh[1][i];
+      return (kflag == -1) ? -4 : -5;
+    }
+  }
+};
+
+}  // namespace pw
