@@ -1,0 +1,10 @@
+#!/usr/bin/env bash
+# Build the sm_100a engine library in-tree (travels to the GPU box with the snapshot).
+set -euo pipefail
+cd "$(dirname "$0")"
+NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
+OUT=p_winds_b200/libpwinds_b200.so
+$NVCC -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -fmad=false \
+  --expt-relaxed-constexpr --expt-extended-lambda -Xcompiler -fPIC -shared \
+  ${PW_PTXAS_V:+-Xptxas -v} -o $OUT p_winds_b200/csrc/pw_engine.cu
+echo "built $OUT"

@@ -1,0 +1,674 @@
+// pw_engine.cu -- sm_100a kernels and the C ABI (include/pwinds_b200.h) of the
+// p-winds B200 forward-model engine.
+//
+// Kernel map (one retrieval-grid model = one (T0, Mdot, h_fraction) triple):
+//   k_sed_setup     1 CTA       cross-section tables + SED integrals   (per context)
+//   k_hydrogen      1 CTA/model Parker + exact photoionisation + RK45 + relax loop
+//   k_helium        1 thread/model LSODA (Adams/BDF) + relax loop
+//   k_he_density    elementwise  n(He 2^3S) / n(H I) and v in SI for the RT stage
+//   k_rt_los        1 CTA/model LOS projection: column densities + broadening moments
+//   k_rt_sum        (lambda tile, pixel split, model) Voigt + sum_pixels I0 exp(-tau)
+//   k_rt_reduce     deterministic reduction of the pixel splits
+//   k_pixel_table   per geometry: interp1d bracket/weights of every lit pixel
+// No tensor cores: nothing on this path is a dense contraction.
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <algorithm>
+#include <cmath>
+
+#include "../../include/pwinds_b200.h"
+#include "pw_common.cuh"
+#include "pw_parker.cuh"
+#include "pw_sed.cuh"
+#include "pw_rk45.cuh"
+#include "pw_lsoda.cuh"
+#include "pw_hydrogen.cuh"
+#include "pw_helium.cuh"
+#include "pw_transit.cuh"
+
+using namespace pw;
+
+// ------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  int ensure(size_t bytes) {
+    if (bytes <= cap) return 0;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    if (cudaMalloc(&p, bytes) != cudaSuccess) return -1;
+    cap = bytes;
+    return 0;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  template <class T> T* as() const { return (T*)p; }
+};
+
+struct pwb_ctx {
+  int device = 0;
+  int sm_count = 148;
+  std::string err;
+  long long launches = 0;
+  // SED
+  int sed_n = 0, sed_nh = 0;
+  DevBuf sed_gw, sed_sh, sed_she, sed_scal;
+  double sed_scal_host[PW_SC_COUNT] = {0};
+  bool sed_ready = false;
+  // LSODA coefficient tables
+  DevBuf lsoda_tab;
+  // geometry / pixel table
+  int npix = 0, n_active = 0, geo_nr = 0;
+  DevBuf px_lo, px_whi, px_wlo, px_i0, px_meta, geo_r;
+  double geo_s_out = 0.0;
+  bool geo_ready = false;
+  // scratch
+  DevBuf he_work, rt_ncol, rt_sums, rt_partial, fw_f, fw_scal, fw_he, fw_n, fw_v, fw_T, misc;
+};
+
+static int fail(pwb_ctx* c, const char* fmt, const char* a = "") {
+  char buf[512];
+  snprintf(buf, sizeof buf, fmt, a);
+  if (c) c->err = buf;
+  return -1;
+}
+#define PWB_CUDA(c, call)                                                    \
+  do {                                                                       \
+    cudaError_t e_ = (call);                                                 \
+    if (e_ != cudaSuccess) return fail((c), "CUDA error: %s", cudaGetErrorString(e_)); \
+  } while (0)
+
+// ------------------------------------------------------------------------------------
+// kernels
+// ------------------------------------------------------------------------------------
+__global__ void k_sed_setup(const double* __restrict__ wl, const double* __restrict__ flux, int n,
+                            double* gw, double* s_h, double* s_he, double* scalars) {
+  __shared__ double red[40];
+  sed_setup(wl, flux, n, gw, s_h, s_he, scalars, red);
+}
+
+__global__ void k_lsoda_tables(LsodaTables* t) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) lsoda_tables_init(t);
+}
+
+__global__ void k_parker(const double* __restrict__ r, int n, double* v, double* rho) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) parker_point(r[i], &v[i], &rho[i]);
+}
+
+__global__ void k_parker_tidal(const double* __restrict__ r, int n, double cs, double rs, double mp,
+                               double ms, double a, double* v, double* rho) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const TidalCoef c = tidal_coef(cs, rs, mp, ms, a);
+  if (i < n) parker_point_tidal(c, r[i], &v[i], &rho[i]);
+}
+
+// One CTA per model.  Dynamic shared memory: [3*n_h tables (optional)] [10*Nr work] [40 red]
+__global__ void __launch_bounds__(128)
+k_hydrogen(int B, const double* __restrict__ T, const double* __restrict__ mdot,
+           const double* __restrict__ hfrac, const double* __restrict__ mu0,
+           const double* __restrict__ r, int nr, pwb_h_opts o, const double* __restrict__ gw,
+           const double* __restrict__ s_h, const double* __restrict__ s_he, int n_h, int tables_in_smem,
+           double* f_r, double* v, double* rho, double* scal, int* status) {
+  extern __shared__ double smem[];
+  const int b = blockIdx.x;
+  if (b >= B) return;
+  double* base = smem;
+  SedTables t;
+  t.n_h = n_h; t.i1 = 0; t.i0 = 0;
+  if (tables_in_smem) {
+    double* tg = base; double* th = base + n_h; double* the = base + 2 * n_h;
+    for (int j = threadIdx.x; j < n_h; j += blockDim.x) { tg[j] = gw[j]; th[j] = s_h[j]; the[j] = s_he[j]; }
+    t.gw = tg; t.s_h = th; t.s_he = the;
+    base += 3 * n_h;
+  } else {
+    t.gw = gw; t.s_h = s_h; t.s_he = s_he;
+  }
+  HWork w;
+  w.rn = base; w.v = base + nr; w.rho = base + 2 * nr; w.phi = base + 3 * nr; w.tau = base + 4 * nr;
+  w.f = base + 5 * nr; w.fprev = base + 6 * nr; w.colh = base + 7 * nr; w.colhe = base + 8 * nr;
+  w.rcm = base + 9 * nr; w.red = base + 10 * nr;
+  __syncthreads();
+  HParams p;
+  p.T = T[b]; p.mdot = mdot[b]; p.h_fraction = hfrac[b]; p.mu0 = mu0[b];
+  p.r_pl = o.planet_radius; p.m_pl = o.planet_mass; p.m_star = o.star_mass; p.a_au = o.semimajor_axis;
+  p.initial_f_ion = o.initial_f_ion; p.convergence = o.convergence; p.max_n_relax = o.max_n_relax;
+  p.relax = o.relax_solution; p.exact_phi = o.exact_phi; p.phi_abs = o.phi_abs; p.a0 = o.a_0;
+  p.ivp.rtol = o.rtol; p.ivp.atol = o.atol; p.ivp.first_step = o.first_step; p.ivp.max_step = o.max_step;
+  p.out_tidal = o.structure_tidal;
+  HOut out{f_r + (size_t)b * nr, v + (size_t)b * nr, rho + (size_t)b * nr, scal + (size_t)b * 8, status + b};
+  h_ion_fraction_model(p, t, r, nr, w, out);
+}
+
+// One thread per model; `lanes` models share a warp (latency-bound regime: fewer lanes
+// per warp spread the independent serial solves over more warp schedulers).
+__global__ void __launch_bounds__(32)
+k_helium(int B, int lanes, const double* __restrict__ T, const double* __restrict__ hfrac,
+         const double* __restrict__ vs, const double* __restrict__ rs, const double* __restrict__ rhos,
+         int sstride, const double* __restrict__ r, int nr, const double* __restrict__ v,
+         const double* __restrict__ rho, const double* __restrict__ f_h, pwb_he_opts o,
+         const LsodaTables* __restrict__ tab, double* work, double* f1, double* f3, double* scal,
+         double* rates, int* status) {
+  const int lane = threadIdx.x;
+  if (lane >= lanes) return;
+  const int b = blockIdx.x * lanes + lane;
+  if (b >= B) return;
+  if (status[b] != PW_OK) {  // upstream failure: propagate NaNs
+    const double nan_ = nan("");
+    for (int i = 0; i < nr; ++i) { f1[(size_t)b * nr + i] = nan_; f3[(size_t)b * nr + i] = nan_; }
+    for (int k = 0; k < 4; ++k) scal[(size_t)b * 4 + k] = 0.0;
+    return;
+  }
+  HeParams p;
+  p.T = T[b]; p.h_fraction = hfrac[b];
+  p.vs = vs[(size_t)b * sstride]; p.rs = rs[(size_t)b * sstride]; p.rhos = rhos[(size_t)b * sstride];
+  p.r_pl = o.planet_radius; p.y0[0] = o.initial_state[0]; p.y0[1] = o.initial_state[1];
+  p.relax = o.relax_solution; p.max_n_relax = o.max_n_relax; p.convergence = o.convergence;
+  for (int k = 0; k < 6; ++k) p.rates[k] = o.rates[k];
+  p.method = o.method; p.rtol = o.rtol; p.atol = o.atol; p.first_step = o.first_step; p.max_step = o.max_step;
+  double* wb = work + (size_t)b * 10 * nr;
+  HeWork w{wb, wb + nr, wb + 2 * nr, wb + 3 * nr, wb + 4 * nr, wb + 5 * nr};
+  HeOut out{f1 + (size_t)b * nr, f3 + (size_t)b * nr, scal + (size_t)b * 4,
+            rates ? rates + (size_t)b * 11 * nr : nullptr, status + b};
+  he_population_model(p, *tab, r, v + (size_t)b * nr, rho + (size_t)b * nr, f_h + (size_t)b * nr, nr, w, out);
+}
+
+// n [m^-3] and v [m/s] for the RT stage (quickstart.ipynb cells 10-11; SURVEY 8(d) cfg 2)
+__global__ void k_he_density(int B, int nr, int species, const double* __restrict__ hfrac,
+                             const double* __restrict__ hscal, const double* __restrict__ f_r,
+                             const double* __restrict__ f3, const double* __restrict__ rho,
+                             const double* __restrict__ v, const double* __restrict__ T,
+                             double* n_out, double* v_out, double* T_out) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)B * nr) return;
+  const int b = (int)(idx / nr);
+  const double h = hfrac[b], he = 1 - h;
+  const double vs = hscal[(size_t)b * 8 + 1], rhos = hscal[(size_t)b * 8 + 3];
+  double n;
+  if (species == 1) {
+    n = (1 - f_r[idx]) * rho[idx] * rhos * h / (h + 4 * he) / 1.67262192369e-24 * 1E6;
+  } else {
+    const double n_he = rho[idx] * rhos * he / (h + 4 * he) / 1.67262192369e-24;
+    n = (f3[idx] * n_he) * 1E6;
+  }
+  n_out[idx] = n;
+  v_out[idx] = v[idx] * vs * 1000;
+  if (T_out && idx % nr == 0) T_out[b] = T[b];
+}
+
+// Per-geometry pixel table: for every pixel with I0 != 0 and r inside the radius grid,
+// the interp1d bracket and weights; everything else contributes I0 * exp(0).
+// meta[0] = number of active pixels, meta[1] = sum of I0 over the inactive ones.
+__global__ void k_pixel_table(const double* __restrict__ i0, const double* __restrict__ rmap, int npix,
+                              const double* __restrict__ r, int nr, int* lo, double* whi, double* wlo,
+                              double* pi0, double* meta) {
+  __shared__ int s_cnt[1024];
+  __shared__ int s_base;
+  __shared__ double red[40];
+  const int tid = threadIdx.x, nt = blockDim.x;
+  if (tid == 0) s_base = 0;
+  double s_out = 0.0;
+  __syncthreads();
+  for (int start = 0; start < npix; start += nt) {
+    const int p = start + tid;
+    int act = 0;
+    double x = 0, in = 0;
+    if (p < npix) {
+      in = i0[p]; x = rmap[p];
+      const bool inside = !(x < r[0] || x > r[nr - 1]) && (x == x);
+      if (in != 0.0) { if (inside) act = 1; else s_out += in; }
+    }
+    s_cnt[tid] = act;
+    __syncthreads();
+    // inclusive scan (Hillis-Steele), deterministic order = pixel order
+    for (int off = 1; off < nt; off <<= 1) {
+      int vtmp = (tid >= off) ? s_cnt[tid - off] : 0;
+      __syncthreads();
+      s_cnt[tid] += vtmp;
+      __syncthreads();
+    }
+    if (act) {
+      const int q = s_base + s_cnt[tid] - 1;
+      const int hi = interp1d_hi(r, nr, x);
+      const double dx = r[hi] - r[hi - 1];
+      lo[q] = hi - 1;
+      whi[q] = (x - r[hi - 1]) / dx;
+      wlo[q] = (r[hi] - x) / dx;
+      pi0[q] = in;
+    }
+    __syncthreads();
+    if (tid == nt - 1) s_base += s_cnt[tid];
+    __syncthreads();
+  }
+  const double tot = block_sum(s_out, red);
+  if (tid == 0) { meta[0] = (double)s_base; meta[1] = tot; }
+}
+
+__global__ void __launch_bounds__(256)
+k_rt_los(int B, const double* __restrict__ r, const double* __restrict__ n, const double* __restrict__ v,
+         const double* __restrict__ Tprof, int t_is_profile, int nr, int nz, const int* __restrict__ status,
+         double* ncol, double* sums) {
+  extern __shared__ double sm[];  // r, n, v, (T) staged: 4*nr + 40
+  const int b = blockIdx.x;
+  if (b >= B) return;
+  if (status && status[b] != PW_OK && status[b] != PW_WARN_HE_RELAX) return;
+  double* sr = sm; double* sn = sm + nr; double* sv = sm + 2 * nr; double* st = sm + 3 * nr;
+  double* red = sm + 4 * nr;
+  for (int i = threadIdx.x; i < nr; i += blockDim.x) {
+    sr[i] = r[i]; sn[i] = n[(size_t)b * nr + i]; sv[i] = v[(size_t)b * nr + i];
+    st[i] = t_is_profile ? Tprof[(size_t)b * nr + i] : 0.0;
+  }
+  __syncthreads();
+  rt_los_average(sr, sn, sv, t_is_profile ? st : nullptr, nr, nz, ncol + (size_t)b * nr, sums + (size_t)b * 4, red);
+}
+
+// grid = (lambda tiles, pixel splits, B).  Thread <-> wavelength bin; every thread
+// accumulates sum_p I0_p exp(-N_p Phi_lambda) over its split of the active pixels.
+// Pixels are staged through shared memory in chunks with their interpolated column
+// density, so the inner loop is 2 LDS + 1 DMUL + exp + 1 DFMA per (pixel, lambda).
+#define PW_RT_CHUNK 256
+__global__ void __launch_bounds__(256)
+k_rt_sum(int B, int nw, int nr, pwb_rt_opts o, const double* __restrict__ wl, const double* __restrict__ T,
+         const double* __restrict__ ncol, const double* __restrict__ sums, const int* __restrict__ status,
+         const int* __restrict__ px_lo, const double* __restrict__ px_whi, const double* __restrict__ px_wlo,
+         const double* __restrict__ px_i0, const double* __restrict__ meta, int nsplit, double* out /*[B][nsplit][nw]*/,
+         double* tau_out /*[B][nr][nw] or null*/) {
+  __shared__ double s_ncol[1024];
+  __shared__ double s_np[PW_RT_CHUNK], s_i0[PW_RT_CHUNK];
+  const int b = blockIdx.z, split = blockIdx.y;
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;  // wavelength index
+  const bool bad = status && status[b] != PW_OK && status[b] != PW_WARN_HE_RELAX;
+  if (bad) {
+    if (k < nw) out[((size_t)b * nsplit + split) * nw + k] = (split == 0) ? nan("") : 0.0;
+    return;
+  }
+  for (int i = threadIdx.x; i < nr; i += blockDim.x) s_ncol[i] = ncol[(size_t)b * nr + i];
+  // Phase B: Voigt sum for this wavelength ('average' broadening, transit.py:479-513)
+  RtParams p;
+  p.n_lines = o.n_lines;
+  for (int q = 0; q < 8; ++q) { p.w0[q] = o.central_wavelength[q]; p.fosc[q] = o.oscillator_strength[q]; p.aij[q] = o.einstein_coefficient[q]; }
+  p.mass = o.particle_mass; p.v_bulk = o.bulk_los_velocity; p.rv_planet = o.planet_radial_velocity;
+  p.nz = o.z_grid_size; p.turbulence = o.turbulence_broadening; p.t_is_profile = o.temperature_is_profile;
+  const double s_n = sums[(size_t)b * 4], s_v2n = sums[(size_t)b * 4 + 1], s_tn = sums[(size_t)b * 4 + 2];
+  const double vw2 = s_v2n / s_n;
+  const double temp = o.temperature_is_profile ? s_tn / s_n : T[b];
+  double phi = 0.0;
+  if (k < nw) phi = rt_phi_average(p, wl[k], temp, vw2);
+  __syncthreads();
+  if (tau_out && split == 0 && k < nw)
+    for (int i = 0; i < nr; ++i) tau_out[((size_t)b * nr + i) * nw + k] = s_ncol[i] * phi;
+  // Phase C: pixel sum
+  const int n_act = (int)meta[0];
+  const int per = (n_act + nsplit - 1) / nsplit;
+  const int p0 = split * per, p1 = min(n_act, p0 + per);
+  double acc = 0.0;
+  for (int start = p0; start < p1; start += PW_RT_CHUNK) {
+    const int q = start + threadIdx.x;
+    __syncthreads();
+    if (threadIdx.x < PW_RT_CHUNK) {
+      if (q < p1) {
+        const int lo = px_lo[q];
+        s_np[threadIdx.x] = px_whi[q] * s_ncol[lo + 1] + px_wlo[q] * s_ncol[lo];
+        s_i0[threadIdx.x] = px_i0[q];
+      } else {
+        s_np[threadIdx.x] = 0.0; s_i0[threadIdx.x] = 0.0;
+      }
+    }
+    __syncthreads();
+    const int cnt = min(PW_RT_CHUNK, p1 - start);
+#pragma unroll 4
+    for (int j = 0; j < cnt; ++j) acc += s_i0[j] * exp(-(s_np[j] * phi));
+  }
+  if (k < nw) {
+    if (split == 0) acc += meta[1];  // pixels with tau = 0
+    out[((size_t)b * nsplit + split) * nw + k] = acc;
+  }
+}
+
+__global__ void k_rt_reduce(int B, int nw, int nsplit, const double* __restrict__ part, double* spec) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)B * nw) return;
+  const int b = (int)(idx / nw), k = (int)(idx % nw);
+  double s = 0.0;
+  for (int q = 0; q < nsplit; ++q) s += part[((size_t)b * nsplit + q) * nw + k];
+  spec[idx] = s;
+}
+
+__global__ void k_chi2(int B, int nw, const double* __restrict__ spec, const double* __restrict__ data,
+                       const double* __restrict__ sigma, double norm, const int* __restrict__ status,
+                       double* chi2) {
+  __shared__ double red[40];
+  const int b = blockIdx.x;
+  double s = 0.0;
+  for (int k = threadIdx.x; k < nw; k += blockDim.x) {
+    const double d = (data[k] - spec[(size_t)b * nw + k] / norm) / sigma[k];
+    s += d * d;
+  }
+  const double t = block_sum(s, red);
+  if (threadIdx.x == 0) {
+    const bool bad = status && status[b] != PW_OK && status[b] != PW_WARN_HE_RELAX;
+    chi2[b] = bad ? (1.0 / 0.0) : t;
+  }
+}
+
+// FP64 peak probe: 8 independent DFMA chains per thread
+__global__ void k_fp64_peak(double* out, int iters) {
+  double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+  const double m = 1.0000001, c = 1e-9;
+  for (int i = 0; i < iters; ++i) {
+    a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+    a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+// mu_0 = (1 + 4 he/h) / (1 + he/h + mean_f_ion), mean_f_ion = 0 (quickstart.ipynb cell 2)
+__global__ void k_mu0(int B, const double* __restrict__ hfrac, double* mu0) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const double he_h = (1 - hfrac[b]) / hfrac[b];
+  mu0[b] = (1 + 4 * he_h) / (1 + he_h + 0.0);
+}
+
+// ------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------
+extern "C" {
+
+const char* pwb_version(void) { return "p_winds_b200 0.1 (sm_100a)"; }
+
+int pwb_create(int device, pwb_ctx** out) {
+  if (!out) return -1;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return -2;  // no CUDA device: no fallback
+  if (device < 0 || device >= ndev) return -3;
+  if (cudaSetDevice(device) != cudaSuccess) return -4;
+  pwb_ctx* c = new pwb_ctx();
+  c->device = device;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->sm_count = prop.multiProcessorCount;
+  if (c->lsoda_tab.ensure(sizeof(LsodaTables)) != 0) { delete c; return -5; }
+  k_lsoda_tables<<<1, 32>>>(c->lsoda_tab.as<LsodaTables>());
+  c->launches++;
+  if (cudaDeviceSynchronize() != cudaSuccess) { delete c; return -6; }
+  cudaFuncSetAttribute(k_hydrogen, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(k_rt_los, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  *out = c;
+  return 0;
+}
+
+void pwb_destroy(pwb_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  DevBuf* bufs[] = {&c->sed_gw, &c->sed_sh, &c->sed_she, &c->sed_scal, &c->lsoda_tab, &c->px_lo, &c->px_whi,
+                    &c->px_wlo, &c->px_i0, &c->px_meta, &c->geo_r, &c->he_work, &c->rt_ncol, &c->rt_sums,
+                    &c->rt_partial, &c->fw_f, &c->fw_scal, &c->fw_he, &c->fw_n, &c->fw_v, &c->fw_T, &c->misc};
+  for (DevBuf* b : bufs) b->release();
+  delete c;
+}
+
+const char* pwb_last_error(pwb_ctx* c) { return c ? c->err.c_str() : "null context"; }
+long long pwb_launch_count(pwb_ctx* c) { return c ? c->launches : 0; }
+
+int pwb_set_sed(pwb_ctx* c, const double* d_wl, const double* d_flux, int n, void* stream) {
+  if (!c) return -1;
+  if (n < 3 || !d_wl || !d_flux) return fail(c, "pwb_set_sed: need >= 3 spectral points");
+  cudaStream_t s = (cudaStream_t)stream;
+  PWB_CUDA(c, cudaSetDevice(c->device));
+  if (c->sed_gw.ensure(sizeof(double) * n) || c->sed_sh.ensure(sizeof(double) * n) ||
+      c->sed_she.ensure(sizeof(double) * n) || c->sed_scal.ensure(sizeof(double) * PW_SC_COUNT))
+    return fail(c, "pwb_set_sed: out of device memory");
+  k_sed_setup<<<1, 256, 0, s>>>(d_wl, d_flux, n, c->sed_gw.as<double>(), c->sed_sh.as<double>(),
+                               c->sed_she.as<double>(), c->sed_scal.as<double>());
+  c->launches++;
+  PWB_CUDA(c, cudaGetLastError());
+  PWB_CUDA(c, cudaMemcpyAsync(c->sed_scal_host, c->sed_scal.p, sizeof(double) * PW_SC_COUNT,
+                              cudaMemcpyDeviceToHost, s));
+  PWB_CUDA(c, cudaStreamSynchronize(s));
+  c->sed_n = n;
+  c->sed_nh = (int)c->sed_scal_host[PW_SC_N_H];
+  c->sed_ready = true;
+  return 0;
+}
+
+int pwb_get_sed_scalars(pwb_ctx* c, double* out16) {
+  if (!c || !c->sed_ready) return fail(c, "pwb_get_sed_scalars: no SED set");
+  memcpy(out16, c->sed_scal_host, sizeof(double) * PW_SC_COUNT);
+  return 0;
+}
+
+int pwb_parker_structure(pwb_ctx* c, const double* d_r, int n, double* d_v, double* d_rho, void* stream) {
+  if (!c) return -1;
+  if (n <= 0) return 0;
+  k_parker<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(d_r, n, d_v, d_rho);
+  c->launches++;
+  PWB_CUDA(c, cudaGetLastError());
+  return 0;
+}
+
+int pwb_parker_structure_tidal(pwb_ctx* c, const double* d_r, int n, double cs, double rs, double mp,
+                               double ms, double a, double* d_v, double* d_rho, void* stream) {
+  if (!c) return -1;
+  if (n <= 0) return 0;
+  k_parker_tidal<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(d_r, n, cs, rs, mp, ms, a, d_v, d_rho);
+  c->launches++;
+  PWB_CUDA(c, cudaGetLastError());
+  return 0;
+}
+
+int pwb_h_ion_fraction_batch(pwb_ctx* c, int B, const double* d_T, const double* d_mdot,
+                             const double* d_hfrac, const double* d_mu0, const double* d_r, int Nr,
+                             const pwb_h_opts* o, double* d_f_r, double* d_v, double* d_rho,
+                             double* d_scal, int* d_status, void* stream) {
+  if (!c) return -1;
+  if (B <= 0) return 0;
+  if (Nr < 2) return fail(c, "pwb_h_ion_fraction_batch: radius profile needs >= 2 points");
+  if (o->exact_phi && !c->sed_ready) return fail(c, "pwb_h_ion_fraction_batch: exact_phi needs pwb_set_sed");
+  const int n_h = c->sed_ready ? c->sed_nh : 0;
+  size_t work = sizeof(double) * (10 * (size_t)Nr + 40);
+  size_t tab = sizeof(double) * 3 * (size_t)n_h;
+  int in_smem = (o->exact_phi && work + tab <= 160 * 1024) ? 1 : 0;
+  size_t smem = work + (in_smem ? tab : 0);
+  if (smem > 200 * 1024) return fail(c, "pwb_h_ion_fraction_batch: radius profile too long for shared memory");
+  k_hydrogen<<<B, 128, smem, (cudaStream_t)stream>>>(
+      B, d_T, d_mdot, d_hfrac, d_mu0, d_r, Nr, *o, c->sed_gw.as<double>(), c->sed_sh.as<double>(),
+      c->sed_she.as<double>(), n_h, in_smem, d_f_r, d_v, d_rho, d_scal, d_status);
+  c->launches++;
+  PWB_CUDA(c, cudaGetLastError());
+  return 0;
+}
+
+static int he_lanes(pwb_ctx* c, int B) {
+  // spread the independent serial solves over the warp schedulers (4 per SM), a few
+  // warps deep, before packing more models into one warp
+  const long long target_warps = (long long)c->sm_count * 4 * 4;
+  long long lanes = (B + target_warps - 1) / target_warps;
+  if (lanes < 1) lanes = 1;
+  if (lanes > 32) lanes = 32;
+  const char* e = getenv("PWB_HE_LANES");
+  if (e) { int v = atoi(e); if (v >= 1 && v <= 32) lanes = v; }
+  return (int)lanes;
+}
+
+int pwb_he_population_batch(pwb_ctx* c, int B, const double* d_T, const double* d_hfrac,
+                            const double* d_vs, const double* d_rs, const double* d_rhos,
+                            int sstride, const double* d_r, int Nr, const double* d_v,
+                            const double* d_rho, const double* d_f_h, const pwb_he_opts* o,
+                            double* d_f1, double* d_f3, double* d_scal, double* d_rates,
+                            int* d_status, void* stream) {
+  if (!c) return -1;
+  if (B <= 0) return 0;
+  if (Nr < 2) return fail(c, "pwb_he_population_batch: radius profile needs >= 2 points");
+  if (o->method < 0 || o->method > 2) return fail(c, "pwb_he_population_batch: unsupported method");
+  if (c->he_work.ensure(sizeof(double) * 10 * (size_t)Nr * B)) return fail(c, "out of device memory");
+  const int lanes = he_lanes(c, B);
+  const int blocks = (B + lanes - 1) / lanes;
+  k_helium<<<blocks, 32, 0, (cudaStream_t)stream>>>(
+      B, lanes, d_T, d_hfrac, d_vs, d_rs, d_rhos, sstride, d_r, Nr, d_v, d_rho, d_f_h, *o,
+      c->lsoda_tab.as<LsodaTables>(), c->he_work.as<double>(), d_f1, d_f3, d_scal, d_rates, d_status);
+  c->launches++;
+  PWB_CUDA(c, cudaGetLastError());
+  return 0;
+}
+
+int pwb_set_geometry(pwb_ctx* c, const double* d_i0, const double* d_r_map, int npix,
+                     const double* d_r_si, int Nr, void* stream) {
+  if (!c) return -1;
+  if (npix <= 0 || Nr < 2 || Nr > 1024) return fail(c, "pwb_set_geometry: bad sizes (need 2 <= Nr <= 1024)");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (c->px_lo.ensure(sizeof(int) * npix) || c->px_whi.ensure(sizeof(double) * npix) ||
+      c->px_wlo.ensure(sizeof(double) * npix) || c->px_i0.ensure(sizeof(double) * npix) ||
+      c->px_meta.ensure(sizeof(double) * 2) || c->geo_r.ensure(sizeof(double) * Nr))
+    return fail(c, "pwb_set_geometry: out of device memory");
+  PWB_CUDA(c, cudaMemcpyAsync(c->geo_r.p, d_r_si, sizeof(double) * Nr, cudaMemcpyDeviceToDevice, s));
+  k_pixel_table<<<1, 1024, 0, s>>>(d_i0, d_r_map, npix, c->geo_r.as<double>(), Nr, c->px_lo.as<int>(),
+                                   c->px_whi.as<double>(), c->px_wlo.as<double>(), c->px_i0.as<double>(),
+                                   c->px_meta.as<double>());
+  c->launches++;
+  PWB_CUDA(c, cudaGetLastError());
+  double meta[2];
+  PWB_CUDA(c, cudaMemcpyAsync(meta, c->px_meta.p, sizeof meta, cudaMemcpyDeviceToHost, s));
+  PWB_CUDA(c, cudaStreamSynchronize(s));
+  c->npix = npix; c->n_active = (int)meta[0]; c->geo_s_out = meta[1]; c->geo_nr = Nr;
+  c->geo_ready = true;
+  return 0;
+}
+
+int pwb_rt2d_batch(pwb_ctx* c, int B, const double* d_n, const double* d_v, const double* d_T,
+                   const double* d_wl, int Nw, const pwb_rt_opts* o, const int* d_status,
+                   double* d_spectrum, double* d_tau, void* stream) {
+  if (!c) return -1;
+  if (B <= 0) return 0;
+  if (!c->geo_ready) return fail(c, "pwb_rt2d_batch: call pwb_set_geometry first");
+  if (o->n_lines < 1 || o->n_lines > 8) return fail(c, "pwb_rt2d_batch: 1..8 spectral lines supported");
+  if (o->wind_broadening_method != 0)
+    return fail(c, "The chosen ``wind_broadening_method`` is not implemented on the GPU path yet ('average' only).");
+  if (o->z_grid_size < 2) return fail(c, "pwb_rt2d_batch: z_grid_size must be >= 2");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int Nr = c->geo_nr;
+  if (c->rt_ncol.ensure(sizeof(double) * (size_t)B * Nr) || c->rt_sums.ensure(sizeof(double) * (size_t)B * 4))
+    return fail(c, "out of device memory");
+  k_rt_los<<<B, 256, sizeof(double) * (4 * (size_t)Nr + 40), s>>>(
+      B, c->geo_r.as<double>(), d_n, d_v, d_T, o->temperature_is_profile, Nr, o->z_grid_size, d_status,
+      c->rt_ncol.as<double>(), c->rt_sums.as<double>());
+  c->launches++;
+  PWB_CUDA(c, cudaGetLastError());
+  const int tiles = (Nw + 255) / 256;
+  // enough CTAs to fill the machine (>= 4 per SM) when the batch alone does not
+  int nsplit = 1;
+  const long long want = (long long)c->sm_count * 4;
+  if ((long long)B * tiles < want) nsplit = (int)std::min<long long>((want + (long long)B * tiles - 1) / ((long long)B * tiles), 64);
+  if (c->n_active < nsplit * PW_RT_CHUNK) nsplit = std::max(1, c->n_active / PW_RT_CHUNK);
+  double* part = d_spectrum;
+  if (nsplit > 1) {
+    if (c->rt_partial.ensure(sizeof(double) * (size_t)B * nsplit * Nw)) return fail(c, "out of device memory");
+    part = c->rt_partial.as<double>();
+  }
+  dim3 grid(tiles, nsplit, B);
+  k_rt_sum<<<grid, 256, 0, s>>>(B, Nw, Nr, *o, d_wl, d_T, c->rt_ncol.as<double>(), c->rt_sums.as<double>(),
+                                d_status, c->px_lo.as<int>(), c->px_whi.as<double>(), c->px_wlo.as<double>(),
+                                c->px_i0.as<double>(), c->px_meta.as<double>(), nsplit, part, d_tau);
+  c->launches++;
+  PWB_CUDA(c, cudaGetLastError());
+  if (nsplit > 1) {
+    const size_t tot = (size_t)B * Nw;
+    k_rt_reduce<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(B, Nw, nsplit, part, d_spectrum);
+    c->launches++;
+    PWB_CUDA(c, cudaGetLastError());
+  }
+  return 0;
+}
+
+int pwb_forward_batch(pwb_ctx* c, int B, const double* d_T, const double* d_mdot,
+                      const double* d_hfrac, const double* d_r, int Nr, const pwb_h_opts* hopts,
+                      const pwb_he_opts* heopts, const pwb_rt_opts* rtopts, int species,
+                      const double* d_wl, int Nw, double* d_spectrum, double* d_f_r, double* d_f1,
+                      double* d_f3, double* d_v, double* d_rho, double* d_hscal, double* d_hescal,
+                      int* d_status, void* stream) {
+  if (!c) return -1;
+  if (B <= 0) return 0;
+  if (!d_spectrum || !d_status) return fail(c, "pwb_forward_batch: d_spectrum and d_status are required");
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t bn = (size_t)B * Nr;
+  // scratch for outputs the caller did not ask for: f_r, f1, f3, v, rho
+  if (c->fw_f.ensure(sizeof(double) * bn * 6) || c->fw_scal.ensure(sizeof(double) * (size_t)B * 8) ||
+      c->fw_he.ensure(sizeof(double) * (size_t)B * 4) || c->fw_n.ensure(sizeof(double) * bn) ||
+      c->fw_v.ensure(sizeof(double) * bn) || c->fw_T.ensure(sizeof(double) * B))
+    return fail(c, "out of device memory");
+  double* base = c->fw_f.as<double>();
+  double* f_r = d_f_r ? d_f_r : base;
+  double* f1 = d_f1 ? d_f1 : base + bn;
+  double* f3 = d_f3 ? d_f3 : base + 2 * bn;
+  double* v = d_v ? d_v : base + 3 * bn;
+  double* rho = d_rho ? d_rho : base + 4 * bn;
+  double* mu0 = base + 5 * bn;  // [B]
+  double* hscal = d_hscal ? d_hscal : c->fw_scal.as<double>();
+  double* hescal = d_hescal ? d_hescal : c->fw_he.as<double>();
+  // mu_0 of a neutral H/He mix (quickstart.ipynb cell 2)
+  k_mu0<<<(B + 255) / 256, 256, 0, s>>>(B, d_hfrac, mu0);
+  c->launches++;
+  int rc = pwb_h_ion_fraction_batch(c, B, d_T, d_mdot, d_hfrac, mu0, d_r, Nr, hopts, f_r, v, rho, hscal,
+                                    d_status, stream);
+  if (rc) return rc;
+  if (species == 0) {
+    rc = pwb_he_population_batch(c, B, d_T, d_hfrac, hscal + 1, hscal + 2, hscal + 3, 8, d_r, Nr, v, rho, f_r,
+                                 heopts, f1, f3, hescal, nullptr, d_status, stream);
+    if (rc) return rc;
+  }
+  k_he_density<<<(unsigned)((bn + 255) / 256), 256, 0, s>>>(B, Nr, species, d_hfrac, hscal, f_r, f3, rho, v, d_T,
+                                                          c->fw_n.as<double>(), c->fw_v.as<double>(),
+                                                          c->fw_T.as<double>());
+  c->launches++;
+  PWB_CUDA(c, cudaGetLastError());
+  return pwb_rt2d_batch(c, B, c->fw_n.as<double>(), c->fw_v.as<double>(), c->fw_T.as<double>(), d_wl, Nw, rtopts,
+                        d_status, d_spectrum, nullptr, stream);
+}
+
+int pwb_chi2_batch(pwb_ctx* c, int B, const double* d_spectrum, int Nw, const double* d_data,
+                   const double* d_sigma, double norm, const int* d_status, double* d_chi2, void* stream) {
+  if (!c) return -1;
+  if (B <= 0) return 0;
+  k_chi2<<<B, 128, 0, (cudaStream_t)stream>>>(B, Nw, d_spectrum, d_data, d_sigma, norm, d_status, d_chi2);
+  c->launches++;
+  PWB_CUDA(c, cudaGetLastError());
+  return 0;
+}
+
+int pwb_fp64_peak(pwb_ctx* c, double* tflops, void* stream) {
+  if (!c) return -1;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int blocks = c->sm_count * 8, threads = 256, iters = 20000;
+  if (c->misc.ensure(sizeof(double) * (size_t)blocks * threads)) return fail(c, "out of device memory");
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  k_fp64_peak<<<blocks, threads, 0, s>>>(c->misc.as<double>(), 1000);  // warm-up
+  double best = 0.0;
+  for (int rep = 0; rep < 3; ++rep) {
+    cudaEventRecord(e0, s);
+    k_fp64_peak<<<blocks, threads, 0, s>>>(c->misc.as<double>(), iters);
+    cudaEventRecord(e1, s);
+    cudaEventSynchronize(e1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double fl = 2.0 * 8.0 * (double)iters * (double)blocks * threads;
+    best = std::max(best, fl / (ms * 1e-3) / 1e12);
+  }
+  c->launches += 4;
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  PWB_CUDA(c, cudaGetLastError());
+  *tflops = best;
+  return 0;
+}
+
+int pwb_draw_transit(pwb_ctx* c, double, double, double, double, int, int, int, const double*, double*,
+                     double*, double*, void*) {
+  return fail(c, "pwb_draw_transit: not built yet");
+}
+
+}  // extern "C"
+

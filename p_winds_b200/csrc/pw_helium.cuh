@@ -29,13 +29,13 @@ struct HeParams {
 };
 
 // helium.collision (helium.py:317-380)
-PW_HD void he_collision(double T, double* q13, double* q31a, double* q31b, double* bq_he, double* bq_hep) {
+PW_HD_NOINLINE void he_collision(double T, double* q13, double* q31a, double* q31b, double* bq_he, double* bq_hep) {
   const double lt[9] = {3.75, 4.00, 4.25, 4.50, 4.75, 5.00, 5.25, 5.50, 5.75};
   const double g13[9] = {6.198E-2, 6.458E-2, 6.387E-2, 6.157E-2, 5.832E-2, 5.320E-2, 4.787E-2, 4.018E-2, 3.167E-2};
   const double g31a[9] = {2.389, 2.456, 2.275, 1.916, 1.496, 1.111, 8.003E-1, 5.660E-1, 3.944E-1};
   const double g31b[9] = {7.965E-1, 9.579E-1, 1.042, 1.015, 8.950E-1, 7.265E-1, 5.516E-1, 3.948E-1, 2.677E-1};
   double tt[9];
-  for (int i = 0; i < 9; ++i) tt[i] = pow(10.0, lt[i]);
+  for (int i = 0; i < 9; ++i) tt[i] = pw_pow(10.0, lt[i]);
   const int j = bracket(tt, 9, T, 0);
   const double G13 = np_interp_at(tt, g13, 9, T, j);
   const double G31a = np_interp_at(tt, g31a, 9, T, j);
@@ -45,8 +45,8 @@ PW_HD void he_collision(double T, double* q13, double* q31a, double* q31b, doubl
   *q13 = k1 * G13 * exp(-19.81 / kt);
   *q31a = k1 * G31a / 3 * exp(-0.80 / kt);
   *q31b = k1 * G31b / 3 * exp(-1.40 / kt);
-  *bq_he = 1.75E-11 * pow(300 / T, 0.75) * exp(-128E3 / T);
-  *bq_hep = 1.25E-15 * pow(300 / T, -0.25);
+  *bq_he = 1.75E-11 * pw_pow(300 / T, 0.75) * exp(-128E3 / T);
+  *bq_hep = 1.25E-15 * pw_pow(300 / T, -0.25);
 }
 
 // Right-hand side helium.py:624-686.  The eight density-weighted rate
@@ -66,7 +66,7 @@ struct HeRhs {
   double sl[5], x0, b0[5];
   int jc;
 
-  PW_HD void coeffs(double x) {
+  PW_HD_NOINLINE void coeffs(double x) {
     const int jj = bracket(rn, n, x, j);
     j = jj;
     double v_, rho_, fh_, t1, t3;
@@ -157,7 +157,7 @@ struct HeOut {
 
 // Integrate once over the radius grid; returns false when the reference's solver
 // would have reported a problem (odeint warning / solve_ivp short output).
-PW_HD bool he_solve(const HeParams& p, HeRhs& rhs, const LsodaTables& tab, int nr, double* f1, double* f3,
+PW_HD_NOINLINE bool he_solve(const HeParams& p, HeRhs& rhs, const LsodaTables& tab, int nr, double* f1, double* f3,
                     double* ytmp, int* nfe, int* nst, int* nje) {
   const double* rn = rhs.rn;
   rhs.j = 0; rhs.jc = -2; rhs.xc = nan("");
@@ -206,8 +206,8 @@ PW_HD void he_population_model(const HeParams& p, const LsodaTables& tab, const 
                                const double* __restrict__ f_h, int nr, const HeWork& w, const HeOut& out) {
   const double rs_cm = p.rs * 7.1492E+09;
   const double alpha_unit = (rs_cm * rs_cm) * p.vs * 1E5;                 // helium.py:553
-  const double a_r1 = 1.54E-13 * pow(p.T / 1E4, -0.486) / alpha_unit;     // :290, :555
-  const double a_r3 = 2.10E-13 * pow(p.T / 1E4, -0.778) / alpha_unit;     // :291, :556
+  const double a_r1 = 1.54E-13 * pw_pow(p.T / 1E4, -0.486) / alpha_unit;     // :290, :555
+  const double a_r3 = 2.10E-13 * pw_pow(p.T / 1E4, -0.778) / alpha_unit;     // :291, :556
   const double m_h = 1.67262192E-24 / (p.rhos * (rs_cm * rs_cm * rs_cm)); // :559-560
   const double phi_unit = p.vs * 1E5 / p.rs / 7.1492E+09;                 // :570
   const double phi_1 = p.rates[0] / phi_unit, phi_3 = p.rates[1] / phi_unit;

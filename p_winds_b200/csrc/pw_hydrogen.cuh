@@ -125,7 +125,7 @@ struct HRhs {
 // One model, one CTA.  `r` is the radius profile in planetary radii (global).
 PW_HD void h_ion_fraction_model(const HParams& p, const SedTables& sed, const double* __restrict__ r,
                                 int nr, const HWork& w, const HOut& out) {
-  const double alpha_rec = 2.59E-13 * pow(p.T / 1E4, -0.7);  // hydrogen.py:207-223
+  const double alpha_rec = 2.59E-13 * pw_pow(p.T / 1E4, -0.7);  // hydrogen.py:207-223
   const double he_fraction = 1 - p.h_fraction;
   const double he_h = he_fraction / p.h_fraction;
   const double a_0 = p.exact_phi ? 0. : p.a0;

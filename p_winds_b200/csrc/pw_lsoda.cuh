@@ -146,7 +146,7 @@ struct Lsoda {
     el0 = el[1];
     conit = 0.5 / (double)(nq + 2);
   }
-  PW_HD void scaleh(double* rh, double* pdh) {  // stoda labels 175-180
+  PW_HD_NOINLINE void scaleh(double* rh, double* pdh) {  // stoda labels 175-180
     *rh = fmin(*rh, rmax);
     *rh = *rh / fmax(1., fabs(h) * hmxi * (*rh));
     if (meth == 1) {
@@ -178,7 +178,7 @@ struct Lsoda {
   }
 
   // prja, miter = 2: finite-difference Jacobian, P = I - h*el0*J, LU (dgefa)
-  PW_HD void prja() {
+  PW_HD_NOINLINE void prja() {
     ++nje;
     ierpj = 0;
     jcur = 1;
@@ -246,7 +246,7 @@ struct Lsoda {
 
   // stoda corrector loop (labels 220-450).  Returns corflag: 0 converged,
   // 1 retry with smaller h (rh set), 2 give up (kflag = -2).
-  PW_HD int correction(double pnorm, double* del_out, double told, int* ncf, double* rh, int* m_out) {
+  PW_HD_NOINLINE int correction(double pnorm, double* del_out, double told, int* ncf, double* rh, int* m_out) {
     int m = 0;
     double rate = 0., del = 0., delp = 0.;
     for (int i = 0; i < N; ++i) y[i] = yh[1][i];
@@ -329,7 +329,7 @@ struct Lsoda {
     return 1;
   }
 
-  PW_HD void methodswitch(double dsm, double pnorm, double* pdh, double* rh) {
+  PW_HD_NOINLINE void methodswitch(double dsm, double pnorm, double* pdh, double* rh) {
     if (meth == 1) {
       int nqm2;
       double rh2;
@@ -340,7 +340,7 @@ struct Lsoda {
         nqm2 = nq < mxords ? nq : mxords;
       } else {
         const double exsm = 1. / (double)l;
-        double rh1 = 1. / (1.2 * pow(dsm, exsm) + 0.0000012);
+        double rh1 = 1. / (1.2 * pw_pow(dsm, exsm) + 0.0000012);
         double rh1it = 2. * rh1;
         *pdh = pdlast * fabs(h);
         if ((*pdh * rh1) > 0.00001) rh1it = sm1(nq) / *pdh;
@@ -350,10 +350,10 @@ struct Lsoda {
           const int lm2 = mxords + 1;
           const double exm2 = 1. / (double)lm2;
           const double dm2 = vmnorm(yh[lm2 + 1]) / tab.cm2[mxords];
-          rh2 = 1. / (1.2 * pow(dm2, exm2) + 0.0000012);
+          rh2 = 1. / (1.2 * pw_pow(dm2, exm2) + 0.0000012);
         } else {
           const double dm2 = dsm * (tab.cm1[nq] / tab.cm2[nq]);
-          rh2 = 1. / (1.2 * pow(dm2, exsm) + 0.0000012);
+          rh2 = 1. / (1.2 * pw_pow(dm2, exsm) + 0.0000012);
           nqm2 = nq;
         }
         if (rh2 < ratio * rh1) return;
@@ -376,10 +376,10 @@ struct Lsoda {
       const int lm1 = mxordn + 1;
       exm1 = 1. / (double)lm1;
       dm1 = vmnorm(yh[lm1 + 1]) / tab.cm1[mxordn];
-      rh1 = 1. / (1.2 * pow(dm1, exm1) + 0.0000012);
+      rh1 = 1. / (1.2 * pw_pow(dm1, exm1) + 0.0000012);
     } else {
       dm1 = dsm * (tab.cm2[nq] / tab.cm1[nq]);
-      rh1 = 1. / (1.2 * pow(dm1, exsm) + 0.0000012);
+      rh1 = 1. / (1.2 * pw_pow(dm1, exsm) + 0.0000012);
       nqm1 = nq;
       exm1 = exsm;
     }
@@ -387,10 +387,10 @@ struct Lsoda {
     *pdh = pdnorm * fabs(h);
     if ((*pdh * rh1) > 0.00001) rh1it = sm1(nqm1) / *pdh;
     rh1 = fmin(rh1, rh1it);
-    const double rh2 = 1. / (1.2 * pow(dsm, exsm) + 0.0000012);
+    const double rh2 = 1. / (1.2 * pw_pow(dsm, exsm) + 0.0000012);
     if ((rh1 * ratio) < (5. * rh2)) return;
     const double alpha = fmax(0.001, rh1);
-    dm1 *= pow(alpha, exm1);
+    dm1 *= pw_pow(alpha, exm1);
     if (dm1 <= 1000. * kEps * pnorm) return;
     *rh = rh1;
     icount = 20;
@@ -402,15 +402,15 @@ struct Lsoda {
   }
 
   // labels 540-630.  orderflag: 0 no change, 1 h changes, 2 h and nq change
-  PW_HD void orderswitch(double rhup, double dsm, double* pdh, double* rh, int* orderflag) {
+  PW_HD_NOINLINE void orderswitch(double rhup, double dsm, double* pdh, double* rh, int* orderflag) {
     *orderflag = 0;
     const double exsm = 1. / (double)l;
-    double rhsm = 1. / (1.2 * pow(dsm, exsm) + 0.0000012);
+    double rhsm = 1. / (1.2 * pw_pow(dsm, exsm) + 0.0000012);
     double rhdn = 0.;
     if (nq != 1) {
       const double ddn = vmnorm(yh[l]) / tesco(nq, 1);
       const double exdn = 1. / (double)nq;
-      rhdn = 1. / (1.3 * pow(ddn, exdn) + 0.0000013);
+      rhdn = 1. / (1.3 * pw_pow(ddn, exdn) + 0.0000013);
     }
     if (meth == 1) {
       *pdh = fmax(fabs(h) * pdlast, 0.000001);
@@ -469,7 +469,7 @@ struct Lsoda {
   }
 
   // One step of the core integrator (DSTODA).
-  PW_HD void stoda() {
+  PW_HD_NOINLINE void stoda() {
     kflag = 0;
     const double told = tn;
     int ncf = 0;
@@ -552,7 +552,7 @@ struct Lsoda {
             for (int i = 0; i < N; ++i) savf[i] = acor[i] - yh[lmax][i];
             const double dup = vmnorm(savf) / tesco(nq, 3);
             const double exup = 1. / (double)(l + 1);
-            rhup = 1. / (1.4 * pow(dup, exup) + 0.0000014);
+            rhup = 1. / (1.4 * pw_pow(dup, exup) + 0.0000014);
           }
           int orderflag;
           orderswitch(rhup, dsm, &pdh, &rh, &orderflag);
@@ -625,7 +625,7 @@ struct Lsoda {
 
   // One `lsoda(..., itask = 1)` call: advance to tout and interpolate.
   // First call initialises from (t0, y0).  Returns istate.
-  PW_HD int call(double t0, const double* y0, double tout, double* yout) {
+  PW_HD_NOINLINE int call(double t0, const double* y0, double tout, double* yout) {
     if (!started) {
       started = true;
       mxordn = kLsodaMaxOrdN; mxords = kLsodaMaxOrdS;

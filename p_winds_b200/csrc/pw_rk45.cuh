@@ -97,7 +97,7 @@ PW_HD_NOINLINE int rk45_solve(RHS& rhs, const double* __restrict__ t_eval, int n
       const double d2 = rms(tmp) / h0;
       double h1;
       if (d1 <= 1e-15 && d2 <= 1e-15) h1 = fmax(1e-6, h0 * 1e-3);
-      else h1 = pow(0.01 / fmax(d1, d2), 1.0 / (4 + 1));
+      else h1 = pw_pow(0.01 / fmax(d1, d2), 1.0 / (4 + 1));
       h_abs = fmin(fmin(100 * h0, h1), fmin(interval, max_step));
     }
   }
@@ -162,12 +162,12 @@ PW_HD_NOINLINE int rk45_solve(RHS& rhs, const double* __restrict__ t_eval, int n
       if (error_norm < 1) {
         double factor;
         if (error_norm == 0) factor = MAX_FACTOR;
-        else factor = fmin(MAX_FACTOR, SAFETY * pow(error_norm, -0.2));
+        else factor = fmin(MAX_FACTOR, SAFETY * pw_pow(error_norm, -0.2));
         if (rejected) factor = fmin(1.0, factor);
         ha *= factor;
         accepted = true;
       } else if (error_norm >= 1) {
-        ha *= fmax(MIN_FACTOR, SAFETY * pow(error_norm, -0.2));
+        ha *= fmax(MIN_FACTOR, SAFETY * pw_pow(error_norm, -0.2));
         rejected = true;
         ++nrej;
       } else {
