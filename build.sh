@@ -3,8 +3,8 @@
 set -euo pipefail
 cd "$(dirname "$0")"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
-OUT=p_winds_b200/libpwinds_b200.so
-$NVCC -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -fmad=false \
+OUT=${PW_OUT:-p_winds_b200/libpwinds_b200.so}
+$NVCC -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -fmad=${PW_FMAD:-false} ${PW_DEFS:-} \
   --expt-relaxed-constexpr --expt-extended-lambda -Xcompiler -fPIC -shared \
   ${PW_PTXAS_V:+-Xptxas -v} -o $OUT p_winds_b200/csrc/pw_engine.cu
 echo "built $OUT"

@@ -88,7 +88,7 @@ def one_model(sp, geom, T0, mdot, h, tidal, tight):
     wl = np.linspace(1.0827, 1.0832, 200) * 1E-6
     i0, r_map = geom
     o['spectrum'] = transit.radiative_transfer_2d(
-        i0, r_map, R * R_PL * 71492000, f3 * n_he * 1E6, v * vs * 1000,
+        i0, r_map, R * (R_PL * 71492000), f3 * n_he * 1E6, v * vs * 1000,
         np.array([w0, w1, w2]), np.array([f0, f1_, f2]), np.array([a_ij] * 3),
         wl, float(T0), M_HE, wind_broadening_method='average')
     return o

@@ -5,7 +5,8 @@ Fails loudly when the CUDA library has not been built: there is no CPU path.
 import ctypes as C
 import os
 
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'libpwinds_b200.so')
+LIB_PATH = os.environ.get('PWB_LIB_PATH') or os.path.join(
+    os.path.dirname(os.path.abspath(__file__)), 'libpwinds_b200.so')
 
 c_double_p = C.POINTER(C.c_double)
 

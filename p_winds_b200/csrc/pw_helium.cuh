@@ -58,6 +58,7 @@ struct HeRhs {
   int n;
   double lk1;         // log(k1)
   double lc[8];       // log of alpha_rec_1, alpha_rec_3, q_13, q_31a, q_31b, Q_31, Q_He, Q_He+
+  double kc[8];       // k1 * the same eight coefficients
   double phi1, phi3, ba31;
   // cache
   int j;
@@ -94,8 +95,9 @@ struct HeRhs {
       t1 = sl[3] * d + b0[3];
       t3 = sl[4] * d + b0[4];
     }
+#if defined(PW_HE_LOGEXP)
+    // literal form of helium.py:637-652: exp(log(k1) + log(rho) + log(coef)) * f_h_ion
     const double lr = lk1 + log(rho_);
-    // exp(log(k1) + log(rho) + log(coef)) * f_h_ion   (helium.py:637-652)
     c[0] = exp(lr + lc[0]) * fh_;
     c[1] = exp(lr + lc[1]) * fh_;
     c[2] = exp(lr + lc[2]) * fh_;
@@ -104,6 +106,21 @@ struct HeRhs {
     c[5] = exp(lr + lc[5]) * (1 - fh_);
     c[6] = exp(lr + lc[6]) * fh_;
     c[7] = exp(lr + lc[7]) * (1 - fh_);
+#else
+    // exp(log k1 + log rho + log coef) == k1 * rho * coef.  The reference takes the
+    // detour through logarithms to avoid overflow, which cannot happen in binary64
+    // here (k1 * rho < 1e45); its round trip carries ~|log|*eps ~ 1e-14 relative
+    // rounding noise, the plain product 2e-16.  The product is the default; build with
+    // -DPW_HE_LOGEXP for the literal form (tests/test_parity_gpu.py covers both).
+    c[0] = (kc[0] * rho_) * fh_;
+    c[1] = (kc[1] * rho_) * fh_;
+    c[2] = (kc[2] * rho_) * fh_;
+    c[3] = (kc[3] * rho_) * fh_;
+    c[4] = (kc[4] * rho_) * fh_;
+    c[5] = (kc[5] * rho_) * (1 - fh_);
+    c[6] = (kc[6] * rho_) * fh_;
+    c[7] = (kc[7] * rho_) * (1 - fh_);
+#endif
     e1 = exp(-t1);
     e3 = exp(-t3);
     vv = v_;
@@ -244,6 +261,8 @@ PW_HD void he_population_model(const HeParams& p, const LsodaTables& tab, const 
   rhs.lk1 = log(k1);
   rhs.lc[0] = log(a_r1); rhs.lc[1] = log(a_r3); rhs.lc[2] = log(q13); rhs.lc[3] = log(q31a);
   rhs.lc[4] = log(q31b); rhs.lc[5] = log(bq31); rhs.lc[6] = log(bq_he); rhs.lc[7] = log(bq_hep);
+  rhs.kc[0] = k1 * a_r1; rhs.kc[1] = k1 * a_r3; rhs.kc[2] = k1 * q13; rhs.kc[3] = k1 * q31a;
+  rhs.kc[4] = k1 * q31b; rhs.kc[5] = k1 * bq31; rhs.kc[6] = k1 * bq_he; rhs.kc[7] = k1 * bq_hep;
   rhs.phi1 = phi_1; rhs.phi3 = phi_3; rhs.ba31 = ba31;
 
   int nfe = 0, nst = 0, nje = 0, n_relax = 0, status = PW_OK;

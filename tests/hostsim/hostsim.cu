@@ -137,3 +137,40 @@ int hs_rk45_vdp(double mu, const double* y0, const double* t, int n, double rtol
   return got;
 }
 }
+
+#include "../../p_winds_b200/csrc/pw_transit.cuh"
+
+extern "C" {
+
+void hs_wofz_re(const double* x, const double* y, int n, double* out) {
+  for (int i = 0; i < n; ++i) out[i] = wofz_re(x[i], y[i]);
+}
+
+void hs_voigt(const double* x, int n, double sigma, double gamma, double* out) {
+  for (int i = 0; i < n; ++i) out[i] = voigt_profile(x[i], sigma, gamma);
+}
+
+// 'average' optical depth table tau[nr][nw] exactly as the kernels form it
+// (k_rt_los + k_rt_sum phase B): ncol[i] * Phi(lambda)
+void hs_tau_average(const double* r, const double* n, const double* v, const double* tprof, int nr,
+                    const double* w0, const double* fosc, const double* aij, int nlines, double mass,
+                    double v_bulk, double rv, int nz, int turbulence, double T, const double* wl, int nw,
+                    double* tau, double* sums_out) {
+  std::vector<double> ncol(nr);
+  double sums[4], red[40];
+  rt_los_average(r, n, v, tprof, nr, nz, ncol.data(), sums, red);
+  RtParams p;
+  p.n_lines = nlines;
+  for (int k = 0; k < nlines; ++k) { p.w0[k] = w0[k]; p.fosc[k] = fosc[k]; p.aij[k] = aij[k]; }
+  p.mass = mass; p.v_bulk = v_bulk; p.rv_planet = rv; p.nz = nz; p.turbulence = turbulence;
+  p.t_is_profile = tprof != nullptr;
+  const double vw2 = sums[1] / sums[0];
+  const double temp = tprof ? sums[2] / sums[0] : T;
+  for (int k = 0; k < nw; ++k) {
+    const double phi = rt_phi_average(p, wl[k], temp, vw2);
+    for (int i = 0; i < nr; ++i) tau[(size_t)i * nw + k] = ncol[i] * phi;
+  }
+  if (sums_out) { sums_out[0] = sums[0]; sums_out[1] = sums[1]; sums_out[2] = sums[2]; }
+}
+
+}  // extern "C"

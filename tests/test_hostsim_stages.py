@@ -1,0 +1,192 @@
+"""Parity tier P1 for the physics stages: the host build of the device code against
+the oracle (== the reference, see test_oracle_vs_golden.py)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+from scipy.special import wofz
+
+from conftest import P, golden
+
+R = np.logspace(0, np.log10(20), 100)
+
+
+@pytest.fixture(scope='module')
+def tables(hostsim, sed):
+    n = len(sed.wl)
+    gw, sh, she, sc = np.zeros(n), np.zeros(n), np.zeros(n), np.zeros(16)
+    hostsim.hs_sed_setup(P(sed.wl), P(sed.flux), n, P(gw), P(sh), P(she), P(sc))
+    return gw, sh, she, sc
+
+
+def test_sed_tables_and_scalars(tables, oracle, sed):
+    gw, sh, she, sc = tables
+    ref = np.array(list(oracle.h_radiative_processes(sed)) + list(oracle.he_radiative_processes(sed)))
+    assert np.max(np.abs(sc[:8] / ref - 1)) < 5e-15
+    assert (int(sc[8]), int(sc[9]), int(sc[10])) == (912, 504, 911)
+    nh = int(sc[8])
+    assert np.max(np.abs(sh[:nh] / oracle.sigma_h(sed.wl[:nh]) - 1)) < 5e-15
+    ref_he = oracle.sigma_he_total(sed.wl[:nh])
+    m = ref_he > 0
+    assert np.array_equal(she[:nh][~m], ref_he[~m])
+    assert np.max(np.abs(she[:nh][m] / ref_he[m] - 1)) < 1e-12
+
+
+def test_parker_structure(hostsim, oracle):
+    g = golden('parker')
+    r = np.ascontiguousarray(g['r'])
+    v, rho = np.zeros_like(r), np.zeros_like(r)
+    hostsim.hs_parker(P(r), len(r), P(v), P(rho))
+    m = np.abs(r - 1.0) > 1e-6     # at r == 1 the reference's secant is only sqrt(eps) accurate
+    assert np.max(np.abs(v[m] / g['v'][m] - 1)) < 2e-13
+    assert np.max(np.abs(rho[m] / g['rho'][m] - 1)) < 2e-13
+    assert abs(v[~m][0] - 1.0) < 1e-15 and abs(g['v'][~m][0] - 1.0) < 1e-6   # reference tests/test_parker.py
+    hostsim.hs_parker_tidal.argtypes = [C.c_void_p, C.c_int] + [C.c_double] * 5 + [C.c_void_p] * 2
+    hostsim.hs_parker_tidal(P(r), len(r), float(g['cs']), float(g['rs_tidal']), 0.73, 1.07, 0.04634, P(v), P(rho))
+    assert np.max(np.abs(v[m] / g['v_tidal'][m] - 1)) < 2e-13
+    assert np.max(np.abs(rho[m] / g['rho_tidal'][m] - 1)) < 2e-13
+
+
+def _h_host(hostsim, tables, T, md, h, tidal, r, exact=1, relax=1, mu0=None, rtol=1e-3, atol=1e-6,
+            phi_abs=0., a0=0.):
+    gw, sh, she, sc = tables
+    he_h = (1 - h) / h
+    if mu0 is None:
+        mu0 = (1 + 4 * he_h) / (1 + he_h)
+    model = np.array([T, md, h, mu0])
+    opts = np.array([1.39, 0.73, 1.07 if tidal else 1.0, 0.04634 if tidal else 1.0, 0.0, 0.01, 10, relax, exact,
+                     phi_abs, a0, rtol, atol, 0., 0., 1 if tidal else 0], dtype=float)
+    nr = len(r)
+    f, v, rho, scal = np.zeros(nr), np.zeros(nr), np.zeros(nr), np.zeros(8)
+    st = hostsim.hs_h_ion_fraction(P(model), P(opts), P(np.ascontiguousarray(r)), nr, P(gw), P(sh), P(she),
+                                   int(sc[8]), P(f), P(v), P(rho), P(scal))
+    return st, f, v, rho, scal
+
+
+@pytest.mark.parametrize('tidal', [False, True])
+@pytest.mark.parametrize('T0,md', [(9100., 10 ** 10.27), (9100., 1e11), (12000., 1e10), (7000., 1e11),
+                                   (13000., 10 ** 9.5)])
+def test_hydrogen_stage_trace(hostsim, tables, oracle, sed, tidal, T0, md):
+    """Same solver outcome, same number of relax passes, same total nfev as
+    scipy's RK45 inside the reference algorithm; values to rounding."""
+    mu0 = (1 + 4 * 0.1 / 0.9) / (1 + 0.1 / 0.9)
+    o = oracle.h_ion_fraction(R, 1.39, T0, 0.9, md, 0.73, mu0, *((1.07, 0.04634) if tidal else (1.0, 1.0)),
+                              sed=sed, exact_phi=True, relax_solution=True)
+    st, f, v, rho, scal = _h_host(hostsim, tables, T0, md, 0.9, tidal, R)
+    assert st == o['status']
+    assert int(scal[5]) == sum(o['nfev'])
+    if st == 0:
+        assert int(scal[4]) == o['n_relax']
+        assert np.max(np.abs(f[1:] / o['f_r'][1:] - 1)) < 1e-8
+        assert abs(scal[0] / o['mu_bar'] - 1) < 1e-9
+
+
+def test_hydrogen_reference_test_configuration(hostsim, tables, oracle, sed):
+    """reference tests/test_hydrogen.py (500 radii, mu_0 = 0.7): approximate and exact phi."""
+    g = golden('hydrogen')
+    sc = tables[3]
+    st, f, *_ = _h_host(hostsim, tables, 9E3, 8E10, 0.9, False, g['r500'], exact=0, mu0=0.7,
+                        phi_abs=sc[0], a0=sc[1])
+    assert st == 0 and abs((f[-1] - 0.998737) / f[-1]) < 1e-4
+    assert np.max(np.abs(f[1:] / g['f_approx'][1:] - 1)) < 1e-8
+    st, f, *_ = _h_host(hostsim, tables, 9E3, 8E10, 0.9, False, g['r500'], exact=1, mu0=0.7)
+    assert st == 0 and abs((f[-1] - 0.998913) / f[-1]) < 1e-4
+    assert np.max(np.abs(f[1:] / g['f_exact'][1:] - 1)) < 1e-8
+    # monochromatic EUV channel (quickstart.ipynb last cells)
+    phi, a0 = oracle.h_radiative_processes_mono(1000.)
+    st, f, *_ = _h_host(hostsim, tables, 9100., 10 ** 10.27, 0.9, False, np.linspace(1.0, 20, 500), exact=0,
+                        mu0=0.7613, phi_abs=phi, a0=a0)
+    assert st == 0 and np.max(np.abs(f[1:] / g['f_mono'][1:] - 1)) < 1e-8
+
+
+def _he_host(hostsim, rates, T, h, vs, rs, rhos, r, v, rho, fh, method=0, rtol=0., atol=0., relax=1):
+    model = np.array([T, h, vs, rs, rhos])
+    opts = np.array([1.39, 1.0, 0.0, relax, 10, 0.01, method, rtol, atol, 0., 0.], dtype=float)
+    nr = len(r)
+    f1, f3, scal = np.zeros(nr), np.zeros(nr), np.zeros(4)
+    st = hostsim.hs_he_population(P(model), P(opts), P(rates), P(np.ascontiguousarray(r)),
+                                  P(np.ascontiguousarray(v)), P(np.ascontiguousarray(rho)),
+                                  P(np.ascontiguousarray(fh)), nr, P(f1), P(f3), P(scal), None)
+    return st, f1, f3, scal
+
+
+def _he_inputs(oracle, sed, T0, md, tight):
+    mu0 = (1 + 4 * 0.1 / 0.9) / (1 + 0.1 / 0.9)
+    kw = dict(rtol=1e-10, atol=1e-13) if tight else {}
+    o = oracle.h_ion_fraction(R, 1.39, T0, 0.9, md, 0.73, mu0, sed=sed, exact_phi=True, relax_solution=True, **kw)
+    vs = oracle.sound_speed(T0, o['mu_bar'])
+    rs = oracle.radius_sonic_point(0.73, vs)
+    rhos = oracle.density_sonic_point(md, rs, vs)
+    v, rho = oracle.structure(R * 1.39 / rs)
+    return o['f_r'], vs, rs, rhos, v, rho
+
+
+@pytest.mark.parametrize('T0,md', [(9100., 10 ** 10.27), (11000., 1e11)])
+def test_helium_stage_tight_tolerance(hostsim, oracle, sed, T0, md):
+    """Tier P2 on the host: at rtol=1e-10 / atol=1e-16 the LSODA replica and scipy's
+    LSODA agree far inside the 1e-6 contract; relax counts identical."""
+    rates = np.array(oracle.he_radiative_processes(sed))
+    f_r, vs, rs, rhos, v, rho = _he_inputs(oracle, sed, T0, md, True)
+    oh = oracle.he_population(R, v, rho, f_r, 1.39, T0, 0.9, vs, rs, rhos, rates=tuple(rates),
+                              initial_state=np.array([1., 0.]), relax_solution=True, method='LSODA',
+                              rtol=1e-10, atol=1e-16)
+    st, f1, f3, scal = _he_host(hostsim, rates, T0, 0.9, vs, rs, rhos, R, v, rho, f_r, method=1, rtol=1e-10,
+                                atol=1e-16)
+    assert st == oh['status'] == 0 and int(scal[0]) == oh['n_relax']
+    assert np.max(np.abs(f1 / oh['f_1'] - 1)) < 2e-8
+    ipk = np.argmax(oh['f_3'])
+    assert abs(f3[ipk] / oh['f_3'][ipk] - 1) < 2e-8
+    big = oh['f_3'] > 1e-3 * oh['f_3'][ipk]
+    assert np.max(np.abs(f3[big] / oh['f_3'][big] - 1)) < 1e-6
+
+
+@pytest.mark.parametrize('T0,md', [(9100., 10 ** 10.27), (9100., 1e11), (10000., 1e12)])
+def test_helium_stage_default_tolerance_envelope(hostsim, oracle, sed, T0, md):
+    """Tier P3 on the host: at odeint's default tolerance the output is only defined
+    to the integrator's own noise (f1 ~5e-6 median / 4e-5 max,
+    f3 at its peak ~1e-5 median / 1.6e-4 max for *any* valid integrator, including
+    the reference re-run with 1-ulp input noise).  Work counters within 10 %."""
+    rates = np.array(oracle.he_radiative_processes(sed))
+    f_r, vs, rs, rhos, v, rho = _he_inputs(oracle, sed, T0, md, False)
+    oh = oracle.he_population(R, v, rho, f_r, 1.39, T0, 0.9, vs, rs, rhos, rates=tuple(rates),
+                              initial_state=np.array([1., 0.]), relax_solution=True)
+    st, f1, f3, scal = _he_host(hostsim, rates, T0, 0.9, vs, rs, rhos, R, v, rho, f_r)
+    assert st == oh['status'] == 0 and int(scal[0]) == oh['n_relax']
+    assert np.max(np.abs(f1 / oh['f_1'] - 1)) < 1e-4
+    ipk = np.argmax(oh['f_3'])
+    assert abs(f3[ipk] / oh['f_3'][ipk] - 1) < 1e-3
+    for k, key in ((1, 'nfe'), (2, 'nst'), (3, 'nje')):
+        assert abs(scal[k] / sum(oh[key]) - 1) < 0.10, key
+
+
+def test_wofz_against_scipy(hostsim):
+    rng = np.random.default_rng(0)
+    sets = [(np.linspace(-15, 15, 2001), np.full(2001, 1.4e-4)),        # He 10830
+            (np.linspace(-35, 35, 2001), np.full(2001, 4.9e-4)),        # Ly-alpha
+            (rng.uniform(-60, 60, 20000), 10 ** rng.uniform(-8, 1.5, 20000)),
+            (10 ** rng.uniform(-8, -2, 5000), 10 ** rng.uniform(-6, 0, 5000)),
+            (10 ** rng.uniform(1, 9, 5000), 10 ** rng.uniform(-12, 3, 5000))]
+    for x, y in sets:
+        x, y = np.ascontiguousarray(x), np.ascontiguousarray(y)
+        out = np.zeros_like(x)
+        hostsim.hs_wofz_re(P(x), P(y), len(x), P(out))
+        assert np.max(np.abs(out / wofz(x + 1j * y).real - 1)) < 2e-14
+
+
+def test_optical_depth_average_against_reference(hostsim):
+    """tau[Nr, Nw] of transit.optical_depth_2d ('average'), reference fixture."""
+    d, ka = golden('he_3_profile'), golden('rt_known_answer')
+    w0 = np.array([1.082909114, 1.083025010, 1.083033977]) * 1e-6
+    f = np.array([5.9902e-02, 1.7974e-01, 2.9958e-01])
+    a = np.array([1.0216e+07] * 3)
+    wl = np.ascontiguousarray(ka['wl'])
+    tau = np.zeros((500, 150))
+    hostsim.hs_tau_average.argtypes = [C.c_void_p] * 4 + [C.c_int] + [C.c_void_p] * 3 + [C.c_int] + \
+        [C.c_double] * 3 + [C.c_int, C.c_int, C.c_double, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    hostsim.hs_tau_average(P(np.ascontiguousarray(d['r'])), P(np.ascontiguousarray(d['n'])),
+                           P(np.ascontiguousarray(d['v'])), None, 500, P(w0), P(f), P(a), 3,
+                           4 * 1.67262192369e-27, -2e3, 0.0, 200, 0, 9e3, P(wl), 150, P(tau), None)
+    ref = ka['tau_average']
+    m = ref > 0
+    assert np.array_equal(tau[~m], ref[~m])
+    assert np.max(np.abs(tau[m] / ref[m] - 1)) < 1e-12
