@@ -559,11 +559,10 @@ int pwb_rt2d_batch(pwb_ctx* c, int B, const double* d_n, const double* d_v, cons
   c->launches++;
   PWB_CUDA(c, cudaGetLastError());
   const int tiles = (Nw + 255) / 256;
-  // enough CTAs to fill the machine (>= 4 per SM) when the batch alone does not
-  int nsplit = 1;
-  const long long want = (long long)c->sm_count * 4;
-  if ((long long)B * tiles < want) nsplit = (int)std::min<long long>((want + (long long)B * tiles - 1) / ((long long)B * tiles), 64);
-  if (c->n_active < nsplit * PW_RT_CHUNK) nsplit = std::max(1, c->n_active / PW_RT_CHUNK);
+  // The active pixels are always cut into the same segments, whatever the batch size,
+  // so that a model's spectrum is bit-identical alone or inside a grid (the partial
+  // sums are combined in a fixed order by k_rt_reduce).  <= 16 segments of >= 1024 pixels.
+  int nsplit = std::min(16, std::max(1, (c->n_active + 1023) / 1024));
   double* part = d_spectrum;
   if (nsplit > 1) {
     if (c->rt_partial.ensure(sizeof(double) * (size_t)B * nsplit * Nw)) return fail(c, "out of device memory");
