@@ -1,0 +1,363 @@
+#!/usr/bin/env python
+"""Headline benchmark: He 10830 forward models per second (BASELINE.json `metric`).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (BASELINE.json configs[2], the largest single-GPU configuration the metric
+is quoted on): a 64 x 64 (T0, Mdot) He-triplet retrieval grid per GPU -- HD 209458 b,
+solar SED, 100 radii, exact photoionisation, relax loops on, reference solver
+tolerances (RK45 1e-3/1e-6, odeint 1.49e-8), G = 100 transit map (supersampling 10),
+200 wavelength bins, 3 lines.  One step = one pass of the whole forward-model path
+over the rank's 4096 models + chi^2.  With N GPUs the grid grows to 64 x 64 x N
+(h_fraction axis), models are interleaved over ranks, and the only exchange is the
+final all_gather of chi^2 / status over NCCL (weak scaling).
+
+The reference arm (`--impl reference`) times the CPU oracle port of the reference
+algorithm (oracle/pwinds_oracle.py, scipy solvers) on all host cores on a bounded
+sample of the same grid; under torchrun only rank 0 runs it.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+GOLDEN = os.path.join(ROOT, 'tests', 'golden')
+
+N_GRID = 64
+R_PL, M_PL = 1.39, 0.73
+NR, NW, NLINES = 100, 200, 3
+M_HE = 4 * 1.67262192369e-27
+METRIC = 'He10830 forward models/sec'
+UNIT = 'models/s'
+
+
+def grid(n_gpus):
+    """Global (T0, Mdot, h_fraction) arrays, flattened; SURVEY.md 8(d) throughput grid."""
+    T0 = np.linspace(10000, 13000, N_GRID)
+    md = np.logspace(9.5, 12, N_GRID)
+    hf = np.array([0.90]) if n_gpus == 1 else np.linspace(0.85, 0.95, n_gpus)
+    HH, TT, MM = np.meshgrid(hf, T0, md, indexing='ij')
+    return TT.ravel(), MM.ravel(), HH.ravel()
+
+
+def config(n_gpus):
+    return {'workload': 'He-triplet retrieval grid 64x64 (T0, Mdot) per GPU (BASELINE configs[2]); '
+                        'HD 209458 b, solar SED, Nr=100, G=100 (ss=10), Nw=200, 3 lines, exact_phi, '
+                        'relax_solution, reference solver tolerances',
+            'models_per_gpu': N_GRID * N_GRID, 'global_models': N_GRID * N_GRID * n_gpus,
+            'sharding': 'interleaved over ranks, final all_gather of chi2+status' if n_gpus > 1 else 'single GPU',
+            'l2_policy': 'L2 flushed (512 MiB write) before every timed step'}
+
+
+# ----------------------------------------------------------------------------- CPU side
+def _cpu_init():
+    global _S, _O
+    os.environ['OMP_NUM_THREADS'] = os.environ['OPENBLAS_NUM_THREADS'] = '1'
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    import pwinds_oracle as O
+    g = np.load(os.path.join(GOLDEN, 'solar_sed.npz'))
+    geo = np.load(os.path.join(GOLDEN, 'geometry.npz'))
+    _O = O
+    _S = O.Setup(O.Sed(g['wavelength'], g['flux_lambda']), i0=geo['i0'], r_map=geo['r_map'])
+
+
+def _cpu_model(args):
+    T, md, h = args
+    t = time.perf_counter()
+    o = _O.forward_model(_S, float(T), float(md), float(h))
+    return o['status'], time.perf_counter() - t
+
+
+def cpu_loop(T, md, hf, n_sample, pool, cores):
+    """Reference per-model CPU loop on a deterministic subsample (every k-th model)."""
+    k = max(1, len(T) // n_sample)
+    idx = np.arange(0, len(T), k)[:n_sample]
+    t0 = time.perf_counter()
+    res = pool.map(_cpu_model, [(T[i], md[i], hf[i]) for i in idx], chunksize=1)
+    dt = time.perf_counter() - t0
+    fails = sum(1 for s, _ in res if s in (1, 2))
+    return {'value': len(idx) / dt, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+            'sample': 'every %d-th model of the 64x64 grid (%d models), multiprocessing.Pool(%d), '
+                      'OMP_NUM_THREADS=1; oracle/pwinds_oracle.py (numpy + scipy solve_ivp/odeint), '
+                      '%d failed, mean %.3f s/model/core' % (k, len(idx), cores, fails,
+                                                              float(np.mean([x for _, x in res])))}, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    cores = len(os.sched_getaffinity(0))
+    T, md, hf = grid(args.gpus)
+    n_sample = max(cores * 4, 32)
+    with mp.Pool(cores, initializer=_cpu_init) as pool:
+        for _ in range(args.warmup):
+            cpu_loop(T, md, hf, cores, pool, cores)
+        tot_models, tot_t, base = 0, 0.0, None
+        for _ in range(args.steps):
+            base, dt = cpu_loop(T, md, hf, n_sample, pool, cores)
+            tot_models += min(n_sample, len(T))
+            tot_t += dt
+    value = tot_models / tot_t
+    base['value'] = value
+    line = {'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
+            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * tot_t / args.steps,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
+            'data': 'synthetic grid over the reference solar SED', 'config': config(args.gpus),
+            'cpu_baseline': base,
+            'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'gpu_launches': 0}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- GPU side
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,'
+             'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+             'clocks_event_reasons.sw_power_cap')
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + q,
+                                      '--format=csv,noheader,nounits'], capture_output=True, text=True,
+                                     timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(',')])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        if not self.rows:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        sm = [float(r[0]) for r in self.rows if r[0].replace('.', '').isdigit()]
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = sorted({n for r in self.rows for n, v in zip(names, r[2:6]) if v.lower().startswith('active')})
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': float(self.rows[0][1]),
+                'reasons': reasons, 'samples': len(self.rows)}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from p_winds_b200.engine import Engine
+    from p_winds_b200 import lines, grid as pgrid
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit('launch with torchrun --nproc-per-node %d for --gpus %d' % (args.gpus, args.gpus))
+        args.gpus = world
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    dev = torch.device('cuda', local_rank)
+
+    g = np.load(os.path.join(GOLDEN, 'solar_sed.npz'))
+    geo = np.load(os.path.join(GOLDEN, 'geometry.npz'))
+    r = np.logspace(0, np.log10(20), NR)
+    wl = np.linspace(1.0827, 1.0832, NW) * 1E-6
+    eng = Engine(local_rank)
+    eng.set_sed(g['wavelength'], g['flux_lambda'])
+    eng.set_geometry(geo['i0'], geo['r_map'], r * (R_PL * 71492000))
+    sc = eng.sed_scalars()
+    rates = [sc[k] for k in ('he_phi_1', 'he_phi_3', 'he_a_1', 'he_a_3', 'he_a_h_1', 'he_a_h_3')]
+    ho = Engine.h_opts(R_PL, M_PL, relax_solution=True, exact_phi=True)
+    heo = Engine.he_opts(R_PL, rates, (1.0, 0.0), True)
+    w = lines.he_3_properties()
+    rto = Engine.rt_opts(w[:3], w[3:6], [w[6]] * 3, M_HE)
+    fp64_peak = eng.fp64_peak_tflops()
+
+    T, md, hf = grid(world)
+    n_global = len(T)
+    idx = pgrid.shard_indices(n_global, rank, world)
+    B = len(idx)
+    # host side of the public API: pinned host buffers in, pinned host buffers out
+    h_in = torch.from_numpy(np.stack([T[idx], md[idx], hf[idx]])).pin_memory()
+    d_in = torch.empty_like(h_in, device=dev)
+    out = eng.alloc_forward(B, NR, NW)
+    h_spec = torch.empty((B, NW), dtype=torch.float64).pin_memory()
+    h_chi2 = torch.empty(n_global, dtype=torch.float64).pin_memory()
+    h_status = torch.empty(B, dtype=torch.int32).pin_memory()
+    rd, wd = eng.dev(r), eng.dev(wl)
+    # synthetic "observation": the model at the grid centre + fixed noise level
+    data = torch.ones(NW, dtype=torch.float64, device=dev)
+    sigma = torch.full((NW,), 1e-3, dtype=torch.float64, device=dev)
+    norm = float(geo['i0'].sum())
+    flush = torch.empty(512 * 1024 * 1024 // 8, dtype=torch.float64, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step(e2e, events=None):
+        if e2e:
+            d_in.copy_(h_in, non_blocking=True)
+        Td, mdd, hfd = d_in[0], d_in[1], d_in[2]
+        if events:
+            events[0].record()
+        eng.forward_batch(Td, mdd, hfd, rd, ho, heo, rto, wd, out=out)
+        if events:
+            events[1].record()
+        chi2 = eng.chi2_batch(out['spectrum'], data, sigma, norm, out['status'])
+        allchi = pgrid.gather_interleaved(chi2, n_global, rank, world)
+        if e2e:
+            h_spec.copy_(out['spectrum'], non_blocking=True)
+            h_chi2.copy_(allchi, non_blocking=True)
+            h_status.copy_(out['status'], non_blocking=True)
+        return allchi
+
+    def timed(e2e, steps):
+        """K steps timed with CUDA events on the launching stream; L2 flushed before each."""
+        total_ms = 0.0
+        for _ in range(steps):
+            flush.fill_(1.0)
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            step(e2e)
+            e1.record()
+            if e2e:
+                torch.cuda.current_stream().synchronize()
+            barrier()
+            total_ms += e0.elapsed_time(e1)
+        return total_ms
+
+    d_in.copy_(h_in)
+    for _ in range(max(args.warmup, 3)):
+        step(True)
+    barrier()
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = eng.launch_count()
+    t_wall = time.perf_counter()
+    ms_dev = timed(False, args.steps)
+    wall_dev = time.perf_counter() - t_wall
+    launches = eng.launch_count() - launches0
+    ms_e2e = timed(True, args.steps)
+    sampler.stop_flag = True
+    sampler.join(2)
+
+    # per-kernel device time of one step (CUDA events around each stage call)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+    barrier()
+    Td, mdd, hfd = d_in[0], d_in[1], d_in[2]
+    mu0 = (1 + 4 * (1 - hfd) / hfd) / (1 + (1 - hfd) / hfd)
+    ev[0].record()
+    h = eng.h_ion_fraction_batch(Td, mdd, hfd, mu0, rd, ho)
+    ev[1].record()
+    he = eng.he_population_batch(Td, hfd, h['scal'][:, 1].contiguous(), h['scal'][:, 2].contiguous(),
+                                 h['scal'][:, 3].contiguous(), rd, h['v'], h['rho'], h['f_r'], heo,
+                                 status=h['status'].clone())
+    ev[2].record()
+    nhe = h['rho'] * h['scal'][:, 3:4] * (1 - hfd[:, None]) / (hfd[:, None] + 4 * (1 - hfd[:, None])) \
+        / 1.67262192369e-24 * he['f_3'] * 1e6
+    vsi = h['v'] * h['scal'][:, 1:2] * 1000
+    ev[3].record()
+    eng.rt2d_batch(nhe, vsi, Td, wd, rto, status=he['status'])
+    ev[4].record()
+    barrier()
+    t_h, t_he, t_rt = ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2]), ev[3].elapsed_time(ev[4])
+    status = out['status'].cpu().numpy()
+    nfe_he = float(he['scal'][:, 1].sum())
+    nfev_h = float(h['scal'][:, 5].sum())
+    n_relax_h = float(h['scal'][:, 4].sum())
+    n_ok = int((status == 0).sum() + (status == 3).sum())
+
+    # algorithmic FP64 work, SURVEY.md 8(d) convention (add/mul 1, FMA 2, div/sqrt 8, exp/log 20,
+    # linear interp 20, Lambert-W 200, wofz 150); measured counters instead of estimates
+    px = int((geo['i0'] != 0).sum())
+    w_he = nfe_he * 540.0
+    w_h = (n_relax_h + B) * NR * sc['n_cut_h'] * 28.0 + nfev_h * 85.0 + (2 * (n_relax_h + B) + B) * NR * 200.0
+    w_rt = n_ok * (px * (35.0 + NW * 26.0) + 200 * NR * 60.0 + NLINES * NW * 150.0)
+    tms = torch.tensor([ms_dev, ms_e2e, t_h, t_he, t_rt], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms_dev, ms_e2e, t_h, t_he, t_rt = tms.tolist()
+    value = n_global * args.steps / (ms_dev * 1e-3)
+    e2e = n_global * args.steps / (ms_e2e * 1e-3)
+
+    kernels = {
+        'k_helium': {'ms': t_he, 'share_of_step': t_he / (t_h + t_he + t_rt), 'flop': w_he,
+                     'achieved_tflops': w_he / (t_he * 1e-3) / 1e12,
+                     'note': 'latency bound: %.0f dependent RHS evaluations per model (max %.0f), one thread '
+                             'per model' % (nfe_he / B, float(he['scal'][:, 1].max()))},
+        'k_hydrogen': {'ms': t_h, 'share_of_step': t_h / (t_h + t_he + t_rt), 'flop': w_h,
+                       'achieved_tflops': w_h / (t_h * 1e-3) / 1e12},
+        'k_rt_los+k_rt_sum+k_rt_reduce': {'ms': t_rt, 'share_of_step': t_rt / (t_h + t_he + t_rt),
+                                           'flop': w_rt, 'achieved_tflops': w_rt / (t_rt * 1e-3) / 1e12},
+    }
+    dom = max(kernels, key=lambda k: kernels[k]['ms'])
+    roofline = {'bound': 'fp64', 'kernel': dom, 'achieved': kernels[dom]['achieved_tflops'],
+                'peak': fp64_peak, 'unit': 'TFLOP/s', 'frac': kernels[dom]['achieved_tflops'] / fp64_peak,
+                'traffic': None,
+                'peak_source': 'FP64 DFMA microbenchmark run in this process (pwb_fp64_peak); '
+                               'MEASURED_PEAKS.json has no FP64 figure; no tensor cores on this path',
+                'whole_step': {'flop': w_h + w_he + w_rt,
+                               'achieved': (w_h + w_he + w_rt) / ((t_h + t_he + t_rt) * 1e-3) / 1e12,
+                               'frac': (w_h + w_he + w_rt) / ((t_h + t_he + t_rt) * 1e-3) / 1e12 / fp64_peak},
+                'hbm': {'bytes_per_model': 8 * (4 * NR + NW) + 12 + 24,
+                        'achieved_gbs': n_global * args.steps * (8 * (4 * NR + NW) + 36) / (ms_dev * 1e-3) / 1e9,
+                        'note': 'profiles + spectrum written per model; inputs (SED tables 22 KB, pixel table '
+                                '%d KB) stay L2 resident: HBM is not the bound' % (px * 28 // 1024)},
+                'kernels': kernels}
+
+    cpu_base = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        import multiprocessing as mp
+        cores = len(os.sched_getaffinity(0))
+        with mp.get_context('fork').Pool(cores, initializer=_cpu_init) as pool:
+            cpu_base, _ = cpu_loop(T, md, hf, max(64, 2 * cores), pool, cores)
+
+    if rank == 0:
+        line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+                'warmup': max(args.warmup, 3), 'ms_per_step': ms_dev / args.steps, 'higher_is_better': True,
+                'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
+                'data': 'synthetic (T0, Mdot, h) grid; reference solar SED and HD 209458 b geometry',
+                'config': config(world),
+                'e2e': {'value': e2e, 'unit': UNIT, 'ms_per_step': ms_e2e / args.steps,
+                        'h2d_bytes_per_step': int(h_in.numel() * 8),
+                        'd2h_bytes_per_step': int(h_spec.numel() * 8 + h_chi2.numel() * 8 + h_status.numel() * 4),
+                        'api': 'p_winds_b200.engine.Engine.forward_batch + chi2_batch (C ABI pwb_forward_batch), '
+                               'pinned host buffers in and out'},
+                'gpu_launches': int(launches), 'clocks': sampler.summary(), 'roofline': roofline,
+                'cpu_baseline': cpu_base,
+                'models_ok_frac': n_ok / B, 'wall_s_timed_region': wall_dev}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == '__main__':
+    main()

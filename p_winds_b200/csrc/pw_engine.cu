@@ -486,7 +486,7 @@ int pwb_h_ion_fraction_batch(pwb_ctx* c, int B, const double* d_T, const double*
 static int he_lanes(pwb_ctx* c, int B) {
   // spread the independent serial solves over the warp schedulers (4 per SM), a few
   // warps deep, before packing more models into one warp
-  const long long target_warps = (long long)c->sm_count * 4 * 4;
+  const long long target_warps = (long long)c->sm_count * 4 * 2;
   long long lanes = (B + target_warps - 1) / target_warps;
   if (lanes < 1) lanes = 1;
   if (lanes > 32) lanes = 32;
