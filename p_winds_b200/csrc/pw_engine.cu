@@ -484,9 +484,11 @@ int pwb_h_ion_fraction_batch(pwb_ctx* c, int B, const double* d_T, const double*
 }
 
 static int he_lanes(pwb_ctx* c, int B) {
-  // spread the independent serial solves over the warp schedulers (4 per SM), a few
-  // warps deep, before packing more models into one warp
-  const long long target_warps = (long long)c->sm_count * 4 * 2;
+  // Models per warp.  The solve is a long dependent chain (latency bound), so small
+  // batches are spread one warp per scheduler (4 per SM) before models are packed into
+  // the lanes of a warp; measured on B200 for 4096 models: 6-12 lanes 136-139 ms,
+  // 1 lane 167 ms (issue/I-cache contention), 32 lanes 180 ms (divergence).
+  const long long target_warps = (long long)c->sm_count * 4;
   long long lanes = (B + target_warps - 1) / target_warps;
   if (lanes < 1) lanes = 1;
   if (lanes > 32) lanes = 32;

@@ -279,39 +279,38 @@ PW_HD void he_population_model(const HeParams& p, const LsodaTables& tab, const 
   double* p1 = w.w + nr;
   double* p3 = w.w + 2 * nr;
   double* ytmp = w.w + 3 * nr;
-  bool ok = he_solve(p, rhs, tab, nr, f1, f3, ytmp, &nfe, &nst, &nje);
-  if (!ok) {
-    status = PW_FAIL_HE_SOLVER;  // helium.py:693-697, :708-710
-  } else {
-    clamp();
-    if (p.relax) {
-      for (int it = 0; it < p.max_n_relax; ++it) {
-        ++n_relax;
-        // new optical depths from the current populations (:729-732); keep the sums
-        // of the previous profiles for the convergence test (:753-756)
-        double c1 = 0.0, c3 = 0.0, s1 = 0.0, s3 = 0.0;
-        for (int i = nr - 1; i >= 0; --i) {
-          c1 += w.w[i] * f1[i];
-          c3 += w.w[i] * f3[i];
-          w.tau1[i] = k2 * a_1 * c1 + w.tau1h[i];
-          w.tau3[i] = k2 * a_3 * c3 + w.tau3h[i];
-        }
-        for (int i = 0; i < nr; ++i) { s1 += f1[i]; s3 += f3[i]; p1[i] = f1[i]; p3[i] = f3[i]; }
-        ok = he_solve(p, rhs, tab, nr, f1, f3, ytmp, &nfe, &nst, &nje);
-        if (!ok) {
-          if (p.method == PW_HE_ODEINT) {
-            status = PW_WARN_HE_RELAX;  // helium.py:736 is outside the warnings->error guard
-          } else {
-            status = PW_FAIL_HE_SOLVER;  // solve_ivp returned a short array -> shape error downstream
-            break;
-          }
-        }
-        clamp();
-        double d1 = 0.0, d3 = 0.0;
-        for (int i = 0; i < nr; ++i) { d1 += f1[i] - p1[i]; d3 += f3[i] - p3[i]; }
-        const double rel1 = fabs(d1) / s1, rel3 = fabs(d3) / s3;
-        if (rel1 < p.convergence && rel3 < p.convergence) break;
+  // pass 0 = the first solve (helium.py:688-718); passes 1..max_n_relax = the relax loop
+  // (:723-763).  One call site keeps a single copy of the integrator in the kernel.
+  const int n_pass = p.relax ? p.max_n_relax + 1 : 1;
+  for (int it = 0; it < n_pass; ++it) {
+    double s1 = 0.0, s3 = 0.0;
+    if (it > 0) {
+      ++n_relax;
+      // new optical depths from the current populations (:729-732); keep the previous
+      // profiles for the convergence test (:753-756)
+      double c1 = 0.0, c3 = 0.0;
+      for (int i = nr - 1; i >= 0; --i) {
+        c1 += w.w[i] * f1[i];
+        c3 += w.w[i] * f3[i];
+        w.tau1[i] = k2 * a_1 * c1 + w.tau1h[i];
+        w.tau3[i] = k2 * a_3 * c3 + w.tau3h[i];
       }
+      for (int i = 0; i < nr; ++i) { s1 += f1[i]; s3 += f3[i]; p1[i] = f1[i]; p3[i] = f3[i]; }
+    }
+    const bool ok = he_solve(p, rhs, tab, nr, f1, f3, ytmp, &nfe, &nst, &nje);
+    if (!ok) {
+      if (it == 0 || p.method != PW_HE_ODEINT) {
+        status = PW_FAIL_HE_SOLVER;  // helium.py:693-697, :708-710 (short solve_ivp output)
+        break;
+      }
+      status = PW_WARN_HE_RELAX;     // helium.py:736 is outside the warnings->error guard
+    }
+    clamp();
+    if (it > 0) {
+      double d1 = 0.0, d3 = 0.0;
+      for (int i = 0; i < nr; ++i) { d1 += f1[i] - p1[i]; d3 += f3[i] - p3[i]; }
+      const double rel1 = fabs(d1) / s1, rel3 = fabs(d3) / s3;
+      if (rel1 < p.convergence && rel3 < p.convergence) break;
     }
   }
   if (status == PW_FAIL_HE_SOLVER) {
