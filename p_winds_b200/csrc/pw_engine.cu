@@ -28,6 +28,7 @@
 #include "pw_hydrogen.cuh"
 #include "pw_helium.cuh"
 #include "pw_transit.cuh"
+#include "pw_draw.cuh"
 
 using namespace pw;
 
@@ -66,6 +67,10 @@ struct pwb_ctx {
   DevBuf px_lo, px_whi, px_wlo, px_i0, px_meta, geo_r;
   double geo_s_out = 0.0;
   bool geo_ready = false;
+  // internal streams for the chunked forward pipeline
+  static const int kMaxChunks = 4;
+  cudaStream_t streams[kMaxChunks] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_start = nullptr, ev_done[kMaxChunks] = {nullptr, nullptr, nullptr, nullptr};
   // scratch
   DevBuf he_work, rt_ncol, rt_sums, rt_partial, fw_f, fw_scal, fw_he, fw_n, fw_v, fw_T, misc;
 };
@@ -266,7 +271,7 @@ k_rt_los(int B, const double* __restrict__ r, const double* __restrict__ n, cons
   rt_los_average(sr, sn, sv, t_is_profile ? st : nullptr, nr, nz, ncol + (size_t)b * nr, sums + (size_t)b * 4, red);
 }
 
-// grid = (lambda tiles, pixel splits, B).  Thread <-> wavelength bin; every thread
+// grid = (B, pixel splits, lambda tiles).  Thread <-> wavelength bin; every thread
 // accumulates sum_p I0_p exp(-N_p Phi_lambda) over its split of the active pixels.
 // Pixels are staged through shared memory in chunks with their interpolated column
 // density, so the inner loop is 2 LDS + 1 DMUL + exp + 1 DFMA per (pixel, lambda).
@@ -279,8 +284,8 @@ k_rt_sum(int B, int nw, int nr, pwb_rt_opts o, const double* __restrict__ wl, co
          double* tau_out /*[B][nr][nw] or null*/) {
   __shared__ double s_ncol[1024];
   __shared__ double s_np[PW_RT_CHUNK], s_i0[PW_RT_CHUNK];
-  const int b = blockIdx.z, split = blockIdx.y;
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;  // wavelength index
+  const int b = blockIdx.x, split = blockIdx.y;
+  const int k = blockIdx.z * blockDim.x + threadIdx.x;  // wavelength index
   const bool bad = status && status[b] != PW_OK && status[b] != PW_WARN_HE_RELAX;
   if (bad) {
     if (k < nw) out[((size_t)b * nsplit + split) * nw + k] = (split == 0) ? nan("") : 0.0;
@@ -355,6 +360,94 @@ __global__ void k_chi2(int B, int nw, const double* __restrict__ spec, const dou
   }
 }
 
+
+// ------------------------------------------------------------------------------------
+// transit.draw_transit (transit.py:20-116) with flatstar's rasteriser restated:
+// star and planet disks are the pixel spans of Pillow's ImageDraw.ellipse (integer walk
+// done on the host, O(grid) work), limb darkening per super-sampled pixel, flux
+// conserving box re-binning (the reference's default resample method).
+// ------------------------------------------------------------------------------------
+struct DrawParams {
+  int n;            // super-sampled grid size
+  int g;            // output grid size
+  int ss;           // n / g
+  double cen, r_star;
+  int law;
+  double c[4];
+};
+
+__device__ __forceinline__ double limb_darkening(int law, const double* c, double mu) {
+  switch (law) {
+    case 1: return 1 - c[0] * (1 - mu);
+    case 2: return 1 - c[0] * (1 - mu) - c[1] * ((1 - mu) * (1 - mu));
+    case 3: return 1 - c[0] * (1 - mu) - c[1] * (1 - sqrt(mu));
+    case 4: return 1 - c[0] * (1 - mu) - c[1] * ((mu > 0) ? mu * log(mu) : 0.0);
+    case 5: return 1 - c[0] * (1 - mu) - c[1] / (1 - exp(mu));
+    case 6: return 1 - c[0] * (1 - mu) - c[1] * (1 - mu * sqrt(mu)) - c[2] * (1 - mu * mu);
+    case 7: return 1 - c[0] * (1 - sqrt(mu)) - c[1] * (1 - mu) - c[2] * (1 - mu * sqrt(mu)) - c[3] * (1 - mu * mu);
+    default: return 1.0;
+  }
+}
+
+__device__ __forceinline__ void draw_pixel(const DrawParams& p, const int* __restrict__ spans, int row, int col,
+                                           double* star, double* lit) {
+  // spans: [4][n] = star_lo, star_hi, planet_lo, planet_hi per row (hi < lo: empty)
+  const int n = p.n;
+  double in = 0.0, tr = 0.0;
+  if (col >= spans[row] && col <= spans[n + row]) {
+    const double dx = col - p.cen, dy = row - p.cen;
+    double m2 = 1 - (dx * dx + dy * dy) / (p.r_star * p.r_star);
+    m2 = fmin(fmax(m2, 0.0), 1.0);
+    in = limb_darkening(p.law, p.c, sqrt(m2));
+    const bool behind = col >= spans[2 * n + row] && col <= spans[3 * n + row];
+    tr = behind ? in * 0.0 : in;   // inten * (1 - planet): keeps a NaN of the 'exp' law like numpy
+  }
+  *star = in;
+  *lit = tr;
+}
+
+// per-block partial sums of the star and of the transit image over the super-sampled grid
+__global__ void k_draw_sums(DrawParams p, const int* __restrict__ spans, double* partial) {
+  __shared__ double red[40];
+  double s_in = 0.0, s_tr = 0.0;
+  const long long tot = (long long)p.n * p.n;
+  for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < tot; q += (long long)gridDim.x * blockDim.x) {
+    double a, b;
+    draw_pixel(p, spans, (int)(q / p.n), (int)(q % p.n), &a, &b);
+    s_in += a; s_tr += b;
+  }
+  const double t_in = block_sum(s_in, red);
+  const double t_tr = block_sum(s_tr, red);
+  if (threadIdx.x == 0) { partial[2 * blockIdx.x] = t_in; partial[2 * blockIdx.x + 1] = t_tr; }
+}
+
+__global__ void k_draw_total(int nblocks, const double* __restrict__ partial, double* total) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    double a = 0.0, b = 0.0;
+    for (int i = 0; i < nblocks; ++i) { a += partial[2 * i]; b += partial[2 * i + 1]; }
+    total[0] = a; total[1] = b;
+  }
+}
+
+// one thread per output pixel: box sum of its ss x ss block, normalised; radius map
+__global__ void k_draw_bin(DrawParams p, const int* __restrict__ spans, const double* __restrict__ total,
+                           double x_p, double y_p, double px_size, double* i0, double* r_map) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= p.g * p.g) return;
+  const int row = q / p.g, col = q % p.g;
+  const double norm = total[0];
+  double acc = 0.0;
+  for (int a = 0; a < p.ss; ++a)
+    for (int b = 0; b < p.ss; ++b) {
+      double in, tr;
+      draw_pixel(p, spans, row * p.ss + a, col * p.ss + b, &in, &tr);
+      acc += tr / norm;
+    }
+  i0[q] = acc;
+  const double dx = col - x_p, dy = row - y_p;
+  r_map[q] = sqrt(dx * dx + dy * dy) * px_size;
+}
+
 // FP64 peak probe: 8 independent DFMA chains per thread
 __global__ void k_fp64_peak(double* out, int iters) {
   double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
@@ -373,6 +466,7 @@ __global__ void k_mu0(int B, const double* __restrict__ hfrac, double* mu0) {
   const double he_h = (1 - hfrac[b]) / hfrac[b];
   mu0[b] = (1 + 4 * he_h) / (1 + he_h + 0.0);
 }
+
 
 // ------------------------------------------------------------------------------------
 // C ABI
@@ -396,6 +490,11 @@ int pwb_create(int device, pwb_ctx** out) {
   k_lsoda_tables<<<1, 32>>>(c->lsoda_tab.as<LsodaTables>());
   c->launches++;
   if (cudaDeviceSynchronize() != cudaSuccess) { delete c; return -6; }
+  for (int i = 0; i < pwb_ctx::kMaxChunks; ++i) {
+    cudaStreamCreateWithFlags(&c->streams[i], cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming);
+  }
+  cudaEventCreateWithFlags(&c->ev_start, cudaEventDisableTiming);
   cudaFuncSetAttribute(k_hydrogen, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   cudaFuncSetAttribute(k_rt_los, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
   *out = c;
@@ -409,6 +508,11 @@ void pwb_destroy(pwb_ctx* c) {
                     &c->px_wlo, &c->px_i0, &c->px_meta, &c->geo_r, &c->he_work, &c->rt_ncol, &c->rt_sums,
                     &c->rt_partial, &c->fw_f, &c->fw_scal, &c->fw_he, &c->fw_n, &c->fw_v, &c->fw_T, &c->misc};
   for (DevBuf* b : bufs) b->release();
+  for (int i = 0; i < pwb_ctx::kMaxChunks; ++i) {
+    if (c->streams[i]) cudaStreamDestroy(c->streams[i]);
+    if (c->ev_done[i]) cudaEventDestroy(c->ev_done[i]);
+  }
+  if (c->ev_start) cudaEventDestroy(c->ev_start);
   delete c;
 }
 
@@ -497,6 +601,19 @@ static int he_lanes(pwb_ctx* c, int B) {
   return (int)lanes;
 }
 
+static int launch_helium(pwb_ctx* c, cudaStream_t s, int B, int lanes, const double* d_T, const double* d_hfrac,
+                         const double* d_vs, const double* d_rs, const double* d_rhos, int sstride,
+                         const double* d_r, int Nr, const double* d_v, const double* d_rho, const double* d_f_h,
+                         const pwb_he_opts* o, double* work, double* d_f1, double* d_f3, double* d_scal,
+                         double* d_rates, int* d_status) {
+  const int blocks = (B + lanes - 1) / lanes;
+  k_helium<<<blocks, 32, 0, s>>>(B, lanes, d_T, d_hfrac, d_vs, d_rs, d_rhos, sstride, d_r, Nr, d_v, d_rho, d_f_h,
+                                 *o, c->lsoda_tab.as<LsodaTables>(), work, d_f1, d_f3, d_scal, d_rates, d_status);
+  c->launches++;
+  PWB_CUDA(c, cudaGetLastError());
+  return 0;
+}
+
 int pwb_he_population_batch(pwb_ctx* c, int B, const double* d_T, const double* d_hfrac,
                             const double* d_vs, const double* d_rs, const double* d_rhos,
                             int sstride, const double* d_r, int Nr, const double* d_v,
@@ -508,14 +625,8 @@ int pwb_he_population_batch(pwb_ctx* c, int B, const double* d_T, const double* 
   if (Nr < 2) return fail(c, "pwb_he_population_batch: radius profile needs >= 2 points");
   if (o->method < 0 || o->method > 2) return fail(c, "pwb_he_population_batch: unsupported method");
   if (c->he_work.ensure(sizeof(double) * 10 * (size_t)Nr * B)) return fail(c, "out of device memory");
-  const int lanes = he_lanes(c, B);
-  const int blocks = (B + lanes - 1) / lanes;
-  k_helium<<<blocks, 32, 0, (cudaStream_t)stream>>>(
-      B, lanes, d_T, d_hfrac, d_vs, d_rs, d_rhos, sstride, d_r, Nr, d_v, d_rho, d_f_h, *o,
-      c->lsoda_tab.as<LsodaTables>(), c->he_work.as<double>(), d_f1, d_f3, d_scal, d_rates, d_status);
-  c->launches++;
-  PWB_CUDA(c, cudaGetLastError());
-  return 0;
+  return launch_helium(c, (cudaStream_t)stream, B, he_lanes(c, B), d_T, d_hfrac, d_vs, d_rs, d_rhos, sstride, d_r,
+                       Nr, d_v, d_rho, d_f_h, o, c->he_work.as<double>(), d_f1, d_f3, d_scal, d_rates, d_status);
 }
 
 int pwb_set_geometry(pwb_ctx* c, const double* d_i0, const double* d_r_map, int npix,
@@ -541,39 +652,37 @@ int pwb_set_geometry(pwb_ctx* c, const double* d_i0, const double* d_r_map, int 
   return 0;
 }
 
-int pwb_rt2d_batch(pwb_ctx* c, int B, const double* d_n, const double* d_v, const double* d_T,
-                   const double* d_wl, int Nw, const pwb_rt_opts* o, const int* d_status,
-                   double* d_spectrum, double* d_tau, void* stream) {
-  if (!c) return -1;
-  if (B <= 0) return 0;
+static int rt_nsplit(const pwb_ctx* c) {
+  // The active pixels are always cut into the same segments, whatever the batch size,
+  // so that a model's spectrum is bit-identical alone or inside a grid (the partial
+  // sums are combined in a fixed order by k_rt_reduce).  <= 16 segments of >= 1024 pixels.
+  return std::min(16, std::max(1, (c->n_active + 1023) / 1024));
+}
+
+static int rt_check(pwb_ctx* c, const pwb_rt_opts* o) {
   if (!c->geo_ready) return fail(c, "pwb_rt2d_batch: call pwb_set_geometry first");
   if (o->n_lines < 1 || o->n_lines > 8) return fail(c, "pwb_rt2d_batch: 1..8 spectral lines supported");
   if (o->wind_broadening_method != 0)
     return fail(c, "The chosen ``wind_broadening_method`` is not implemented on the GPU path yet ('average' only).");
   if (o->z_grid_size < 2) return fail(c, "pwb_rt2d_batch: z_grid_size must be >= 2");
-  cudaStream_t s = (cudaStream_t)stream;
+  return 0;
+}
+
+static int launch_rt(pwb_ctx* c, cudaStream_t s, int B, const double* d_n, const double* d_v, const double* d_T,
+                     const double* d_wl, int Nw, const pwb_rt_opts* o, const int* d_status, double* d_spectrum,
+                     double* d_tau, double* ncol, double* sums, double* partial) {
   const int Nr = c->geo_nr;
-  if (c->rt_ncol.ensure(sizeof(double) * (size_t)B * Nr) || c->rt_sums.ensure(sizeof(double) * (size_t)B * 4))
-    return fail(c, "out of device memory");
   k_rt_los<<<B, 256, sizeof(double) * (4 * (size_t)Nr + 40), s>>>(
-      B, c->geo_r.as<double>(), d_n, d_v, d_T, o->temperature_is_profile, Nr, o->z_grid_size, d_status,
-      c->rt_ncol.as<double>(), c->rt_sums.as<double>());
+      B, c->geo_r.as<double>(), d_n, d_v, d_T, o->temperature_is_profile, Nr, o->z_grid_size, d_status, ncol, sums);
   c->launches++;
   PWB_CUDA(c, cudaGetLastError());
   const int tiles = (Nw + 255) / 256;
-  // The active pixels are always cut into the same segments, whatever the batch size,
-  // so that a model's spectrum is bit-identical alone or inside a grid (the partial
-  // sums are combined in a fixed order by k_rt_reduce).  <= 16 segments of >= 1024 pixels.
-  int nsplit = std::min(16, std::max(1, (c->n_active + 1023) / 1024));
-  double* part = d_spectrum;
-  if (nsplit > 1) {
-    if (c->rt_partial.ensure(sizeof(double) * (size_t)B * nsplit * Nw)) return fail(c, "out of device memory");
-    part = c->rt_partial.as<double>();
-  }
-  dim3 grid(tiles, nsplit, B);
-  k_rt_sum<<<grid, 256, 0, s>>>(B, Nw, Nr, *o, d_wl, d_T, c->rt_ncol.as<double>(), c->rt_sums.as<double>(),
-                                d_status, c->px_lo.as<int>(), c->px_whi.as<double>(), c->px_wlo.as<double>(),
-                                c->px_i0.as<double>(), c->px_meta.as<double>(), nsplit, part, d_tau);
+  const int nsplit = rt_nsplit(c);
+  double* part = (nsplit > 1) ? partial : d_spectrum;
+  dim3 grid(B, nsplit, tiles);
+  k_rt_sum<<<grid, 256, 0, s>>>(B, Nw, Nr, *o, d_wl, d_T, ncol, sums, d_status, c->px_lo.as<int>(),
+                                c->px_whi.as<double>(), c->px_wlo.as<double>(), c->px_i0.as<double>(),
+                                c->px_meta.as<double>(), nsplit, part, d_tau);
   c->launches++;
   PWB_CUDA(c, cudaGetLastError());
   if (nsplit > 1) {
@@ -585,6 +694,21 @@ int pwb_rt2d_batch(pwb_ctx* c, int B, const double* d_n, const double* d_v, cons
   return 0;
 }
 
+int pwb_rt2d_batch(pwb_ctx* c, int B, const double* d_n, const double* d_v, const double* d_T,
+                   const double* d_wl, int Nw, const pwb_rt_opts* o, const int* d_status,
+                   double* d_spectrum, double* d_tau, void* stream) {
+  if (!c) return -1;
+  if (B <= 0) return 0;
+  if (rt_check(c, o)) return -1;
+  const int Nr = c->geo_nr;
+  const int nsplit = rt_nsplit(c);
+  if (c->rt_ncol.ensure(sizeof(double) * (size_t)B * Nr) || c->rt_sums.ensure(sizeof(double) * (size_t)B * 4) ||
+      (nsplit > 1 && c->rt_partial.ensure(sizeof(double) * (size_t)B * nsplit * Nw)))
+    return fail(c, "out of device memory");
+  return launch_rt(c, (cudaStream_t)stream, B, d_n, d_v, d_T, d_wl, Nw, o, d_status, d_spectrum, d_tau,
+                   c->rt_ncol.as<double>(), c->rt_sums.as<double>(), c->rt_partial.as<double>());
+}
+
 int pwb_forward_batch(pwb_ctx* c, int B, const double* d_T, const double* d_mdot,
                       const double* d_hfrac, const double* d_r, int Nr, const pwb_h_opts* hopts,
                       const pwb_he_opts* heopts, const pwb_rt_opts* rtopts, int species,
@@ -594,12 +718,21 @@ int pwb_forward_batch(pwb_ctx* c, int B, const double* d_T, const double* d_mdot
   if (!c) return -1;
   if (B <= 0) return 0;
   if (!d_spectrum || !d_status) return fail(c, "pwb_forward_batch: d_spectrum and d_status are required");
+  if (Nr < 2) return fail(c, "pwb_forward_batch: radius profile needs >= 2 points");
+  if (hopts->exact_phi && !c->sed_ready) return fail(c, "pwb_forward_batch: exact_phi needs pwb_set_sed");
+  if (species == 0 && (heopts->method < 0 || heopts->method > 2)) return fail(c, "unsupported helium method");
+  if (rt_check(c, rtopts)) return -1;
+  if (c->geo_nr != Nr) return fail(c, "pwb_forward_batch: pwb_set_geometry was called with a different radius grid");
   cudaStream_t s = (cudaStream_t)stream;
   const size_t bn = (size_t)B * Nr;
-  // scratch for outputs the caller did not ask for: f_r, f1, f3, v, rho
-  if (c->fw_f.ensure(sizeof(double) * bn * 6) || c->fw_scal.ensure(sizeof(double) * (size_t)B * 8) ||
+  const int nsplit = rt_nsplit(c);
+  // scratch for the whole batch; every chunk works on its own slice
+  if (c->fw_f.ensure(sizeof(double) * (bn * 5 + B)) || c->fw_scal.ensure(sizeof(double) * (size_t)B * 8) ||
       c->fw_he.ensure(sizeof(double) * (size_t)B * 4) || c->fw_n.ensure(sizeof(double) * bn) ||
-      c->fw_v.ensure(sizeof(double) * bn) || c->fw_T.ensure(sizeof(double) * B))
+      c->fw_v.ensure(sizeof(double) * bn) || c->fw_T.ensure(sizeof(double) * B) ||
+      c->he_work.ensure(sizeof(double) * 10 * bn) || c->rt_ncol.ensure(sizeof(double) * bn) ||
+      c->rt_sums.ensure(sizeof(double) * (size_t)B * 4) ||
+      (nsplit > 1 && c->rt_partial.ensure(sizeof(double) * (size_t)B * nsplit * Nw)))
     return fail(c, "out of device memory");
   double* base = c->fw_f.as<double>();
   double* f_r = d_f_r ? d_f_r : base;
@@ -610,24 +743,56 @@ int pwb_forward_batch(pwb_ctx* c, int B, const double* d_T, const double* d_mdot
   double* mu0 = base + 5 * bn;  // [B]
   double* hscal = d_hscal ? d_hscal : c->fw_scal.as<double>();
   double* hescal = d_hescal ? d_hescal : c->fw_he.as<double>();
-  // mu_0 of a neutral H/He mix (quickstart.ipynb cell 2)
-  k_mu0<<<(B + 255) / 256, 256, 0, s>>>(B, d_hfrac, mu0);
-  c->launches++;
-  int rc = pwb_h_ion_fraction_batch(c, B, d_T, d_mdot, d_hfrac, mu0, d_r, Nr, hopts, f_r, v, rho, hscal,
-                                    d_status, stream);
-  if (rc) return rc;
-  if (species == 0) {
-    rc = pwb_he_population_batch(c, B, d_T, d_hfrac, hscal + 1, hscal + 2, hscal + 3, 8, d_r, Nr, v, rho, f_r,
-                                 heopts, f1, f3, hescal, nullptr, d_status, stream);
-    if (rc) return rc;
+  const int n_h = c->sed_ready ? c->sed_nh : 0;
+  const size_t work = sizeof(double) * (10 * (size_t)Nr + 40), tab = sizeof(double) * 3 * (size_t)n_h;
+  const int in_smem = (hopts->exact_phi && work + tab <= 160 * 1024) ? 1 : 0;
+  const size_t smem = work + (in_smem ? tab : 0);
+  if (smem > 200 * 1024) return fail(c, "pwb_forward_batch: radius profile too long for shared memory");
+
+  // The helium stage is a long serial solve per model whose slowest members leave most
+  // of the GPU idle; cutting the batch into chunks on separate streams lets the H and RT
+  // stages of one chunk run under the helium tail of another.
+  int nchunk = std::min<int>(pwb_ctx::kMaxChunks, std::max(1, B / 512));
+  nchunk = 1;  // measured on B200 (64x64 grid): 1 chunk 175 ms, 2 chunks 197 ms, 4 chunks 191 ms -- the H stage of
+               // the next chunk steals issue slots from the latency-critical helium warps; kept as a knob
+  { const char* e = getenv("PWB_CHUNKS"); if (e) { int q = atoi(e); if (q >= 1 && q <= pwb_ctx::kMaxChunks) nchunk = q; } }
+  const int lanes = he_lanes(c, B);
+  const int per = (B + nchunk - 1) / nchunk;
+  PWB_CUDA(c, cudaEventRecord(c->ev_start, s));
+  for (int q = 0; q < nchunk; ++q) {
+    const int b0 = q * per, nb = std::min(per, B - b0);
+    if (nb <= 0) { nchunk = q; break; }
+    cudaStream_t cs = (nchunk == 1) ? s : c->streams[q];
+    if (nchunk > 1) PWB_CUDA(c, cudaStreamWaitEvent(cs, c->ev_start, 0));
+    const size_t o1 = (size_t)b0, oN = (size_t)b0 * Nr;
+    k_mu0<<<(nb + 255) / 256, 256, 0, cs>>>(nb, d_hfrac + o1, mu0 + o1);   // quickstart.ipynb cell 2
+    c->launches++;
+    k_hydrogen<<<nb, 128, smem, cs>>>(nb, d_T + o1, d_mdot + o1, d_hfrac + o1, mu0 + o1, d_r, Nr, *hopts,
+                                      c->sed_gw.as<double>(), c->sed_sh.as<double>(), c->sed_she.as<double>(), n_h,
+                                      in_smem, f_r + oN, v + oN, rho + oN, hscal + o1 * 8, d_status + o1);
+    c->launches++;
+    PWB_CUDA(c, cudaGetLastError());
+    if (species == 0) {
+      if (launch_helium(c, cs, nb, lanes, d_T + o1, d_hfrac + o1, hscal + o1 * 8 + 1, hscal + o1 * 8 + 2,
+                        hscal + o1 * 8 + 3, 8, d_r, Nr, v + oN, rho + oN, f_r + oN, heopts,
+                        c->he_work.as<double>() + 10 * oN, f1 + oN, f3 + oN, hescal + o1 * 4, nullptr, d_status + o1))
+        return -1;
+    }
+    k_he_density<<<(unsigned)(((size_t)nb * Nr + 255) / 256), 256, 0, cs>>>(
+        nb, Nr, species, d_hfrac + o1, hscal + o1 * 8, f_r + oN, f3 + oN, rho + oN, v + oN, d_T + o1,
+        c->fw_n.as<double>() + oN, c->fw_v.as<double>() + oN, c->fw_T.as<double>() + o1);
+    c->launches++;
+    PWB_CUDA(c, cudaGetLastError());
+    if (launch_rt(c, cs, nb, c->fw_n.as<double>() + oN, c->fw_v.as<double>() + oN, c->fw_T.as<double>() + o1, d_wl,
+                  Nw, rtopts, d_status + o1, d_spectrum + o1 * Nw, nullptr, c->rt_ncol.as<double>() + oN,
+                  c->rt_sums.as<double>() + o1 * 4, c->rt_partial.as<double>() + o1 * nsplit * Nw))
+      return -1;
+    if (nchunk > 1) {
+      PWB_CUDA(c, cudaEventRecord(c->ev_done[q], cs));
+      PWB_CUDA(c, cudaStreamWaitEvent(s, c->ev_done[q], 0));
+    }
   }
-  k_he_density<<<(unsigned)((bn + 255) / 256), 256, 0, s>>>(B, Nr, species, d_hfrac, hscal, f_r, f3, rho, v, d_T,
-                                                          c->fw_n.as<double>(), c->fw_v.as<double>(),
-                                                          c->fw_T.as<double>());
-  c->launches++;
-  PWB_CUDA(c, cudaGetLastError());
-  return pwb_rt2d_batch(c, B, c->fw_n.as<double>(), c->fw_v.as<double>(), c->fw_T.as<double>(), d_wl, Nw, rtopts,
-                        d_status, d_spectrum, nullptr, stream);
+  return 0;
 }
 
 int pwb_chi2_batch(pwb_ctx* c, int B, const double* d_spectrum, int Nw, const double* d_data,
@@ -666,9 +831,41 @@ int pwb_fp64_peak(pwb_ctx* c, double* tflops, void* stream) {
   return 0;
 }
 
-int pwb_draw_transit(pwb_ctx* c, double, double, double, double, int, int, int, const double*, double*,
-                     double*, double*, void*) {
-  return fail(c, "pwb_draw_transit: not built yet");
+int pwb_draw_transit(pwb_ctx* c, double k, double r_phys, double b, double phase, int grid_size,
+                     int supersampling, int ld_law, const double* ld, double* d_i0, double* d_r_map,
+                     double* transit_depth, void* stream) {
+  if (!c) return -1;
+  if (grid_size < 2 || supersampling < 1 || ld_law < 0 || ld_law > 7)
+    return fail(c, "pwb_draw_transit: bad grid_size / supersampling / limb-darkening law");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int n = grid_size * supersampling;
+  DrawParams p;
+  p.n = n; p.g = grid_size; p.ss = supersampling; p.cen = n / 2.0; p.r_star = n * 0.5; p.law = ld_law;
+  for (int i = 0; i < 4; ++i) p.c[i] = ld ? ld[i] : 0.0;
+  double r_p = p.r_star * k;
+  double x_p = n / 2.0 + 2 * phase * p.r_star;
+  double y_p = n / 2.0 + b * p.r_star;
+  std::vector<int> spans(4 * (size_t)n);
+  pil_ellipse_rows(p.cen - p.r_star, p.cen - p.r_star, p.cen + p.r_star, p.cen + p.r_star, n, &spans[0], &spans[n]);
+  pil_ellipse_rows(x_p - r_p, y_p - r_p, x_p + r_p, y_p + r_p, n, &spans[2 * n], &spans[3 * n]);
+  const int nblocks = c->sm_count * 4;
+  if (c->misc.ensure(sizeof(int) * 4 * (size_t)n + sizeof(double) * (2 * (size_t)nblocks + 2) + 64))
+    return fail(c, "out of device memory");
+  double* partial = c->misc.as<double>();
+  double* total = partial + 2 * nblocks;
+  int* d_spans = (int*)(total + 2);
+  PWB_CUDA(c, cudaMemcpyAsync(d_spans, spans.data(), sizeof(int) * 4 * (size_t)n, cudaMemcpyHostToDevice, s));
+  k_draw_sums<<<nblocks, 256, 0, s>>>(p, d_spans, partial);
+  k_draw_total<<<1, 32, 0, s>>>(nblocks, partial, total);
+  if (supersampling > 1) { const double f = 1.0 / supersampling; x_p *= f; y_p *= f; r_p *= f; }
+  k_draw_bin<<<(grid_size * grid_size + 255) / 256, 256, 0, s>>>(p, d_spans, total, x_p, y_p, r_phys / r_p, d_i0, d_r_map);
+  c->launches += 3;
+  PWB_CUDA(c, cudaGetLastError());
+  double tot[2];
+  PWB_CUDA(c, cudaMemcpyAsync(tot, total, sizeof tot, cudaMemcpyDeviceToHost, s));
+  PWB_CUDA(c, cudaStreamSynchronize(s));   // also keeps `spans` alive until the copy is done
+  if (transit_depth) *transit_depth = 1 - tot[1] / tot[0];
+  return 0;
 }
 
 }  // extern "C"

@@ -174,3 +174,9 @@ void hs_tau_average(const double* r, const double* n, const double* v, const dou
 }
 
 }  // extern "C"
+
+#include "../../p_winds_b200/csrc/pw_draw.cuh"
+
+extern "C" void hs_pil_ellipse_rows(double x0, double y0, double x1, double y1, int n, int* lo, int* hi) {
+  pw::pil_ellipse_rows(x0, y0, x1, y1, n, lo, hi);
+}

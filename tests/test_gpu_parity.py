@@ -353,3 +353,43 @@ def test_edge_cases(eng):
     assert np.array_equal(a['f_3'][0], b['f_3'][1])
     with pytest.raises(ValueError, match='no CPU fallback'):
         Engine.he_opts(1.39, [0] * 6, method='BDF')
+
+
+# --------------------------------------------------------------------------- draw_transit
+def test_draw_transit_reference_signature(eng, oracle):
+    """reference tests/test_transit.py:28-39 through transit.draw_transit, plus the
+    quickstart geometry and the limb-darkening laws (fixtures from the reference with the
+    recovered flatstar rasteriser)."""
+    from p_winds_b200 import transit
+    geo = golden('geometry')
+    i0, depth, rm = transit.draw_transit(planet_to_star_ratio=0.12086, planet_physical_radius=1.39 * 71492000,
+                                         impact_parameter=0.0, phase=0.0, supersampling=10, grid_size=101)
+    assert abs((i0[30, 30] - 1.249219E-4) / i0[30, 30]) < 5e-3
+    assert abs((depth - 0.015012130070238605) / depth) < 5e-3
+    assert abs(depth / geo['test_depth'] - 1) < 1e-12
+    m = geo['test_i0'] != 0
+    assert np.array_equal(i0 != 0, m) and np.max(_rel(i0[m], geo['test_i0'][m])) < 1e-12
+    assert np.max(np.abs(rm - geo['test_r_map'])) < 1e-12 * geo['test_r_map'].max()
+    i0, depth, rm = transit.draw_transit(0.12086, 1.39 * 71492000, 0.499, 0.0, supersampling=10, grid_size=100)
+    m = geo['i0'] != 0
+    assert np.array_equal(i0 != 0, m) and np.max(_rel(i0[m], geo['i0'][m])) < 1e-12
+    assert abs(depth / geo['depth'] - 1) < 1e-12 and abs(i0.sum() - (1 - depth)) < 1e-12
+    assert np.max(np.abs(rm - geo['r_map'])) < 1e-12 * geo['r_map'].max()
+    for law, c in (('linear', 0.5), ('quadratic', [0.3, 0.2]), ('square-root', [0.3, 0.2]), ('log', [0.3, 0.2]),
+                   ('s3', [0.3, 0.2, 0.1]), ('c4', [0.3, 0.2, 0.1, 0.05])):
+        i0, depth, rm = transit.draw_transit(0.1, 1.0, 0.3, -0.2, supersampling=4, grid_size=40,
+                                             limb_darkening_law=law, ld_coefficient=c)
+        ref = geo['ld_%s_map' % law]
+        m = ref != 0
+        assert np.array_equal(i0 != 0, m), law
+        assert np.max(_rel(i0[m], ref[m])) < 1e-11, law
+        assert abs(depth / geo['ld_%s_depth' % law] - 1) < 1e-11, law
+    # no supersampling, planet partly off the disk, vs the oracle run live
+    ref = oracle.draw_transit(0.2, 2.5, 0.7, 0.33, grid_size=64)
+    i0, depth, rm = transit.draw_transit(0.2, 2.5, 0.7, 0.33, grid_size=64)
+    assert 0 < ref[1] < 0.04            # the planet straddles the limb
+    m = ref[0] != 0
+    assert np.array_equal(i0 != 0, m) and np.max(_rel(i0[m], ref[0][m])) < 1e-12
+    assert abs(depth / ref[1] - 1) < 1e-12 and np.max(np.abs(rm - ref[2])) < 1e-12 * ref[2].max()
+    with pytest.raises(ValueError, match='box'):
+        transit.draw_transit(0.1, 1.0, resample_method='lanczos', supersampling=2)

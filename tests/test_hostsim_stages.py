@@ -190,3 +190,26 @@ def test_optical_depth_average_against_reference(hostsim):
     m = ref > 0
     assert np.array_equal(tau[~m], ref[~m])
     assert np.max(np.abs(tau[m] / ref[m] - 1)) < 1e-12
+
+
+def test_pil_ellipse_spans_against_pillow(hostsim, oracle):
+    """The span table behind pwb_draw_transit vs Pillow itself (flatstar's rasteriser)
+    and vs the oracle's restatement, incl. clipping, odd/even diameters, off-grid planets."""
+    from PIL import Image, ImageDraw
+    hostsim.hs_pil_ellipse_rows.argtypes = [C.c_double] * 4 + [C.c_int, C.c_void_p, C.c_void_p]
+    rng = np.random.default_rng(1)
+    cases = [(505.0, 505.0, 505.0, 1010), (505.0, 505.0, 505 * 0.12086, 1010), (50.5, 50.5, 50.5, 101)]
+    for _ in range(60):
+        n = int(rng.integers(20, 400))
+        cases.append((rng.uniform(-0.2, 1.2) * n, rng.uniform(-0.2, 1.2) * n, rng.uniform(0.5, 0.7 * n), n))
+    for cx, cy, rad, n in cases:
+        lo, hi = np.zeros(n, dtype=np.int32), np.zeros(n, dtype=np.int32)
+        hostsim.hs_pil_ellipse_rows(cx - rad, cy - rad, cx + rad, cy + rad, n, P(lo), P(hi))
+        mask = np.zeros((n, n))
+        for r in range(n):
+            if hi[r] >= lo[r]:
+                mask[r, lo[r]:hi[r] + 1] = 1.0
+        im = Image.new('1', (n, n))
+        ImageDraw.Draw(im).ellipse([(cx - rad, cy - rad), (cx + rad, cy + rad)], outline=1, fill=1)
+        assert np.array_equal(mask, np.array(im).astype(float)), (cx, cy, rad, n)
+        assert np.array_equal(mask, oracle._disk((cx, cy), rad, n))
