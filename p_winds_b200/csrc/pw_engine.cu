@@ -72,7 +72,7 @@ struct pwb_ctx {
   cudaStream_t streams[kMaxChunks] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev_start = nullptr, ev_done[kMaxChunks] = {nullptr, nullptr, nullptr, nullptr};
   // scratch
-  DevBuf he_work, rt_ncol, rt_sums, rt_partial, fw_f, fw_scal, fw_he, fw_n, fw_v, fw_T, misc;
+  DevBuf he_work, rt_ncol, rt_sums, rt_partial, rt_tau, fw_f, fw_scal, fw_he, fw_n, fw_v, fw_T, misc;
 };
 
 static int fail(pwb_ctx* c, const char* fmt, const char* a = "") {
@@ -271,6 +271,61 @@ k_rt_los(int B, const double* __restrict__ r, const double* __restrict__ n, cons
   rt_los_average(sr, sn, sv, t_is_profile ? st : nullptr, nr, nz, ncol + (size_t)b * nr, sums + (size_t)b * 4, red);
 }
 
+
+// 'formal' wind broadening (transit.py:463-473, :512-519): per LOS cell Doppler width
+// and wind shift, one Voigt evaluation per (z, b, lambda, line).  grid = (Nr, B); the CTA
+// stages the Nz cells of its impact parameter in shared memory, threads own wavelengths.
+__global__ void __launch_bounds__(256)
+k_rt_formal_tau(int B, int nw, int nr, pwb_rt_opts o, const double* __restrict__ r, const double* __restrict__ n,
+                const double* __restrict__ v, const double* __restrict__ T, const double* __restrict__ wl,
+                const int* __restrict__ status, double* tau /*[B][nr][nw]*/) {
+  extern __shared__ double sm[];  // r, n, v, T (4*nr) | n_c, v_los, T_c, z (4*nz)
+  const int i = blockIdx.x, b = blockIdx.y;
+  if (status && status[b] != PW_OK && status[b] != PW_WARN_HE_RELAX) return;
+  const int nz = o.z_grid_size;
+  double* sr = sm; double* sn = sm + nr; double* sv = sm + 2 * nr; double* st = sm + 3 * nr;
+  double* cn = sm + 4 * nr; double* cv = cn + nz; double* ct = cv + nz; double* cz = ct + nz;
+  const bool tp = o.temperature_is_profile != 0;
+  for (int q = threadIdx.x; q < nr; q += blockDim.x) {
+    sr[q] = r[q]; sn[q] = n[(size_t)b * nr + q]; sv[q] = v[(size_t)b * nr + q];
+    st[q] = tp ? T[(size_t)b * nr + q] : 0.0;
+  }
+  __syncthreads();
+  const double r_top = sr[nr - 1], bb = sr[i];
+  for (int j = threadIdx.x; j < nz; j += blockDim.x) {
+    const double z = los_z(r_top, nz, j);
+    double nc, vl, tc = 0.0;
+    los_cell(sr, sn, sv, tp ? st : nullptr, nr, bb, z, &nc, &vl, tp ? &tc : nullptr);
+    cn[j] = nc; cv[j] = vl; ct[j] = tc; cz[j] = z;
+  }
+  __syncthreads();
+  const double c_speed = 2.99792458e+08, k_b = 1.380649e-23;
+  const double t_scalar = tp ? 0.0 : T[b];
+  for (int k = threadIdx.x; k < nw; k += blockDim.x) {
+    const double nu_rest = c_speed / wl[k];
+    double tot = 0.0;
+    for (int line = 0; line < o.n_lines; ++line) {
+      const double nu0 = c_speed / o.central_wavelength[line];
+      const double gamma = o.einstein_coefficient[line] / 4 / kPi;
+      const double dnu = nu_rest - nu0;
+      const double alpha0 = nu0 / c_speed * sqrt(k_b * t_scalar / o.particle_mass);
+      double acc = 0.0, yprev = 0.0;
+      for (int j = 0; j < nz; ++j) {
+        double y = 0.0;
+        if (cn[j] != 0.0) {
+          const double alpha = tp ? nu0 / c_speed * sqrt(k_b * ct[j] / o.particle_mass) : alpha0;
+          const double add = (cv[j] + o.bulk_los_velocity + o.planet_radial_velocity) / c_speed * nu0;
+          y = voigt_profile(dnu + add, alpha, gamma) * cn[j];
+        }
+        if (j > 0) acc += (cz[j] - cz[j - 1]) * (y + yprev) / 2.0;
+        yprev = y;
+      }
+      tot += acc * (2.654008854574474e-06 * o.oscillator_strength[line]);
+    }
+    tau[((size_t)b * nr + i) * nw + k] = tot;
+  }
+}
+
 // grid = (B, pixel splits, lambda tiles).  Thread <-> wavelength bin; every thread
 // accumulates sum_p I0_p exp(-N_p Phi_lambda) over its split of the active pixels.
 // Pixels are staged through shared memory in chunks with their interpolated column
@@ -281,7 +336,7 @@ k_rt_sum(int B, int nw, int nr, pwb_rt_opts o, const double* __restrict__ wl, co
          const double* __restrict__ ncol, const double* __restrict__ sums, const int* __restrict__ status,
          const int* __restrict__ px_lo, const double* __restrict__ px_whi, const double* __restrict__ px_wlo,
          const double* __restrict__ px_i0, const double* __restrict__ meta, int nsplit, double* out /*[B][nsplit][nw]*/,
-         double* tau_out /*[B][nr][nw] or null*/) {
+         double* tau_out /*[B][nr][nw] or null*/, const double* __restrict__ tau_tab /*'formal': [B][nr][nw]*/) {
   __shared__ double s_ncol[1024];
   __shared__ double s_np[PW_RT_CHUNK], s_i0[PW_RT_CHUNK];
   const int b = blockIdx.x, split = blockIdx.y;
@@ -289,6 +344,27 @@ k_rt_sum(int B, int nw, int nr, pwb_rt_opts o, const double* __restrict__ wl, co
   const bool bad = status && status[b] != PW_OK && status[b] != PW_WARN_HE_RELAX;
   if (bad) {
     if (k < nw) out[((size_t)b * nsplit + split) * nw + k] = (split == 0) ? nan("") : 0.0;
+    return;
+  }
+  if (tau_tab) {
+    // 'formal' broadening: tau(b, lambda) was tabulated by k_rt_formal_tau; interpolate it
+    // per pixel (transit.py:220-222) -- two table reads + exp per (pixel, lambda)
+    const int n_act = (int)meta[0];
+    const int per = (n_act + nsplit - 1) / nsplit;
+    const int p0 = split * per, p1 = min(n_act, p0 + per);
+    double acc = 0.0;
+    if (k < nw) {
+      const double* tb = tau_tab + (size_t)b * nr * nw + k;
+      for (int q = p0; q < p1; ++q) {
+        const int lo = px_lo[q];
+        const double t = px_whi[q] * tb[(size_t)(lo + 1) * nw] + px_wlo[q] * tb[(size_t)lo * nw];
+        acc += px_i0[q] * exp(-t);
+      }
+      if (split == 0) acc += meta[1];
+      out[((size_t)b * nsplit + split) * nw + k] = acc;
+      if (tau_out && split == 0)
+        for (int i = 0; i < nr; ++i) tau_out[((size_t)b * nr + i) * nw + k] = tb[(size_t)i * nw];
+    }
     return;
   }
   for (int i = threadIdx.x; i < nr; i += blockDim.x) s_ncol[i] = ncol[(size_t)b * nr + i];
@@ -497,6 +573,7 @@ int pwb_create(int device, pwb_ctx** out) {
   cudaEventCreateWithFlags(&c->ev_start, cudaEventDisableTiming);
   cudaFuncSetAttribute(k_hydrogen, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   cudaFuncSetAttribute(k_rt_los, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  cudaFuncSetAttribute(k_rt_formal_tau, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
   *out = c;
   return 0;
 }
@@ -506,7 +583,7 @@ void pwb_destroy(pwb_ctx* c) {
   cudaSetDevice(c->device);
   DevBuf* bufs[] = {&c->sed_gw, &c->sed_sh, &c->sed_she, &c->sed_scal, &c->lsoda_tab, &c->px_lo, &c->px_whi,
                     &c->px_wlo, &c->px_i0, &c->px_meta, &c->geo_r, &c->he_work, &c->rt_ncol, &c->rt_sums,
-                    &c->rt_partial, &c->fw_f, &c->fw_scal, &c->fw_he, &c->fw_n, &c->fw_v, &c->fw_T, &c->misc};
+                    &c->rt_partial, &c->rt_tau, &c->fw_f, &c->fw_scal, &c->fw_he, &c->fw_n, &c->fw_v, &c->fw_T, &c->misc};
   for (DevBuf* b : bufs) b->release();
   for (int i = 0; i < pwb_ctx::kMaxChunks; ++i) {
     if (c->streams[i]) cudaStreamDestroy(c->streams[i]);
@@ -662,27 +739,37 @@ static int rt_nsplit(const pwb_ctx* c) {
 static int rt_check(pwb_ctx* c, const pwb_rt_opts* o) {
   if (!c->geo_ready) return fail(c, "pwb_rt2d_batch: call pwb_set_geometry first");
   if (o->n_lines < 1 || o->n_lines > 8) return fail(c, "pwb_rt2d_batch: 1..8 spectral lines supported");
-  if (o->wind_broadening_method != 0)
-    return fail(c, "The chosen ``wind_broadening_method`` is not implemented on the GPU path yet ('average' only).");
+  if (o->wind_broadening_method != 0 && o->wind_broadening_method != 1)
+    return fail(c, "The chosen ``wind_broadening_method`` is not implemented.");
   if (o->z_grid_size < 2) return fail(c, "pwb_rt2d_batch: z_grid_size must be >= 2");
   return 0;
 }
 
 static int launch_rt(pwb_ctx* c, cudaStream_t s, int B, const double* d_n, const double* d_v, const double* d_T,
                      const double* d_wl, int Nw, const pwb_rt_opts* o, const int* d_status, double* d_spectrum,
-                     double* d_tau, double* ncol, double* sums, double* partial) {
+                     double* d_tau, double* ncol, double* sums, double* partial, double* tau_tab) {
   const int Nr = c->geo_nr;
-  k_rt_los<<<B, 256, sizeof(double) * (4 * (size_t)Nr + 40), s>>>(
-      B, c->geo_r.as<double>(), d_n, d_v, d_T, o->temperature_is_profile, Nr, o->z_grid_size, d_status, ncol, sums);
-  c->launches++;
-  PWB_CUDA(c, cudaGetLastError());
   const int tiles = (Nw + 255) / 256;
   const int nsplit = rt_nsplit(c);
   double* part = (nsplit > 1) ? partial : d_spectrum;
+  if (o->wind_broadening_method == 1) {
+    const size_t smem = sizeof(double) * (4 * (size_t)Nr + 4 * (size_t)o->z_grid_size);
+    if (smem > 100 * 1024) return fail(c, "pwb_rt2d_batch: z_grid_size too large for the 'formal' kernel");
+    dim3 g1(Nr, B);
+    k_rt_formal_tau<<<g1, 256, smem, s>>>(B, Nw, Nr, *o, c->geo_r.as<double>(), d_n, d_v, d_T, d_wl, d_status, tau_tab);
+    c->launches++;
+    PWB_CUDA(c, cudaGetLastError());
+  } else {
+    k_rt_los<<<B, 256, sizeof(double) * (4 * (size_t)Nr + 40), s>>>(
+        B, c->geo_r.as<double>(), d_n, d_v, d_T, o->temperature_is_profile, Nr, o->z_grid_size, d_status, ncol, sums);
+    c->launches++;
+    PWB_CUDA(c, cudaGetLastError());
+    tau_tab = nullptr;
+  }
   dim3 grid(B, nsplit, tiles);
   k_rt_sum<<<grid, 256, 0, s>>>(B, Nw, Nr, *o, d_wl, d_T, ncol, sums, d_status, c->px_lo.as<int>(),
                                 c->px_whi.as<double>(), c->px_wlo.as<double>(), c->px_i0.as<double>(),
-                                c->px_meta.as<double>(), nsplit, part, d_tau);
+                                c->px_meta.as<double>(), nsplit, part, d_tau, tau_tab);
   c->launches++;
   PWB_CUDA(c, cudaGetLastError());
   if (nsplit > 1) {
@@ -703,10 +790,12 @@ int pwb_rt2d_batch(pwb_ctx* c, int B, const double* d_n, const double* d_v, cons
   const int Nr = c->geo_nr;
   const int nsplit = rt_nsplit(c);
   if (c->rt_ncol.ensure(sizeof(double) * (size_t)B * Nr) || c->rt_sums.ensure(sizeof(double) * (size_t)B * 4) ||
-      (nsplit > 1 && c->rt_partial.ensure(sizeof(double) * (size_t)B * nsplit * Nw)))
+      (nsplit > 1 && c->rt_partial.ensure(sizeof(double) * (size_t)B * nsplit * Nw)) ||
+      (o->wind_broadening_method == 1 && c->rt_tau.ensure(sizeof(double) * (size_t)B * Nr * Nw)))
     return fail(c, "out of device memory");
   return launch_rt(c, (cudaStream_t)stream, B, d_n, d_v, d_T, d_wl, Nw, o, d_status, d_spectrum, d_tau,
-                   c->rt_ncol.as<double>(), c->rt_sums.as<double>(), c->rt_partial.as<double>());
+                   c->rt_ncol.as<double>(), c->rt_sums.as<double>(), c->rt_partial.as<double>(),
+                   c->rt_tau.as<double>());
 }
 
 int pwb_forward_batch(pwb_ctx* c, int B, const double* d_T, const double* d_mdot,
@@ -732,7 +821,8 @@ int pwb_forward_batch(pwb_ctx* c, int B, const double* d_T, const double* d_mdot
       c->fw_v.ensure(sizeof(double) * bn) || c->fw_T.ensure(sizeof(double) * B) ||
       c->he_work.ensure(sizeof(double) * 10 * bn) || c->rt_ncol.ensure(sizeof(double) * bn) ||
       c->rt_sums.ensure(sizeof(double) * (size_t)B * 4) ||
-      (nsplit > 1 && c->rt_partial.ensure(sizeof(double) * (size_t)B * nsplit * Nw)))
+      (nsplit > 1 && c->rt_partial.ensure(sizeof(double) * (size_t)B * nsplit * Nw)) ||
+      (rtopts->wind_broadening_method == 1 && c->rt_tau.ensure(sizeof(double) * bn * Nw)))
     return fail(c, "out of device memory");
   double* base = c->fw_f.as<double>();
   double* f_r = d_f_r ? d_f_r : base;
@@ -785,7 +875,8 @@ int pwb_forward_batch(pwb_ctx* c, int B, const double* d_T, const double* d_mdot
     PWB_CUDA(c, cudaGetLastError());
     if (launch_rt(c, cs, nb, c->fw_n.as<double>() + oN, c->fw_v.as<double>() + oN, c->fw_T.as<double>() + o1, d_wl,
                   Nw, rtopts, d_status + o1, d_spectrum + o1 * Nw, nullptr, c->rt_ncol.as<double>() + oN,
-                  c->rt_sums.as<double>() + o1 * 4, c->rt_partial.as<double>() + o1 * nsplit * Nw))
+                  c->rt_sums.as<double>() + o1 * 4, c->rt_partial.as<double>() + o1 * nsplit * Nw,
+                  c->rt_tau.as<double>() + oN * Nw))
       return -1;
     if (nchunk > 1) {
       PWB_CUDA(c, cudaEventRecord(c->ev_done[q], cs));

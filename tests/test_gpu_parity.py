@@ -261,6 +261,13 @@ def test_radiative_transfer_reference_signature(eng):
     s = transit.radiative_transfer_2d(1.0, geo['test_r_map'], prof['r'], prof['n'], prof['v'], w[1], w[4],
                                       w[6], ka['wl'], 9E3, M_HE)
     assert np.max(_rel(s, ka['spectrum_single_line_scalar_i0'])) < 1e-10
+    # 'formal' wind broadening (per-cell Doppler width and wind shift, transit.py:463-473)
+    s = transit.radiative_transfer_2d(geo['test_i0'], geo['test_r_map'], *args, ka['wl'][::6], 9E3, M_HE,
+                                      bulk_los_velocity=-2E3, wind_broadening_method='formal')
+    assert np.max(_rel(s, ka['spectrum_formal'])) < 1e-10
+    s = transit.radiative_transfer_2d(geo['test_i0'], geo['test_r_map'], *args, ka['wl'][::6], ka['tprofile'],
+                                      M_HE, bulk_los_velocity=-2E3, wind_broadening_method='formal')
+    assert np.max(_rel(s, ka['spectrum_formal_tprofile'])) < 1e-10
     tau = transit.optical_depth_2d(*args, ka['wl'], 9E3, M_HE, 200, -2E3)
     ref = ka['tau_average']
     m = ref > 0
