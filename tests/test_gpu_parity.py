@@ -400,3 +400,81 @@ def test_draw_transit_reference_signature(eng, oracle):
     assert abs(depth / ref[1] - 1) < 1e-12 and np.max(np.abs(rm - ref[2])) < 1e-12 * ref[2].max()
     with pytest.raises(ValueError, match='box'):
         transit.draw_transit(0.1, 1.0, resample_method='lanczos', supersampling=2)
+
+
+# --------------------------------------------------------------------------- BASELINE configs 2 and 5
+def test_config2_lyman_alpha_hydrogen_only(eng, oracle, sed):
+    """BASELINE config 2: hydrogen.ion_fraction + Ly-alpha radiative_transfer_2d on a 32x32
+    (T0, Mdot) grid, no helium stage (species = neutral H; line data supplied by the caller
+    because the reference's lines.py has no Ly-alpha entry)."""
+    from p_winds_b200.engine import Engine
+    from p_winds_b200 import lines
+    geo = golden('geometry')
+    w0, f, a = lines.lyman_alpha_properties()
+    m_p = 1.67262192369e-27
+    wl = np.linspace(1214.0, 1217.4, 200) * 1e-10
+    sc = eng.sed_scalars()
+    rates = [sc[k] for k in ('he_phi_1', 'he_phi_3', 'he_a_1', 'he_a_3', 'he_a_h_1', 'he_a_h_3')]
+    heo = Engine.he_opts(1.39, rates, (1.0, 0.0), True)
+    rto = Engine.rt_opts(w0, f, a, m_p)
+    # tight tolerances, per model vs the oracle
+    T = np.array([9100., 11000., 12500.])
+    md = np.array([10 ** 10.27, 1e11, 10 ** 9.8])
+    hf = np.full(3, 0.9)
+    ho = Engine.h_opts(1.39, 0.73, relax_solution=True, exact_phi=True, rtol=1e-10, atol=1e-13)
+    o = eng.forward_batch(T, md, hf, R, ho, heo, rto, wl, species='h1')
+    s = oracle.Setup(sed, r=R, i0=geo['i0'], r_map=geo['r_map'], wl=wl, lines=(np.array([w0]), np.array([f]),
+                     np.array([a])), mass=m_p, h_tol=dict(rtol=1e-10, atol=1e-13), species='h1')
+    spec = o['spectrum'].cpu().numpy()
+    for b in range(3):
+        ref = oracle.forward_model(s, T[b], md[b], hf[b])
+        assert ref['status'] == 0 and int(o['status'][b]) == 0
+        assert np.max(_rel(spec[b], ref['spectrum'])) < 1e-5        # Ly-alpha transit depth contract
+        assert np.max(_rel(o['f_r'][b].cpu().numpy()[1:], ref['f_r'][1:])) < 1e-6
+        assert spec[b].min() < 0.9 * spec[b].max()                   # saturated core (tau up to ~1e7)
+    # full 32x32 grid at the reference's tolerances: invariants + determinism
+    T0 = np.linspace(10000, 13000, 32)
+    Md = np.logspace(9.5, 12, 32)
+    TT, MM = np.meshgrid(T0, Md, indexing='ij')
+    ho = Engine.h_opts(1.39, 0.73, relax_solution=True, exact_phi=True)
+    o1 = eng.forward_batch(TT.ravel(), MM.ravel(), np.full(1024, 0.9), R, ho, heo, rto, wl, species='h1')
+    sp1, st1 = o1['spectrum'].cpu().numpy(), o1['status'].cpu().numpy()
+    o2 = eng.forward_batch(TT.ravel(), MM.ravel(), np.full(1024, 0.9), R, ho, heo, rto, wl, species='h1')
+    assert np.array_equal(sp1, o2['spectrum'].cpu().numpy(), equal_nan=True)
+    assert (st1 == 0).mean() > 0.98
+    ok = st1 == 0
+    cont = geo['i0'].sum()
+    assert (sp1[ok] >= 0).all() and (sp1[ok] <= cont * (1 + 1e-12)).all()
+    assert (sp1[ok].min(axis=1) < 0.95 * cont).all()
+
+
+def test_config5_size_radiative_transfer(eng, oracle):
+    """BASELINE config 5 sizes: 512 x 512 transit cells, 4096 wavelength bins, He 10830 +
+    C II + O I line sets.  The reference needs 11.9 s and 34 GB per model and line set
+    here; the oracle is run on a wavelength subset (the 'average' method is independent per
+    wavelength) and the full-size result is checked through its invariants."""
+    from p_winds_b200 import transit, lines
+    prof = golden('he_3_profile')
+    r, n, v = prof['r'][::5].copy(), prof['n'][::5].copy(), prof['v'][::5].copy()
+    i0, depth, rm = transit.draw_transit(0.12086, 1.39 * 71492000, 0.499, 0.0, grid_size=512, supersampling=2)
+    assert i0.shape == (512, 512) and abs(i0.sum() - (1 - depth)) < 1e-12
+    ref_geo = oracle.draw_transit(0.12086, 1.39 * 71492000, 0.499, 0.0, grid_size=512, supersampling=2)
+    assert np.max(np.abs(i0 - ref_geo[0])) < 1e-15 and abs(depth - ref_geo[1]) < 1e-14
+    m_p = 1.67262192369e-27
+    he, c2, o1 = lines.he_3_properties(), lines.c_ii_properties(), lines.o_i_properties()
+    sets = [((np.array(he[:3]), np.array(he[3:6]), np.array([he[6]] * 3)), 4 * m_p,
+             np.linspace(1.0827, 1.0832, 4096) * 1e-6),
+            ((np.array(c2[:3]), np.array(c2[3:6]), np.array(c2[6:9])), 12 * m_p,
+             np.linspace(1332.9, 1337.1, 4096) * 1e-10),
+            ((np.array(o1[:3]), np.array(o1[3:6]), np.array(o1[6:9])), 16 * m_p,
+             np.linspace(1300.9, 1307.1, 4096) * 1e-10)]
+    for (w0, f, a), mass, wl in sets:
+        s = transit.radiative_transfer_2d(i0, rm, r, n, v, w0, f, a, wl, 9E3, mass, bulk_los_velocity=-2E3)
+        assert s.shape == (4096,) and np.isfinite(s).all()
+        assert (s > 0).all() and (s <= i0.sum() * (1 + 1e-12)).all()
+        sub = np.arange(0, 4096, 128)
+        ref = oracle.radiative_transfer_2d(i0, rm, r, n, v, w0, f, a, wl[sub], 9E3, mass, v_bulk=-2E3)
+        assert np.max(_rel(s[sub], ref)) < 1e-10
+        # linear in the intensity map, exactly (power-of-two scaling)
+        s2 = transit.radiative_transfer_2d(2.0 * i0, rm, r, n, v, w0, f, a, wl, 9E3, mass, bulk_los_velocity=-2E3)
+        assert np.array_equal(s2, 2.0 * s)
