@@ -631,80 +631,96 @@ struct Lsoda {
     return 0;
   }
 
+  // ---- driver (DLSODA), split so that callers can run many integrations in lock step:
+  //   begin()        first-call initialisation (istate = 1 block, initial step size)
+  //   advance_one()  one pass of the main loop: per-step checks + one stoda() step
+  //   reached(tout)  itask = 1 stopping test;  intdy(tout, y) output by interpolation
+  //   new_call()     what a continuation call (istate = 2) does first: nslast = nst
+  // call() strings them together exactly like one `lsoda(..., itask = 1)` invocation.
+  PW_HD void reset() { started = false; }
+
+  PW_LS int begin(double t0, const double* y0, double tout) {
+    started = true;
+    mxordn = kLsodaMaxOrdN; mxords = kLsodaMaxOrdS;
+    hmxi = (o.hmax > 0.) ? 1. / o.hmax : 0.;
+    tn = t0; tsw = t0; maxord = mxordn;
+    jstart = 0; nhnil = 0; nst = 0; nje = 0; nslast = 0; hu = 0.; nqu = 0; mused = 0; miter = 0;
+    meth = 1; jtyp = 2;
+    for (int i = 0; i < N; ++i) { y[i] = y0[i]; yh[1][i] = y0[i]; }
+    f(tn, y, yh[2]);
+    nfe = 1;
+    nq = 1;
+    h = 1.;
+    if (!ewset(yh[1])) return -3;
+    double h0 = o.h0;
+    if (!(h0 > 0.)) {
+      const double tdist = fabs(tout - t0);
+      const double w0 = fmax(fabs(t0), fabs(tout));
+      if (tdist < 2. * kEps * w0) return -3;
+      double tol = o.rtol;
+      if (tol <= 0.)
+        for (int i = 0; i < N; ++i) {
+          const double ayi = fabs(y[i]);
+          if (ayi != 0.) tol = fmax(tol, o.atol / ayi);
+        }
+      tol = fmax(tol, 100. * kEps);
+      tol = fmin(tol, 0.001);
+      double sum = vmnorm(yh[2]);
+      sum = 1. / (tol * w0 * w0) + tol * sum * sum;
+      h0 = 1. / sqrt(sum);
+      h0 = fmin(h0, tdist);
+      h0 = copysign(h0, tout - t0);
+    }
+    const double rh = fabs(h0) * hmxi;
+    if (rh > 1.) h0 /= rh;
+    h = h0;
+    for (int i = 0; i < N; ++i) yh[2][i] *= h0;
+    return 0;
+  }
+
+  PW_HD void new_call() { nslast = nst; }
+  PW_HD bool reached(double tout) const { return (tn - tout) * h >= 0.; }
+
+  // Returns 0 after a successful step, < 0 (ODEPACK istate) on failure.
+  PW_LS int advance_one() {
+    if (nst != 0 || jstart != 0) {  // label 250 (skipped on the very first pass)
+      if ((nst - nslast) >= o.mxstep) return -1;
+      if (!ewset(yh[1])) return -6;
+    }
+    const double tolsf = kEps * vmnorm(yh[1]);
+    if (tolsf > 1.) return (nst == 0) ? -3 : -2;
+    if ((tn + h) == tn) ++nhnil;
+    stoda();
+    if (kflag == 0) {
+      if (meth != mused) {
+        tsw = tn;
+        maxord = mxordn;
+        if (meth == 2) maxord = mxords;
+        jstart = -1;
+      }
+      return 0;
+    }
+    return (kflag == -1) ? -4 : -5;
+  }
+
   // One `lsoda(..., itask = 1)` call: advance to tout and interpolate.
   // First call initialises from (t0, y0).  Returns istate.
-  PW_LS int call(double t0, const double* y0, double tout, double* yout) {
+  PW_HD int call(double t0, const double* y0, double tout, double* yout) {
     if (!started) {
-      started = true;
-      mxordn = kLsodaMaxOrdN; mxords = kLsodaMaxOrdS;
-      hmxi = (o.hmax > 0.) ? 1. / o.hmax : 0.;
-      tn = t0; tsw = t0; maxord = mxordn;
-      jstart = 0; nhnil = 0; nst = 0; nje = 0; nslast = 0; hu = 0.; nqu = 0; mused = 0; miter = 0;
-      meth = 1; jtyp = 2;
-      for (int i = 0; i < N; ++i) { y[i] = y0[i]; yh[1][i] = y0[i]; }
-      f(tn, y, yh[2]);
-      nfe = 1;
-      nq = 1;
-      h = 1.;
-      if (!ewset(yh[1])) return -3;
-      double h0 = o.h0;
-      if (!(h0 > 0.)) {
-        const double tdist = fabs(tout - t0);
-        const double w0 = fmax(fabs(t0), fabs(tout));
-        if (tdist < 2. * kEps * w0) return -3;
-        double tol = o.rtol;
-        if (tol <= 0.)
-          for (int i = 0; i < N; ++i) {
-            const double ayi = fabs(y[i]);
-            if (ayi != 0.) tol = fmax(tol, o.atol / ayi);
-          }
-        tol = fmax(tol, 100. * kEps);
-        tol = fmin(tol, 0.001);
-        double sum = vmnorm(yh[2]);
-        sum = 1. / (tol * w0 * w0) + tol * sum * sum;
-        h0 = 1. / sqrt(sum);
-        h0 = fmin(h0, tdist);
-        h0 = copysign(h0, tout - t0);
-      }
-      const double rh = fabs(h0) * hmxi;
-      if (rh > 1.) h0 /= rh;
-      h = h0;
-      for (int i = 0; i < N; ++i) yh[2][i] *= h0;
+      const int rc = begin(t0, y0, tout);
+      if (rc < 0) return rc;
     } else {
-      nslast = nst;
-      if ((tn - tout) * h >= 0.) {
-        if (intdy(tout, yout) != 0) return -3;
-        return 2;
-      }
+      new_call();
+      if (reached(tout)) return (intdy(tout, yout) != 0) ? -3 : 2;
     }
     for (;;) {
-      if (nst != 0 || jstart != 0) {  // label 250 (skipped on the very first pass)
-        if ((nst - nslast) >= o.mxstep) {
-          for (int i = 0; i < N; ++i) yout[i] = yh[1][i];
-          return -1;
-        }
-        if (!ewset(yh[1])) { for (int i = 0; i < N; ++i) yout[i] = yh[1][i]; return -6; }
-      }
-      double tolsf = kEps * vmnorm(yh[1]);
-      if (tolsf > 1.) {
+      const int rc = advance_one();
+      if (rc < 0) {
         for (int i = 0; i < N; ++i) yout[i] = yh[1][i];
-        return (nst == 0) ? -3 : -2;
+        return rc;
       }
-      if ((tn + h) == tn) ++nhnil;
-      stoda();
-      if (kflag == 0) {
-        if (meth != mused) {
-          tsw = tn;
-          maxord = mxordn;
-          if (meth == 2) maxord = mxords;
-          jstart = -1;
-        }
-        if ((tn - tout) * h < 0.) continue;
-        if (intdy(tout, yout) != 0) return -3;
-        return 2;
-      }
-      for (int i = 0; i < N; ++i) yout[i] = yh[1][i];
-      return (kflag == -1) ? -4 : -5;
+      if (!reached(tout)) continue;
+      return (intdy(tout, yout) != 0) ? -3 : 2;
     }
   }
 };
