@@ -151,6 +151,7 @@ k_hydrogen(int B, const double* __restrict__ T, const double* __restrict__ mdot,
 
 // One thread per model; `lanes` models share a warp (latency-bound regime: fewer lanes
 // per warp spread the independent serial solves over more warp schedulers).
+template <bool kRk45>
 __global__ void __launch_bounds__(32, 1)
 k_helium(int B, int lanes, const double* __restrict__ T, const double* __restrict__ hfrac,
          const double* __restrict__ vs, const double* __restrict__ rs, const double* __restrict__ rhos,
@@ -179,7 +180,7 @@ k_helium(int B, int lanes, const double* __restrict__ T, const double* __restric
   HeWork w{wb, wb + nr, wb + 2 * nr, wb + 3 * nr, wb + 4 * nr, wb + 5 * nr};
   HeOut out{f1 + (size_t)b * nr, f3 + (size_t)b * nr, scal + (size_t)b * 4,
             rates ? rates + (size_t)b * 11 * nr : nullptr, status + b};
-  he_population_model(p, *tab, r, v + (size_t)b * nr, rho + (size_t)b * nr, f_h + (size_t)b * nr, nr, w, out);
+  he_population_model<kRk45>(p, *tab, r, v + (size_t)b * nr, rho + (size_t)b * nr, f_h + (size_t)b * nr, nr, w, out);
 }
 
 // n [m^-3] and v [m/s] for the RT stage (quickstart.ipynb cells 10-11; SURVEY 8(d) cfg 2)
@@ -684,8 +685,14 @@ static int launch_helium(pwb_ctx* c, cudaStream_t s, int B, int lanes, const dou
                          const pwb_he_opts* o, double* work, double* d_f1, double* d_f3, double* d_scal,
                          double* d_rates, int* d_status) {
   const int blocks = (B + lanes - 1) / lanes;
-  k_helium<<<blocks, 32, 0, s>>>(B, lanes, d_T, d_hfrac, d_vs, d_rs, d_rhos, sstride, d_r, Nr, d_v, d_rho, d_f_h,
-                                 *o, c->lsoda_tab.as<LsodaTables>(), work, d_f1, d_f3, d_scal, d_rates, d_status);
+  if (o->method == PW_HE_RK45)
+    k_helium<true><<<blocks, 32, 0, s>>>(B, lanes, d_T, d_hfrac, d_vs, d_rs, d_rhos, sstride, d_r, Nr, d_v, d_rho,
+                                         d_f_h, *o, c->lsoda_tab.as<LsodaTables>(), work, d_f1, d_f3, d_scal,
+                                         d_rates, d_status);
+  else
+    k_helium<false><<<blocks, 32, 0, s>>>(B, lanes, d_T, d_hfrac, d_vs, d_rs, d_rhos, sstride, d_r, Nr, d_v, d_rho,
+                                          d_f_h, *o, c->lsoda_tab.as<LsodaTables>(), work, d_f1, d_f3, d_scal,
+                                          d_rates, d_status);
   c->launches++;
   PWB_CUDA(c, cudaGetLastError());
   return 0;

@@ -67,16 +67,19 @@ struct HeRhs {
   double sl[5], x0, b0[5];
   int jc;
 
-  PW_HD_NOINLINE void coeffs(double x) {
+  // out-of-line copy for the callers that are not latency critical (RK45 stages, the
+  // `return_rates` table): keeps one instance of the two exps and the table walk there
+  PW_HD_NOINLINE void coeffs_out(double x) { coeffs(x); }
+  PW_HD void coeffs(double x) {
     const int jj = bracket(rn, n, x, j);
     j = jj;
     double v_, rho_, fh_, t1, t3;
     if (jj < 0 || jj >= n - 1 || rn[jj] == x) {
-      v_ = np_interp_at(rn, v, n, x, jj);
-      rho_ = np_interp_at(rn, rho, n, x, jj);
-      fh_ = np_interp_at(rn, fh, n, x, jj);
-      t1 = np_interp_at(rn, tau1, n, x, jj);
-      t3 = np_interp_at(rn, tau3, n, x, jj);
+      v_ = np_interp_at_out(rn, v, n, x, jj);
+      rho_ = np_interp_at_out(rn, rho, n, x, jj);
+      fh_ = np_interp_at_out(rn, fh, n, x, jj);
+      t1 = np_interp_at_out(rn, tau1, n, x, jj);
+      t3 = np_interp_at_out(rn, tau3, n, x, jj);
     } else {
       if (jj != jc) {  // slopes exactly as numpy forms them, kept while x stays in the cell
         jc = jj;
@@ -152,8 +155,21 @@ struct HeRhs {
     }
   }
 
-  PW_HD void operator()(double x, const double* y, double* dydx) {
+  // RHS concept of the integrators: at(x) selects the abscissa, eval(y, dydx) evaluates there
+  PW_HD void at(double x) {
     if (!(x == xc)) coeffs(x);
+  }
+  // same, for call sites off the hot path: works on a copy so that this object's address
+  // never escapes into a call (it has to stay in registers for the hot loop)
+  PW_HD void at_cold(double x) {
+    if (x == xc) return;
+    HeRhs t = *this;
+    t.coeffs_out(x);
+    *this = t;
+  }
+  PW_HD void eval(const double* y, double* dydx) const { eval(y, dydx, nullptr); }
+  PW_HD void operator()(double x, const double* y, double* dydx) {
+    if (!(x == xc)) coeffs_out(x);
     eval(y, dydx, nullptr);
   }
 };
@@ -174,11 +190,13 @@ struct HeOut {
 
 // Integrate once over the radius grid; returns false when the reference's solver
 // would have reported a problem (odeint warning / solve_ivp short output).
-PW_HD_NOINLINE bool he_solve(const HeParams& p, HeRhs& rhs, const LsodaTables& tab, int nr, double* f1, double* f3,
+// kRk45 selects the integrator at compile time so that each kernel carries one of them.
+template <bool kRk45>
+PW_HD bool he_solve(const HeParams& p, HeRhs& rhs, const LsodaTables& tab, int nr, double* f1, double* f3,
                     double* ytmp, int* nfe, int* nst, int* nje) {
   const double* rn = rhs.rn;
   rhs.j = 0; rhs.jc = -2; rhs.xc = nan("");
-  if (p.method == PW_HE_RK45) {
+  if (kRk45) {
     // solve_ivp(method='RK45', t_eval=r) (helium.py:702-710); interleaved (f1, f3)
     // samples go to the spare scratch and are split afterwards
     Rk45Opts o{p.rtol, p.atol, p.first_step, p.max_step};
@@ -196,28 +214,36 @@ PW_HD_NOINLINE bool he_solve(const HeParams& p, HeRhs& rhs, const LsodaTables& t
   lo.mxstep = (p.method == PW_HE_ODEINT) ? 500 : 2000000000;
   lo.hmax = (p.max_step > 0.) ? p.max_step : 0.;
   lo.h0 = (p.first_step > 0.) ? p.first_step : 0.;
-  Lsoda<2, HeRhs> s(rhs, tab, lo);
+  double hi_rows[Lsoda<2, HeRhs>::kHiDoubles];
+  Lsoda<2, HeRhs> s(rhs, tab, lo, hi_rows);
   f1[0] = p.y0[0];
   f3[0] = p.y0[1];
-  bool ok = true;
-  for (int k = 1; k < nr; ++k) {
-    double yo[2];
-    const int istate = s.call(rn[0], p.y0, rn[k], yo);
-    if (istate < 0) {
-      // odeint stops at the first failing output point (ODEintWarning) and leaves
-      // the remaining rows of its zero-initialised result array untouched
-      ok = false;
-      for (int q = k; q < nr; ++q) { f1[q] = 0.0; f3[q] = 0.0; }
-      break;
+  // odeint = one lsoda(itask = 1) call per output radius: integrate past r[k], interpolate
+  // back (intdy), carry on from the internal state.  Written as one flat loop over steps --
+  // every radius the last step has passed is emitted before the next step is taken -- so
+  // that the lanes of a warp, each with its own model, all sit in the same loop body.
+  int k = 1;
+  bool ok = s.begin(rn[0], p.y0, rn[1]) >= 0;
+  while (ok && k < nr) {
+    if (s.advance_one() < 0) { ok = false; break; }
+    while (k < nr && s.reached(rn[k])) {
+      double yo[2];
+      s.intdy(rn[k], yo);
+      f1[k] = yo[0];
+      f3[k] = yo[1];
+      ++k;
+      s.new_call();  // the next output radius is a new lsoda call: nslast = nst
     }
-    f1[k] = yo[0];
-    f3[k] = yo[1];
   }
+  // odeint stops at the first failing output point (ODEintWarning) and leaves the
+  // remaining rows of its zero-initialised result array untouched
+  for (int q = k; q < nr; ++q) { f1[q] = 0.0; f3[q] = 0.0; }
   *nfe += s.nfe; *nst += s.nst; *nje += s.nje;
   return ok;
 }
 
 // `r` radius profile in planetary radii (shared), v / rho / f_h per model.
+template <bool kRk45>
 PW_HD void he_population_model(const HeParams& p, const LsodaTables& tab, const double* __restrict__ r,
                                const double* __restrict__ v, const double* __restrict__ rho,
                                const double* __restrict__ f_h, int nr, const HeWork& w, const HeOut& out) {
@@ -258,9 +284,11 @@ PW_HD void he_population_model(const HeParams& p, const LsodaTables& tab, const 
   HeRhs rhs;
   rhs.rn = w.rn; rhs.v = v; rhs.rho = rho; rhs.fh = f_h; rhs.tau1 = w.tau1; rhs.tau3 = w.tau3;
   rhs.n = nr;
+#if defined(PW_HE_LOGEXP)
   rhs.lk1 = log(k1);
   rhs.lc[0] = log(a_r1); rhs.lc[1] = log(a_r3); rhs.lc[2] = log(q13); rhs.lc[3] = log(q31a);
   rhs.lc[4] = log(q31b); rhs.lc[5] = log(bq31); rhs.lc[6] = log(bq_he); rhs.lc[7] = log(bq_hep);
+#endif
   rhs.kc[0] = k1 * a_r1; rhs.kc[1] = k1 * a_r3; rhs.kc[2] = k1 * q13; rhs.kc[3] = k1 * q31a;
   rhs.kc[4] = k1 * q31b; rhs.kc[5] = k1 * bq31; rhs.kc[6] = k1 * bq_he; rhs.kc[7] = k1 * bq_hep;
   rhs.phi1 = phi_1; rhs.phi3 = phi_3; rhs.ba31 = ba31;
@@ -297,7 +325,7 @@ PW_HD void he_population_model(const HeParams& p, const LsodaTables& tab, const 
       }
       for (int i = 0; i < nr; ++i) { s1 += f1[i]; s3 += f3[i]; p1[i] = f1[i]; p3[i] = f3[i]; }
     }
-    const bool ok = he_solve(p, rhs, tab, nr, f1, f3, ytmp, &nfe, &nst, &nje);
+    const bool ok = he_solve<kRk45>(p, rhs, tab, nr, f1, f3, ytmp, &nfe, &nst, &nje);
     if (!ok) {
       if (it == 0 || p.method != PW_HE_ODEINT) {
         status = PW_FAIL_HE_SOLVER;  // helium.py:693-697, :708-710 (short solve_ivp output)
@@ -318,10 +346,11 @@ PW_HD void he_population_model(const HeParams& p, const LsodaTables& tab, const 
     for (int i = 0; i < nr; ++i) { f1[i] = nan_; f3[i] = nan_; }
   } else if (out.rates) {
     // _fun(r, [f_1_r, f_3_r], rates=True) * phi_unit  (:770-773, :684-686)
+    HeRhs rr = rhs;  // a copy, so that the solver's own object never has its address taken
     for (int i = 0; i < nr; ++i) {
       double y[2] = {f1[i], f3[i]}, t[11];
-      rhs.coeffs(w.rn[i]);
-      rhs.eval(y, nullptr, t);
+      rr.coeffs_out(w.rn[i]);
+      rr.eval(y, nullptr, t);
       for (int k = 0; k < 11; ++k) out.rates[k * nr + i] = t[k] * phi_unit;
     }
   }

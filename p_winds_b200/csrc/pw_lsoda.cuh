@@ -15,12 +15,9 @@
 #pragma once
 #include "pw_common.cuh"
 
-// Inlining policy of the integrator's big routines (device only): out-of-line keeps
-// the kernel small (I-cache), inline lets the solver state live in registers.
-#if defined(PW_LSODA_OUTOFLINE)
-#define PW_LS PW_HD_NOINLINE
-#else
-#define PW_LS PW_HD   // measured on B200: 147 ms vs 155 ms for the 64x64 grid
+#if defined(PW_LSODA_HIST) && !defined(__CUDA_ARCH__)
+extern "C" long pw_lsoda_hist[2][13];  // test instrumentation: successful steps per (method, order)
+long pw_lsoda_hist[2][13];
 #endif
 
 namespace pw {
@@ -106,55 +103,132 @@ struct LsodaOpts {
   double h0;    // <= 0: automatic
 };
 
+// Run-time rows of the Nordsieck array (orders above kF; see Lsoda below): all passes of the
+// Pascal-triangle product that touch rows kF+2..nq+1.  hand[(kF+1-j)*N + i] receives row
+// kF+2 as it stands at the start of pass j (j = kF+1..1), which is what pass j adds to row kF+1.
+template <int N>
+PW_HD_NOINLINE void lsoda_pascal_hi(double* yhs, int nq, int kF, double sign, double* hand) {
+  for (int j = nq; j >= kF + 2; --j)
+    for (int i1 = j; i1 <= nq; ++i1)
+      for (int i = 0; i < N; ++i) yhs[i1 * N + i] += sign * yhs[(i1 + 1) * N + i];
+  for (int j = kF + 1; j >= 1; --j) {
+    for (int i = 0; i < N; ++i) hand[(kF + 1 - j) * N + i] = yhs[(kF + 2) * N + i];
+    for (int i1 = kF + 2; i1 <= nq; ++i1)
+      for (int i = 0; i < N; ++i) yhs[i1 * N + i] += sign * yhs[(i1 + 1) * N + i];
+  }
+}
+
 // istate values on return from call(): 2 ok, < 0 failure (ODEPACK numbering)
 //  -1 excess work (mxstep), -2 excess accuracy, -3 illegal input, -4 repeated
 //  error-test failures, -5 repeated convergence failures, -6 ewt <= 0
+//
+// Register-resident layout.  One thread integrates one model and the solve is a chain
+// of ~10^4 dependent steps, so what matters is the latency of one step.  The Nordsieck
+// rows 1..kF+1 (orders <= kF = 5: every BDF order, and the Adams orders a stiff problem
+// ever reaches before the switch to BDF) are addressed only through loops that run to a
+// compile-time bound under an `if (row <= nq)` guard and are fully unrolled: all indices
+// into yh / wm / ipvt are constants, the arrays live in registers, and a guarded-off row
+// costs one issue slot instead of a local-memory round trip.  The rows above (Adams
+// orders 6..12, and ODEPACK's scratch row lmax = 13 of the Adams method) sit in `yhs`
+// and are walked by ordinary run-time loops behind `if (nq > kF)`.  Rows addressed by a
+// run-time index (yh[l], yh[lmax]) go through row_get / row_set.  The method coefficients are not copied (ODEPACK's el array): `elp`
+// points at the row of the coefficient table that dcfode would have loaded, and the three
+// test constants of the current order are cached when that row is (re)selected.
+//
+// RHS concept:  f.at(t)  makes t the current abscissa (may cache t-dependent terms);
+//               f.eval(y, dydt)  evaluates at the current abscissa.
 template <int N, class RHS>
 struct Lsoda {
+  static constexpr int kQ = kLsodaMaxOrdN;  // highest order; rows 1..kQ+1 of the history are used
+  static constexpr int kF = kLsodaMaxOrdS;  // orders whose rows 1..kF+1 are register resident
   RHS& f;
   const LsodaTables& tab;
   LsodaOpts o;
-  // Nordsieck array: yh[j][i], j = 1..lmax (+1 scratch column)
-  double yh[kLsodaMaxOrdN + 3][N];
+  double yh[kF + 2][N];   // Nordsieck array, rows 1..kF+1
+  // rows kF+2..kQ+1, run-time indexed: caller-provided storage of kHiDoubles doubles, kept
+  // outside this object so that the object itself is only ever addressed by constants
+  static constexpr int kHiDoubles = (kQ + 2) * N;
+  double* yhs_;
   double y[N], ewt[N], savf[N], acor[N];
   double wm[N][N];
   int ipvt[N];
-  double el[kLsodaMaxOrdN + 2];
+  const double* elp;     // elco[meth_tab][nq] in force (ODEPACK: el(1..l))
+  double tq1, tq2, tq3;  // tesco(nq, 1..3) of the same table row
+  double tq2u;           // tesco(nqu, 2) as label 700 reads it
   double tn, h, hu, hold, rc, el0, crate, conit, rmax, pdnorm, pdest, pdlast, ratio, hmxi, tsw;
   int nq, l, lmax, meth, mused, meth_tab, miter, jtyp, maxord, mxordn, mxords;
   int ialth, ipup, nslp, icount, irflag, jstart, kflag, jcur, ierpj, iersl;
   int nst, nfe, nje, nqu, nslast, nhnil;
   bool started;
 
-  PW_HD Lsoda(RHS& f_, const LsodaTables& t_, const LsodaOpts& o_) : f(f_), tab(t_), o(o_), started(false) {}
+  PW_HD Lsoda(RHS& f_, const LsodaTables& t_, const LsodaOpts& o_, double* hi_rows)
+      : f(f_), tab(t_), o(o_), yhs_(hi_rows), started(false) {}
 
   PW_HD double vmnorm(const double* v) const {
     double vm = 0.0;
+#pragma unroll
     for (int i = 0; i < N; ++i) vm = fmax(vm, fabs(v[i]) * ewt[i]);
     return vm;
   }
   PW_HD bool ewset(const double* yc) {
+    bool ok = true;
+#pragma unroll
     for (int i = 0; i < N; ++i) {
       const double e = o.rtol * fabs(yc[i]) + o.atol;
-      if (!(e > 0.0)) return false;
+      if (!(e > 0.0)) ok = false;
       ewt[i] = 1.0 / e;
     }
-    return true;
+    return ok;
+  }
+  // yh[k] for a run-time row index
+  PW_HD void row_get(int k, double* out) const {
+    if (k > kF + 1) {
+      for (int i = 0; i < N; ++i) out[i] = yhs_[(k) * N + i];
+      return;
+    }
+    // every row is read unconditionally and the *value* is selected: a conditional read
+    // per row would be merged by the compiler into one read at a run-time address, which
+    // pins the whole object to local memory
+#pragma unroll
+    for (int i = 0; i < N; ++i) out[i] = yh[1][i];
+#pragma unroll
+    for (int j = 2; j <= kF + 1; ++j) {
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+        const double v = yh[j][i];
+        out[i] = (j == k) ? v : out[i];
+      }
+    }
+  }
+  PW_HD void row_set(int k, const double* in) {
+    if (k > kF + 1) {
+      for (int i = 0; i < N; ++i) yhs_[(k) * N + i] = in[i];
+      return;
+    }
+#pragma unroll
+    for (int j = 1; j <= kF + 1; ++j) {
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+        const double v = yh[j][i];
+        yh[j][i] = (j == k) ? in[i] : v;
+      }
+    }
   }
   // ODEPACK keeps ONE elco/tesco table in common storage and reloads it (cfode) only when
   // stoda is re-entered with jstart = -1 after a method switch; until then the old
   // method's coefficients stay in force (e.g. tesco(2,nqu) at label 700).
-  PW_HD double elco(int q, int i) const { return tab.elco[meth_tab - 1][q][i]; }
-  PW_HD double tesco(int q, int k) const { return tab.tesco[meth_tab - 1][q][k]; }
   PW_HD double sm1(int q) const { return tab.sm1[q]; }
 
   PW_HD void resetcoeff() {  // stoda label 150
-    for (int i = 1; i <= l; ++i) el[i] = elco(nq, i);
-    rc = rc * el[1] / el0;
-    el0 = el[1];
+    elp = tab.elco[meth_tab - 1][nq];
+    const double* tq = tab.tesco[meth_tab - 1][nq];
+    tq1 = tq[1]; tq2 = tq[2]; tq3 = tq[3];
+    const double el1 = elp[1];
+    rc = rc * el1 / el0;
+    el0 = el1;
     conit = 0.5 / (double)(nq + 2);
   }
-  PW_LS void scaleh(double* rh, double* pdh) {  // stoda labels 175-180
+  PW_HD void scaleh(double* rh, double* pdh) {  // stoda labels 175-180
     *rh = fmin(*rh, rmax);
     *rh = *rh / fmax(1., fabs(h) * hmxi * (*rh));
     if (meth == 1) {
@@ -166,27 +240,52 @@ struct Lsoda {
       }
     }
     double r = 1.;
-    for (int j = 2; j <= l; ++j) {
-      r *= *rh;
-      for (int i = 0; i < N; ++i) yh[j][i] *= r;
-    }
+#pragma unroll
+    for (int j = 2; j <= kF + 1; ++j)
+      if (j <= l) {
+        r *= *rh;
+#pragma unroll
+        for (int i = 0; i < N; ++i) yh[j][i] *= r;
+      }
+    if (nq > kF)
+#pragma unroll 1
+      for (int j = kF + 2; j <= l; ++j) {
+        r *= *rh;
+        for (int i = 0; i < N; ++i) yhs_[(j) * N + i] *= r;
+      }
     h *= *rh;
     rc *= *rh;
     ialth = l;
   }
-  PW_HD void predict() {
-    for (int j = nq; j >= 1; --j)
-      for (int i1 = j; i1 <= nq; ++i1)
-        for (int i = 0; i < N; ++i) yh[i1][i] += yh[i1 + 1][i];
+  // yh <- yh * Pascal triangle (sign = +1, prediction) or its inverse (sign = -1).  Each
+  // pass j = nq..1 adds row i1+1 to row i1 for i1 = j..nq in ascending order.  For orders
+  // above kF the run-time rows are advanced out of line first (lsoda_pascal_hi); what the
+  // register rows need from them -- row kF+2 as it stands before each of the last kF+1
+  // passes -- comes back in `hand`.
+  template <int kSign>
+  PW_HD void pascal() {
+    double hand[(kF + 1) * N];
+    if (nq > kF) lsoda_pascal_hi<N>(yhs_, nq, kF, (double)kSign, hand);
+#pragma unroll
+    for (int j = kF + 1; j >= 1; --j)
+      if (j <= nq) {
+#pragma unroll
+        for (int i1 = j; i1 <= kF; ++i1)
+          if (i1 <= nq) {
+#pragma unroll
+            for (int i = 0; i < N; ++i) yh[i1][i] += kSign * yh[i1 + 1][i];
+          }
+        if (nq > kF) {
+#pragma unroll
+          for (int i = 0; i < N; ++i) yh[kF + 1][i] += kSign * hand[(kF + 1 - j) * N + i];
+        }
+      }
   }
-  PW_HD void retract() {
-    for (int j = nq; j >= 1; --j)
-      for (int i1 = j; i1 <= nq; ++i1)
-        for (int i = 0; i < N; ++i) yh[i1][i] -= yh[i1 + 1][i];
-  }
+  PW_HD void predict() { pascal<1>(); }
+  PW_HD void retract() { pascal<-1>(); }
 
   // prja, miter = 2: finite-difference Jacobian, P = I - h*el0*J, LU (dgefa)
-  PW_LS void prja() {
+  PW_HD void prja() {
     ++nje;
     ierpj = 0;
     jcur = 1;
@@ -195,40 +294,72 @@ struct Lsoda {
     double r0 = 1000. * fabs(h) * kEps * ((double)N) * fac;
     if (r0 == 0.) r0 = 1.;
     const double srur = sqrt(kEps);
-    double ftem[N];
+    // one column per pass of a *rolled* loop (a single copy of the right-hand side in the
+    // code); the column index only ever selects values, never addresses
+#pragma unroll 1
     for (int j = 0; j < N; ++j) {
-      const double yj = y[j];
-      const double r = fmax(srur * fabs(yj), r0 / ewt[j]);
-      y[j] += r;
+      double yj = 0., ej = 0.;
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+        yj = (i == j) ? y[i] : yj;
+        ej = (i == j) ? ewt[i] : ej;
+      }
+      const double r = fmax(srur * fabs(yj), r0 / ej);
+      double yp[N], ftem[N];
+#pragma unroll
+      for (int i = 0; i < N; ++i) yp[i] = (i == j) ? yj + r : y[i];
       fac = -hl0 / r;
-      f(tn, y, ftem);
-      for (int i = 0; i < N; ++i) wm[i][j] = (ftem[i] - savf[i]) * fac;
-      y[j] = yj;
+      f.eval(yp, ftem);
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+        const double d = (ftem[i] - savf[i]) * fac;
+#pragma unroll
+        for (int jj = 0; jj < N; ++jj) wm[i][jj] = (jj == j) ? d : wm[i][jj];
+      }
     }
     nfe += N;
     // pdnorm = fnorm(wm, ewt) / |hl0| ; fnorm = max_i w_i sum_j |a_ij| / w_j
     double an = 0.;
+#pragma unroll
     for (int i = 0; i < N; ++i) {
       double sum = 0.;
+#pragma unroll
       for (int j = 0; j < N; ++j) sum += fabs(wm[i][j]) / ewt[j];
       an = fmax(an, sum * ewt[i]);
     }
     pdnorm = an / fabs(hl0);
+#pragma unroll
     for (int i = 0; i < N; ++i) wm[i][i] += 1.;
-    // dgefa: Gaussian elimination with partial pivoting, multipliers stored negated
+    // dgefa: Gaussian elimination with partial pivoting, multipliers stored negated.
+    // The pivot row is a run-time index; rows are picked / exchanged with selects.
+#pragma unroll
     for (int k = 0; k < N - 1; ++k) {
       int lp = k;
       double amax = fabs(wm[k][k]);
+#pragma unroll
       for (int i = k + 1; i < N; ++i)
         if (fabs(wm[i][k]) > amax) { amax = fabs(wm[i][k]); lp = i; }
       ipvt[k] = lp;
-      if (wm[lp][k] == 0.) { ierpj = 1; continue; }
-      if (lp != k) { const double t = wm[lp][k]; wm[lp][k] = wm[k][k]; wm[k][k] = t; }
-      const double t = -1. / wm[k][k];
+      double piv = wm[k][k];
+#pragma unroll
+      for (int i = k + 1; i < N; ++i)
+        if (i == lp) piv = wm[i][k];
+      if (piv == 0.) { ierpj = 1; continue; }
+#pragma unroll
+      for (int i = k + 1; i < N; ++i)
+        if (i == lp) wm[i][k] = wm[k][k];
+      wm[k][k] = piv;
+      const double t = -1. / piv;
+#pragma unroll
       for (int i = k + 1; i < N; ++i) wm[i][k] *= t;
+#pragma unroll
       for (int j = k + 1; j < N; ++j) {
-        double tj = wm[lp][j];
-        if (lp != k) { wm[lp][j] = wm[k][j]; wm[k][j] = tj; }
+        double tj = wm[k][j];
+#pragma unroll
+        for (int i = k + 1; i < N; ++i)
+          if (i == lp) { tj = wm[i][j]; wm[i][j] = wm[k][j]; }
+        wm[k][j] = tj;
+#pragma unroll
         for (int i = k + 1; i < N; ++i) wm[i][j] += tj * wm[i][k];
       }
     }
@@ -238,29 +369,39 @@ struct Lsoda {
   // solsy -> dgesl (job = 0)
   PW_HD void solsy(double* b) {
     iersl = 0;
+#pragma unroll
     for (int k = 0; k < N - 1; ++k) {
       const int lp = ipvt[k];
-      double t = b[lp];
-      if (lp != k) { b[lp] = b[k]; b[k] = t; }
+      double t = b[k];
+#pragma unroll
+      for (int i = k + 1; i < N; ++i)
+        if (i == lp) { t = b[i]; b[i] = b[k]; }
+      b[k] = t;
+#pragma unroll
       for (int i = k + 1; i < N; ++i) b[i] += t * wm[i][k];
     }
+#pragma unroll
     for (int kb = 0; kb < N; ++kb) {
       const int k = N - 1 - kb;
       b[k] /= wm[k][k];
       const double t = -b[k];
+#pragma unroll
       for (int i = 0; i < k; ++i) b[i] += t * wm[i][k];
     }
   }
 
   // stoda corrector loop (labels 220-450).  Returns corflag: 0 converged,
   // 1 retry with smaller h (rh set), 2 give up (kflag = -2).
-  PW_LS int correction(double pnorm, double* del_out, double told, int* ncf, double* rh, int* m_out) {
+  PW_HD int correction(double pnorm, double* del_out, double told, int* ncf, double* rh, int* m_out) {
     int m = 0;
     double rate = 0., del = 0., delp = 0.;
+#pragma unroll
     for (int i = 0; i < N; ++i) y[i] = yh[1][i];
-    f(tn, y, savf);
-    ++nfe;
+    f.at(tn);
     for (;;) {
+      // the only evaluation of the right-hand side in the step loop (prja has the other)
+      f.eval(y, savf);
+      ++nfe;
       if (m == 0) {
         if (ipup > 0) {
           prja();
@@ -270,25 +411,30 @@ struct Lsoda {
           crate = 0.7;
           if (ierpj != 0) return corfailure(told, ncf, rh);
         }
+#pragma unroll
         for (int i = 0; i < N; ++i) acor[i] = 0.;
       }
       if (miter == 0) {
+#pragma unroll
         for (int i = 0; i < N; ++i) {
           savf[i] = h * savf[i] - yh[2][i];
           y[i] = savf[i] - acor[i];
         }
         del = vmnorm(y);
+#pragma unroll
         for (int i = 0; i < N; ++i) {
-          y[i] = yh[1][i] + el[1] * savf[i];
+          y[i] = yh[1][i] + el0 * savf[i];
           acor[i] = savf[i];
         }
       } else {
+#pragma unroll
         for (int i = 0; i < N; ++i) y[i] = h * savf[i] - (yh[2][i] + acor[i]);
         solsy(y);
         del = vmnorm(y);
+#pragma unroll
         for (int i = 0; i < N; ++i) {
           acor[i] += y[i];
-          y[i] = yh[1][i] + el[1] * acor[i];
+          y[i] = yh[1][i] + el0 * acor[i];
         }
       }
       // convergence test (label 400)
@@ -302,9 +448,9 @@ struct Lsoda {
           rate = fmax(rate, rm);
           crate = fmax(0.2 * crate, rm);
         }
-        const double dcon = del * fmin(1., 1.5 * crate) / (tesco(nq, 2) * conit);
+        const double dcon = del * fmin(1., 1.5 * crate) / (tq2 * conit);
         if (dcon <= 1.) {
-          pdest = fmax(pdest, rate / fabs(h * el[1]));
+          pdest = fmax(pdest, rate / fabs(h * el0));
           if (pdest != 0.) pdlast = pdest;
           conv = true;
         }
@@ -316,13 +462,10 @@ struct Lsoda {
         ipup = miter;
         // restart the corrector with a fresh Jacobian (label 220)
         m = 0; rate = 0.; del = 0.;
+#pragma unroll
         for (int i = 0; i < N; ++i) y[i] = yh[1][i];
-        f(tn, y, savf);
-        ++nfe;
       } else {
         delp = del;
-        f(tn, y, savf);
-        ++nfe;
       }
     }
   }
@@ -337,7 +480,7 @@ struct Lsoda {
     return 1;
   }
 
-  PW_LS void methodswitch(double dsm, double pnorm, double* pdh, double* rh) {
+  PW_HD void methodswitch(double dsm, double pnorm, double* pdh, double* rh) {
     if (meth == 1) {
       int nqm2;
       double rh2;
@@ -352,16 +495,10 @@ struct Lsoda {
         *pdh = pdlast * fabs(h);
         if ((*pdh * rh1) > 0.00001) rh1it = sm1(nq) / *pdh;
         rh1 = fmin(rh1, rh1it);
-        if (nq > mxords) {
-          nqm2 = mxords;
-          const int lm2 = mxords + 1;
-          const double dm2 = vmnorm(yh[lm2 + 1]) / tab.cm2[mxords];
-          rh2 = 1. / (1.2 * pw_root(dm2, lm2) + 0.0000012);
-        } else {
-          const double dm2 = dsm * (tab.cm1[nq] / tab.cm2[nq]);
-          rh2 = 1. / (1.2 * pw_root(dm2, l) + 0.0000012);
-          nqm2 = nq;
-        }
+        // (ODEPACK's branch for nq > mxords cannot be taken: nq <= 5 = mxords here)
+        const double dm2 = dsm * (tab.cm1[nq] / tab.cm2[nq]);
+        rh2 = 1. / (1.2 * pw_root(dm2, l) + 0.0000012);
+        nqm2 = nq;
         if (rh2 < ratio * rh1) return;
       }
       *rh = rh2;
@@ -380,20 +517,11 @@ struct Lsoda {
     // below is true whatever the two roots are: stay with BDF without evaluating them.
     // (In the stiff regime, where BDF is in use, pdh >> 1 on almost every step.)
     *pdh = pdnorm * fabs(h);
-    if (mxordn >= nq && ratio == 5. && *pdh >= 1.) return;
-    int nqm1, lm1;
-    double rh1, dm1;
-    if (mxordn < nq) {
-      nqm1 = mxordn;
-      lm1 = mxordn + 1;
-      dm1 = vmnorm(yh[lm1 + 1]) / tab.cm1[mxordn];
-      rh1 = 1. / (1.2 * pw_root(dm1, lm1) + 0.0000012);
-    } else {
-      dm1 = dsm * (tab.cm2[nq] / tab.cm1[nq]);
-      rh1 = 1. / (1.2 * pw_root(dm1, l) + 0.0000012);
-      nqm1 = nq;
-      lm1 = l;
-    }
+    if (ratio == 5. && *pdh >= 1.) return;
+    // (ODEPACK's branch for mxordn < nq cannot be taken: nq <= 5 < 12 = mxordn here)
+    double dm1 = dsm * (tab.cm2[nq] / tab.cm1[nq]);
+    double rh1 = 1. / (1.2 * pw_root(dm1, l) + 0.0000012);
+    const int nqm1 = nq, lm1 = l;
     double rh1it = 2. * rh1;
     *pdh = pdnorm * fabs(h);
     if ((*pdh * rh1) > 0.00001) rh1it = sm1(nqm1) / *pdh;
@@ -413,12 +541,14 @@ struct Lsoda {
   }
 
   // labels 540-630.  orderflag: 0 no change, 1 h changes, 2 h and nq change
-  PW_LS void orderswitch(double rhup, double dsm, double* pdh, double* rh, int* orderflag) {
+  PW_HD void orderswitch(double rhup, double dsm, double* pdh, double* rh, int* orderflag) {
     *orderflag = 0;
     double rhsm = 1. / (1.2 * pw_root(dsm, l) + 0.0000012);
     double rhdn = 0.;
     if (nq != 1) {
-      const double ddn = vmnorm(yh[l]) / tesco(nq, 1);
+      double top[N];
+      row_get(l, top);
+      const double ddn = vmnorm(top) / tq1;
       rhdn = 1. / (1.3 * pw_root(ddn, nq) + 0.0000013);
     }
     if (meth == 1) {
@@ -446,10 +576,13 @@ struct Lsoda {
       } else {
         *rh = rhup;
         if (*rh >= 1.1) {
-          const double r = el[l] / (double)l;
+          const double r = elp[l] / (double)l;
           nq = l;
           l = nq + 1;
-          for (int i = 0; i < N; ++i) yh[l][i] = acor[i] * r;
+          double top[N];
+#pragma unroll
+          for (int i = 0; i < N; ++i) top[i] = acor[i] * r;
+          row_set(l, top);
           *orderflag = 2;
           return;
         }
@@ -471,14 +604,15 @@ struct Lsoda {
   }
 
   PW_HD void endstoda() {  // labels 700-720
-    const double r = 1. / tesco(nqu, 2);
+    const double r = 1. / tq2u;
+#pragma unroll
     for (int i = 0; i < N; ++i) acor[i] *= r;
     hold = h;
     jstart = 1;
   }
 
   // One step of the core integrator (DSTODA).
-  PW_LS void stoda() {
+  PW_HD void stoda() {
     kflag = 0;
     const double told = tn;
     int ncf = 0;
@@ -530,50 +664,62 @@ struct Lsoda {
         return;
       }
       jcur = 0;
-      if (m == 0) dsm = del / tesco(nq, 2);
-      if (m > 0) dsm = vmnorm(acor) / tesco(nq, 2);
+      if (m == 0) dsm = del / tq2;
+      if (m > 0) dsm = vmnorm(acor) / tq2;
       if (dsm <= 1.) {
         // successful step
         kflag = 0;
         ++nst;
+#if defined(PW_LSODA_HIST) && !defined(__CUDA_ARCH__)
+        ++pw_lsoda_hist[meth - 1][nq];
+#endif
         hu = h;
         nqu = nq;
+        tq2u = tq2;
         mused = meth;
-        for (int j = 1; j <= l; ++j) {
-          const double r = el[j];
-          for (int i = 0; i < N; ++i) yh[j][i] += r * acor[i];
-        }
+#pragma unroll
+        for (int j = 1; j <= kF + 1; ++j)
+          if (j <= l) {
+            const double r = elp[j];
+#pragma unroll
+            for (int i = 0; i < N; ++i) yh[j][i] += r * acor[i];
+          }
+        if (nq > kF)
+          for (int j = kF + 2; j <= l; ++j) {
+            const double r = elp[j];
+            for (int i = 0; i < N; ++i) yhs_[(j) * N + i] += r * acor[i];
+          }
+        bool rescale = false;  // labels 175-180 + rmax = 10 before label 700
         --icount;
         if (icount < 0) {
           methodswitch(dsm, pnorm, &pdh, &rh);
-          if (meth != mused) {
-            rh = fmax(rh, 0.0 / fabs(h));
-            scaleh(&rh, &pdh);
-            rmax = 10.;
-            endstoda();
-            return;
+          if (meth != mused) rescale = true;
+        }
+        if (!rescale) {
+          --ialth;
+          if (ialth == 0) {
+            double rhup = 0.;
+            if (l != lmax) {
+              double top[N];
+              row_get(lmax, top);
+#pragma unroll
+              for (int i = 0; i < N; ++i) savf[i] = acor[i] - top[i];
+              const double dup = vmnorm(savf) / tq3;
+              rhup = 1. / (1.4 * pw_root(dup, l + 1) + 0.0000014);
+            }
+            int orderflag;
+            orderswitch(rhup, dsm, &pdh, &rh, &orderflag);
+            if (orderflag == 2) resetcoeff();
+            if (orderflag != 0) rescale = true;
+          } else if (!(ialth > 1 || l == lmax)) {
+            row_set(lmax, acor);
           }
         }
-        --ialth;
-        if (ialth == 0) {
-          double rhup = 0.;
-          if (l != lmax) {
-            for (int i = 0; i < N; ++i) savf[i] = acor[i] - yh[lmax][i];
-            const double dup = vmnorm(savf) / tesco(nq, 3);
-            rhup = 1. / (1.4 * pw_root(dup, l + 1) + 0.0000014);
-          }
-          int orderflag;
-          orderswitch(rhup, dsm, &pdh, &rh, &orderflag);
-          if (orderflag == 0) { endstoda(); return; }
-          if (orderflag == 2) resetcoeff();
+        if (rescale) {
           rh = fmax(rh, 0.0 / fabs(h));
           scaleh(&rh, &pdh);
           rmax = 10.;
-          endstoda();
-          return;
         }
-        if (ialth > 1 || l == lmax) { endstoda(); return; }
-        for (int i = 0; i < N; ++i) yh[lmax][i] = acor[i];
         endstoda();
         return;
       }
@@ -607,9 +753,12 @@ struct Lsoda {
       rh = 0.1;
       rh = fmax(0.0 / fabs(h), rh);
       h *= rh;
+#pragma unroll
       for (int i = 0; i < N; ++i) y[i] = yh[1][i];
-      f(tn, y, savf);
+      f.at_cold(tn);
+      f.eval(y, savf);
       ++nfe;
+#pragma unroll
       for (int i = 0; i < N; ++i) yh[2][i] = h * savf[i];
       ipup = miter;
       ialth = 5;
@@ -625,9 +774,23 @@ struct Lsoda {
     const double tp = tn - hu - 100. * kEps * copysign(fabs(tn) + fabs(hu), hu);
     if ((t - tp) * (t - tn) > 0.) return -2;
     const double s = (t - tn) / h;
-    for (int i = 0; i < N; ++i) dky[i] = yh[l][i];
-    for (int j = nq - 1; j >= 0; --j)
-      for (int i = 0; i < N; ++i) dky[i] = yh[j + 1][i] + s * dky[i];
+#pragma unroll
+    for (int i = 0; i < N; ++i) dky[i] = 0.;
+    if (nq > kF) {
+      for (int i = 0; i < N; ++i) dky[i] = yhs_[(l) * N + i];
+#pragma unroll 1
+      for (int j = l - 1; j >= kF + 2; --j)
+        for (int i = 0; i < N; ++i) dky[i] = yhs_[(j) * N + i] + s * dky[i];
+    }
+#pragma unroll
+    for (int j = kF + 1; j >= 1; --j) {
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+        const double v = yh[j][i];  // unconditional read, value select (see row_get)
+        const double hn = v + s * dky[i];
+        dky[i] = (j == l) ? v : ((j < l) ? hn : dky[i]);
+      }
+    }
     return 0;
   }
 
@@ -639,15 +802,23 @@ struct Lsoda {
   // call() strings them together exactly like one `lsoda(..., itask = 1)` invocation.
   PW_HD void reset() { started = false; }
 
-  PW_LS int begin(double t0, const double* y0, double tout) {
+  PW_HD int begin(double t0, const double* y0, double tout) {
     started = true;
     mxordn = kLsodaMaxOrdN; mxords = kLsodaMaxOrdS;
     hmxi = (o.hmax > 0.) ? 1. / o.hmax : 0.;
     tn = t0; tsw = t0; maxord = mxordn;
     jstart = 0; nhnil = 0; nst = 0; nje = 0; nslast = 0; hu = 0.; nqu = 0; mused = 0; miter = 0;
     meth = 1; jtyp = 2;
+#pragma unroll
+    for (int j = 1; j <= kF + 1; ++j)
+#pragma unroll
+      for (int i = 0; i < N; ++i) yh[j][i] = 0.;
+    for (int j = 0; j <= kQ + 1; ++j)
+      for (int i = 0; i < N; ++i) yhs_[(j) * N + i] = 0.;
+#pragma unroll
     for (int i = 0; i < N; ++i) { y[i] = y0[i]; yh[1][i] = y0[i]; }
-    f(tn, y, yh[2]);
+    f.at_cold(tn);
+    f.eval(y, yh[2]);
     nfe = 1;
     nq = 1;
     h = 1.;
@@ -674,6 +845,7 @@ struct Lsoda {
     const double rh = fabs(h0) * hmxi;
     if (rh > 1.) h0 /= rh;
     h = h0;
+#pragma unroll
     for (int i = 0; i < N; ++i) yh[2][i] *= h0;
     return 0;
   }
@@ -682,7 +854,7 @@ struct Lsoda {
   PW_HD bool reached(double tout) const { return (tn - tout) * h >= 0.; }
 
   // Returns 0 after a successful step, < 0 (ODEPACK istate) on failure.
-  PW_LS int advance_one() {
+  PW_HD int advance_one() {
     if (nst != 0 || jstart != 0) {  // label 250 (skipped on the very first pass)
       if ((nst - nslast) >= o.mxstep) return -1;
       if (!ewset(yh[1])) return -6;
@@ -703,6 +875,11 @@ struct Lsoda {
     return (kflag == -1) ? -4 : -5;
   }
 
+  PW_HD void current(double* yout) const {
+#pragma unroll
+    for (int i = 0; i < N; ++i) yout[i] = yh[1][i];
+  }
+
   // One `lsoda(..., itask = 1)` call: advance to tout and interpolate.
   // First call initialises from (t0, y0).  Returns istate.
   PW_HD int call(double t0, const double* y0, double tout, double* yout) {
@@ -716,7 +893,7 @@ struct Lsoda {
     for (;;) {
       const int rc = advance_one();
       if (rc < 0) {
-        for (int i = 0; i < N; ++i) yout[i] = yh[1][i];
+        current(yout);
         return rc;
       }
       if (!reached(tout)) continue;

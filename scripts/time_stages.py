@@ -37,3 +37,7 @@ for rep in range(int(os.environ.get('REPS', '3'))):
     print('N=%d lanes=%s rep %d total %.1f ms -> %.0f models/s | H %.1f He %.1f RT %.1f ms' % (N, os.environ.get('PWB_HE_LANES', 'auto'), rep, tot, T.size / tot * 1e3, ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2]), ev[2].elapsed_time(ev[3])))
 nst = he['scal'][:, 2].cpu().numpy(); nfe = he['scal'][:, 1].cpu().numpy(); st = he['status'].cpu().numpy()
 print('  He nst mean %.0f max %.0f p99 %.0f | nfe mean %.0f max %.0f | status counts' % (nst.mean(), nst.max(), np.percentile(nst, 99), nfe.mean(), nfe.max()), np.bincount(st, minlength=5).tolist(), 'relax max', he['scal'][:, 0].max().item())
+if os.environ.get('DUMP'):
+    os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
+    np.savez(os.path.join(ROOT, 'gpurun_out', os.environ['DUMP']), T=T, md=md, nst=nst, nfe=nfe, status=st,
+             n_relax=he['scal'][:, 0].cpu().numpy(), nje=he['scal'][:, 3].cpu().numpy())

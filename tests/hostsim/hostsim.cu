@@ -86,7 +86,8 @@ int hs_he_population(const double* model, const double* opts, const double* rate
   HeWork w{b, b + nr, b + 2 * nr, b + 3 * nr, b + 4 * nr, b + 5 * nr};
   int status = 0;
   HeOut o{f1, f3, scal, rates_out, &status};
-  he_population_model(p, tab, r, v, rho, f_h, nr, w, o);
+  if (p.method == PW_HE_RK45) he_population_model<true>(p, tab, r, v, rho, f_h, nr, w, o);
+  else he_population_model<false>(p, tab, r, v, rho, f_h, nr, w, o);
   return status;
 }
 
@@ -103,10 +104,13 @@ void hs_lsoda_tables(double* elco, double* tesco) {
 // against scipy (no libm in the RHS, so both sides evaluate identical doubles).
 struct VdpRhs {
   double mu;
-  PW_HD void operator()(double, const double* y, double* d) {
+  PW_HD void at(double) {}
+  PW_HD void at_cold(double) {}
+  PW_HD void eval(const double* y, double* d) const {
     d[0] = y[1];
     d[1] = mu * ((1.0 - y[0] * y[0]) * y[1]) - y[0];
   }
+  PW_HD void operator()(double, const double* y, double* d) { eval(y, d); }
 };
 
 extern "C" {
@@ -117,7 +121,8 @@ int hs_lsoda_vdp(double mu, const double* y0, const double* t, int n, double rto
   lsoda_tables_init(&tab);
   VdpRhs rhs{mu};
   LsodaOpts lo{rtol, atol, mxstep, 0., 0.};
-  Lsoda<2, VdpRhs> s(rhs, tab, lo);
+  double hi_rows[Lsoda<2, VdpRhs>::kHiDoubles];
+  Lsoda<2, VdpRhs> s(rhs, tab, lo, hi_rows);
   yout[0] = y0[0]; yout[1] = y0[1];
   for (int k = 1; k < n; ++k) {
     const int istate = s.call(t[0], y0, t[k], &yout[2 * k]);
