@@ -176,8 +176,8 @@ k_helium(int B, int lanes, const double* __restrict__ T, const double* __restric
   p.relax = o.relax_solution; p.max_n_relax = o.max_n_relax; p.convergence = o.convergence;
   for (int k = 0; k < 6; ++k) p.rates[k] = o.rates[k];
   p.method = o.method; p.rtol = o.rtol; p.atol = o.atol; p.first_step = o.first_step; p.max_step = o.max_step;
-  double* wb = work + (size_t)b * 10 * nr;
-  HeWork w{wb, wb + nr, wb + 2 * nr, wb + 3 * nr, wb + 4 * nr, wb + 5 * nr};
+  double* wb = work + (size_t)b * kHeWorkPerRadius * nr;
+  HeWork w{wb, wb + nr, wb + 2 * nr, wb + 3 * nr, wb + 4 * nr, wb + 5 * nr, wb + 10 * nr};
   HeOut out{f1 + (size_t)b * nr, f3 + (size_t)b * nr, scal + (size_t)b * 4,
             rates ? rates + (size_t)b * 11 * nr : nullptr, status + b};
   he_population_model<kRk45>(p, *tab, r, v + (size_t)b * nr, rho + (size_t)b * nr, f_h + (size_t)b * nr, nr, w, out);
@@ -708,7 +708,7 @@ int pwb_he_population_batch(pwb_ctx* c, int B, const double* d_T, const double* 
   if (B <= 0) return 0;
   if (Nr < 2) return fail(c, "pwb_he_population_batch: radius profile needs >= 2 points");
   if (o->method < 0 || o->method > 2) return fail(c, "pwb_he_population_batch: unsupported method");
-  if (c->he_work.ensure(sizeof(double) * 10 * (size_t)Nr * B)) return fail(c, "out of device memory");
+  if (c->he_work.ensure(sizeof(double) * kHeWorkPerRadius * (size_t)Nr * B)) return fail(c, "out of device memory");
   return launch_helium(c, (cudaStream_t)stream, B, he_lanes(c, B), d_T, d_hfrac, d_vs, d_rs, d_rhos, sstride, d_r,
                        Nr, d_v, d_rho, d_f_h, o, c->he_work.as<double>(), d_f1, d_f3, d_scal, d_rates, d_status);
 }
@@ -826,7 +826,7 @@ int pwb_forward_batch(pwb_ctx* c, int B, const double* d_T, const double* d_mdot
   if (c->fw_f.ensure(sizeof(double) * (bn * 5 + B)) || c->fw_scal.ensure(sizeof(double) * (size_t)B * 8) ||
       c->fw_he.ensure(sizeof(double) * (size_t)B * 4) || c->fw_n.ensure(sizeof(double) * bn) ||
       c->fw_v.ensure(sizeof(double) * bn) || c->fw_T.ensure(sizeof(double) * B) ||
-      c->he_work.ensure(sizeof(double) * 10 * bn) || c->rt_ncol.ensure(sizeof(double) * bn) ||
+      c->he_work.ensure(sizeof(double) * kHeWorkPerRadius * bn) || c->rt_ncol.ensure(sizeof(double) * bn) ||
       c->rt_sums.ensure(sizeof(double) * (size_t)B * 4) ||
       (nsplit > 1 && c->rt_partial.ensure(sizeof(double) * (size_t)B * nsplit * Nw)) ||
       (rtopts->wind_broadening_method == 1 && c->rt_tau.ensure(sizeof(double) * bn * Nw)))
@@ -872,7 +872,7 @@ int pwb_forward_batch(pwb_ctx* c, int B, const double* d_T, const double* d_mdot
     if (species == 0) {
       if (launch_helium(c, cs, nb, lanes, d_T + o1, d_hfrac + o1, hscal + o1 * 8 + 1, hscal + o1 * 8 + 2,
                         hscal + o1 * 8 + 3, 8, d_r, Nr, v + oN, rho + oN, f_r + oN, heopts,
-                        c->he_work.as<double>() + 10 * oN, f1 + oN, f3 + oN, hescal + o1 * 4, nullptr, d_status + o1))
+                        c->he_work.as<double>() + kHeWorkPerRadius * oN, f1 + oN, f3 + oN, hescal + o1 * 4, nullptr, d_status + o1))
         return -1;
     }
     k_he_density<<<(unsigned)(((size_t)nb * Nr + 255) / 256), 256, 0, cs>>>(

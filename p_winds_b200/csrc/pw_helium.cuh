@@ -55,6 +55,7 @@ PW_HD_NOINLINE void he_collision(double T, double* q13, double* q31a, double* q3
 // Jacobian of one LSODA step all evaluate at the same x.
 struct HeRhs {
   const double *rn, *v, *rho, *fh, *tau1, *tau3;
+  const double* slope;  // [5][n]: np.interp slopes of v, rho, fh, tau1, tau3 per cell (HeWork::slope)
   int n;
   double lk1;         // log(k1)
   double lc[8];       // log of alpha_rec_1, alpha_rec_3, q_13, q_31a, q_31b, Q_31, Q_He, Q_He+
@@ -81,15 +82,12 @@ struct HeRhs {
       t1 = np_interp_at_out(rn, tau1, n, x, jj);
       t3 = np_interp_at_out(rn, tau3, n, x, jj);
     } else {
-      if (jj != jc) {  // slopes exactly as numpy forms them, kept while x stays in the cell
+      if (jj != jc) {  // the cell's base values and slopes, kept while x stays in the cell
         jc = jj;
         x0 = rn[jj];
-        const double dx = rn[jj + 1] - x0;
-        b0[0] = v[jj]; sl[0] = (v[jj + 1] - b0[0]) / dx;
-        b0[1] = rho[jj]; sl[1] = (rho[jj + 1] - b0[1]) / dx;
-        b0[2] = fh[jj]; sl[2] = (fh[jj + 1] - b0[2]) / dx;
-        b0[3] = tau1[jj]; sl[3] = (tau1[jj + 1] - b0[3]) / dx;
-        b0[4] = tau3[jj]; sl[4] = (tau3[jj + 1] - b0[4]) / dx;
+        b0[0] = v[jj]; b0[1] = rho[jj]; b0[2] = fh[jj]; b0[3] = tau1[jj]; b0[4] = tau3[jj];
+#pragma unroll
+        for (int q = 0; q < 5; ++q) sl[q] = slope[q * n + jj];
       }
       const double d = x - x0;
       v_ = sl[0] * d + b0[0];
@@ -168,6 +166,13 @@ struct HeRhs {
     *this = t;
   }
   PW_HD void eval(const double* y, double* dydx) const { eval(y, dydx, nullptr); }
+  PW_HD_NOINLINE void eval_out(const double* y, double* dydx) const { eval(y, dydx, nullptr); }
+  PW_HD void eval_cold(const double* y, double* dydx) const {
+    const HeRhs t = *this;
+    double yy[2] = {y[0], y[1]}, dd[2];
+    t.eval_out(yy, dd);
+    dydx[0] = dd[0]; dydx[1] = dd[1];
+  }
   PW_HD void operator()(double x, const double* y, double* dydx) {
     if (!(x == xc)) coeffs_out(x);
     eval(y, dydx, nullptr);
@@ -177,8 +182,17 @@ struct HeRhs {
 // Per-model scratch (global memory on the device), Nr doubles each.
 struct HeWork {
   double *rn, *tau1, *tau3, *tau1h, *tau3h;
-  double* w;  // 5*Nr: [0,Nr) dr*density, [Nr,3Nr) previous profiles, [3Nr,5Nr) RK45 output staging
+  double* w;      // 5*Nr: [0,Nr) dr*density, [Nr,3Nr) previous profiles, [3Nr,5Nr) RK45 output staging
+  double* slope;  // 5*Nr: np.interp slopes (fp[j+1]-fp[j])/(xp[j+1]-xp[j]) of v, rho, fh, tau1, tau3
 };
+constexpr int kHeWorkPerRadius = 15;  // doubles of HeWork per radius and model
+
+// slope table of one interpolated profile, exactly as numpy forms each slope
+PW_HD_NOINLINE void he_slopes(const double* xp, const double* fp, int n, double* out) {
+#pragma unroll 1
+  for (int j = 0; j < n - 1; ++j) out[j] = (fp[j + 1] - fp[j]) / (xp[j + 1] - xp[j]);
+  out[n - 1] = 0.0;
+}
 
 struct HeOut {
   double* f1;      // [Nr]
@@ -283,7 +297,11 @@ PW_HD void he_population_model(const HeParams& p, const LsodaTables& tab, const 
   }
   HeRhs rhs;
   rhs.rn = w.rn; rhs.v = v; rhs.rho = rho; rhs.fh = f_h; rhs.tau1 = w.tau1; rhs.tau3 = w.tau3;
+  rhs.slope = w.slope;
   rhs.n = nr;
+  he_slopes(w.rn, v, nr, w.slope);
+  he_slopes(w.rn, rho, nr, w.slope + nr);
+  he_slopes(w.rn, f_h, nr, w.slope + 2 * nr);
 #if defined(PW_HE_LOGEXP)
   rhs.lk1 = log(k1);
   rhs.lc[0] = log(a_r1); rhs.lc[1] = log(a_r3); rhs.lc[2] = log(q13); rhs.lc[3] = log(q31a);
@@ -325,6 +343,8 @@ PW_HD void he_population_model(const HeParams& p, const LsodaTables& tab, const 
       }
       for (int i = 0; i < nr; ++i) { s1 += f1[i]; s3 += f3[i]; p1[i] = f1[i]; p3[i] = f3[i]; }
     }
+    he_slopes(w.rn, w.tau1, nr, w.slope + 3 * nr);
+    he_slopes(w.rn, w.tau3, nr, w.slope + 4 * nr);
     const bool ok = he_solve<kRk45>(p, rhs, tab, nr, f1, f3, ytmp, &nfe, &nst, &nje);
     if (!ok) {
       if (it == 0 || p.method != PW_HE_ODEINT) {

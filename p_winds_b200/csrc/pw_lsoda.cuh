@@ -29,6 +29,7 @@ constexpr int kLsodaMaxOrdS = 5;   // BDF
 struct LsodaTables {
   double elco[2][13][14];
   double tesco[2][13][4];
+  double rtesco2[2][13];  // 1 / tesco[meth][nq][2] (label 700 scales acor by it)
   double cm1[13], cm2[6];
   double sm1[13];  // Adams stability-region bounds used by the switching logic
 };
@@ -90,6 +91,8 @@ PW_HD void lsoda_tables_init(LsodaTables* t) {
       rq1fac /= fnq;
     }
   }
+  for (int m = 0; m < 2; ++m)
+    for (int a = 0; a < 13; ++a) t->rtesco2[m][a] = (t->tesco[m][a][2] != 0.) ? 1. / t->tesco[m][a][2] : 0.;
   for (int i = 1; i <= 5; ++i) t->cm2[i] = t->tesco[1][i][2] * t->elco[1][i][i + 1];
   for (int i = 1; i <= 12; ++i) t->cm1[i] = t->tesco[0][i][2] * t->elco[0][i][i + 1];
   const double s[13] = {0., 0.5, 0.575, 0.55, 0.45, 0.35, 0.25, 0.2, 0.15, 0.1, 0.075, 0.05, 0.025};
@@ -154,7 +157,7 @@ struct Lsoda {
   int ipvt[N];
   const double* elp;     // elco[meth_tab][nq] in force (ODEPACK: el(1..l))
   double tq1, tq2, tq3;  // tesco(nq, 1..3) of the same table row
-  double tq2u;           // tesco(nqu, 2) as label 700 reads it
+  double rtq2, rtq2u;    // 1 / tesco(nq, 2); the same for (nqu, table in force) as label 700 reads it
   double tn, h, hu, hold, rc, el0, crate, conit, rmax, pdnorm, pdest, pdlast, ratio, hmxi, tsw;
   int nq, l, lmax, meth, mused, meth_tab, miter, jtyp, maxord, mxordn, mxords;
   int ialth, ipup, nslp, icount, irflag, jstart, kflag, jcur, ierpj, iersl;
@@ -167,7 +170,10 @@ struct Lsoda {
   PW_HD double vmnorm(const double* v) const {
     double vm = 0.0;
 #pragma unroll
-    for (int i = 0; i < N; ++i) vm = fmax(vm, fabs(v[i]) * ewt[i]);
+    for (int i = 0; i < N; ++i) {
+      const double a = fabs(v[i]) * ewt[i];
+      vm = (a > vm) ? a : vm;  // == fmax(vm, a) for vm >= 0
+    }
     return vm;
   }
   PW_HD bool ewset(const double* yc) {
@@ -182,7 +188,7 @@ struct Lsoda {
   }
   // yh[k] for a run-time row index
   PW_HD void row_get(int k, double* out) const {
-    if (k > kF + 1) {
+    if (PW_UNLIKELY(k > kF + 1)) {
       for (int i = 0; i < N; ++i) out[i] = yhs_[(k) * N + i];
       return;
     }
@@ -201,7 +207,7 @@ struct Lsoda {
     }
   }
   PW_HD void row_set(int k, const double* in) {
-    if (k > kF + 1) {
+    if (PW_UNLIKELY(k > kF + 1)) {
       for (int i = 0; i < N; ++i) yhs_[(k) * N + i] = in[i];
       return;
     }
@@ -223,6 +229,7 @@ struct Lsoda {
     elp = tab.elco[meth_tab - 1][nq];
     const double* tq = tab.tesco[meth_tab - 1][nq];
     tq1 = tq[1]; tq2 = tq[2]; tq3 = tq[3];
+    rtq2 = tab.rtesco2[meth_tab - 1][nq];
     const double el1 = elp[1];
     rc = rc * el1 / el0;
     el0 = el1;
@@ -247,7 +254,7 @@ struct Lsoda {
 #pragma unroll
         for (int i = 0; i < N; ++i) yh[j][i] *= r;
       }
-    if (nq > kF)
+    if (PW_UNLIKELY(nq > kF))
 #pragma unroll 1
       for (int j = kF + 2; j <= l; ++j) {
         r *= *rh;
@@ -265,7 +272,7 @@ struct Lsoda {
   template <int kSign>
   PW_HD void pascal() {
     double hand[(kF + 1) * N];
-    if (nq > kF) lsoda_pascal_hi<N>(yhs_, nq, kF, (double)kSign, hand);
+    if (PW_UNLIKELY(nq > kF)) lsoda_pascal_hi<N>(yhs_, nq, kF, (double)kSign, hand);
 #pragma unroll
     for (int j = kF + 1; j >= 1; --j)
       if (j <= nq) {
@@ -275,7 +282,7 @@ struct Lsoda {
 #pragma unroll
             for (int i = 0; i < N; ++i) yh[i1][i] += kSign * yh[i1 + 1][i];
           }
-        if (nq > kF) {
+        if (PW_UNLIKELY(nq > kF)) {
 #pragma unroll
           for (int i = 0; i < N; ++i) yh[kF + 1][i] += kSign * hand[(kF + 1 - j) * N + i];
         }
@@ -390,9 +397,9 @@ struct Lsoda {
     }
   }
 
-  // stoda corrector loop (labels 220-450).  Returns corflag: 0 converged,
-  // 1 retry with smaller h (rh set), 2 give up (kflag = -2).
-  PW_HD int correction(double pnorm, double* del_out, double told, int* ncf, double* rh, int* m_out) {
+  // stoda corrector loop (labels 220-430).  Returns true when the corrector failed to
+  // converge (label 430: the caller retracts, and retries with h/4 or gives up).
+  PW_HD bool correction(double pnorm, double* del_out, int* m_out) {
     int m = 0;
     double rate = 0., del = 0., delp = 0.;
 #pragma unroll
@@ -409,7 +416,7 @@ struct Lsoda {
           rc = 1.;
           nslp = nst;
           crate = 0.7;
-          if (ierpj != 0) return corfailure(told, ncf, rh);
+          if (ierpj != 0) return true;
         }
 #pragma unroll
         for (int i = 0; i < N; ++i) acor[i] = 0.;
@@ -438,27 +445,27 @@ struct Lsoda {
         }
       }
       // convergence test (label 400)
-      bool conv = false;
-      if (del <= 100. * pnorm * kEps) {
-        conv = true;
-      } else if (m != 0 || meth != 1) {
+      if (del <= 100. * pnorm * kEps) break;
+      if (m != 0 || meth != 1) {
         if (m != 0) {
           double rm = 1024.;
           if (del <= (1024. * delp)) rm = del / delp;
-          rate = fmax(rate, rm);
-          crate = fmax(0.2 * crate, rm);
+          rate = (rm > rate) ? rm : rate;
+          const double c2 = 0.2 * crate;
+          crate = (rm > c2) ? rm : c2;
         }
-        const double dcon = del * fmin(1., 1.5 * crate) / (tq2 * conit);
+        const double c15 = 1.5 * crate;
+        const double dcon = del * ((c15 < 1.) ? c15 : 1.) / (tq2 * conit);
         if (dcon <= 1.) {
-          pdest = fmax(pdest, rate / fabs(h * el0));
+          const double pd = rate / fabs(h * el0);
+          pdest = (pd > pdest) ? pd : pdest;
           if (pdest != 0.) pdlast = pdest;
-          conv = true;
+          break;
         }
       }
-      if (conv) { *del_out = del; *m_out = m; return 0; }
       ++m;
       if (m == 3 /*maxcor*/ || (m >= 2 && del > 2. * delp)) {
-        if (miter == 0 || jcur == 1) return corfailure(told, ncf, rh);
+        if (miter == 0 || jcur == 1) return true;
         ipup = miter;
         // restart the corrector with a fresh Jacobian (label 220)
         m = 0; rate = 0.; del = 0.;
@@ -468,16 +475,9 @@ struct Lsoda {
         delp = del;
       }
     }
-  }
-  PW_HD int corfailure(double told, int* ncf, double* rh) {  // label 430
-    ++(*ncf);
-    rmax = 2.;
-    tn = told;
-    retract();
-    if (fabs(h) <= 0.0 /*hmin*/ * 1.00001 || *ncf == 10 /*mxncf*/) return 2;
-    *rh = 0.25;
-    ipup = miter;
-    return 1;
+    *del_out = del;
+    *m_out = m;
+    return false;
   }
 
   PW_HD void methodswitch(double dsm, double pnorm, double* pdh, double* rh) {
@@ -604,14 +604,16 @@ struct Lsoda {
   }
 
   PW_HD void endstoda() {  // labels 700-720
-    const double r = 1. / tq2u;
 #pragma unroll
-    for (int i = 0; i < N; ++i) acor[i] *= r;
+    for (int i = 0; i < N; ++i) acor[i] *= rtq2u;
     hold = h;
     jstart = 1;
   }
 
-  // One step of the core integrator (DSTODA).
+  // One step of the core integrator (DSTODA).  ODEPACK's goto web is laid out as ONE loop
+  // with one copy of each block -- coefficient reload (label 150), rescale (175-180),
+  // predict + correct (200-450), retract, order selection (540-630) -- selected by flags, so
+  // that the step loop stays inside the instruction cache.  hmin = 0 throughout.
   PW_HD void stoda() {
     kflag = 0;
     const double told = tn;
@@ -619,13 +621,16 @@ struct Lsoda {
     ierpj = 0; iersl = 0; jcur = 0;
     double rh = 0., pdh = 0., del = 0., dsm = 0.;
     int m = 0;
+    bool reload = false;   // label 150 pending
+    bool rescale = false;  // labels 175-180 pending ...
+    bool finish = false;   // ... followed by rmax = 10 and label 700 (successful step)
     if (jstart == 0) {
       lmax = maxord + 1;
       nq = 1; l = 2; ialth = 2; rmax = 10000.; rc = 0.; el0 = 1.; crate = 0.7;
       hold = h; nslp = 0; ipup = miter;
       icount = 20; irflag = 0; pdest = 0.; pdlast = 0.; ratio = 5.;
       meth_tab = 1;
-      resetcoeff();
+      reload = true;
     }
     if (jstart == -1) {
       ipup = miter;
@@ -634,39 +639,61 @@ struct Lsoda {
       if (meth != mused) {
         meth_tab = meth;  // call dcfode(meth, elco, tesco)
         ialth = l;
-        resetcoeff();
+        reload = true;
       }
       if (h != hold) {
         rh = h / hold;
         h = hold;
-        scaleh(&rh, &pdh);
+        rescale = true;
       }
     }
     for (;;) {
-      // prediction + corrector, retried while the corrector fails
-      double pnorm;
-      for (;;) {
-        if (fabs(rc - 1.) > 0.3 /*ccmax*/) ipup = miter;
-        if (nst >= nslp + 20 /*msbp*/) ipup = miter;
-        tn += h;
-        predict();
-        pnorm = vmnorm(yh[1]);
-        const int corflag = correction(pnorm, &del, told, &ncf, &rh, &m);
-        if (corflag == 0) break;
-        if (corflag == 1) {
-          rh = fmax(rh, 0.0 /*hmin*/ / fabs(h));
-          scaleh(&rh, &pdh);
-          continue;
-        }
-        kflag = -2;
-        hold = h;
-        jstart = 1;
-        return;
+      if (reload) {
+        resetcoeff();
+        reload = false;
       }
-      jcur = 0;
-      if (m == 0) dsm = del / tq2;
-      if (m > 0) dsm = vmnorm(acor) / tq2;
-      if (dsm <= 1.) {
+      if (rescale) {
+        scaleh(&rh, &pdh);
+        rescale = false;
+        if (finish) {
+          rmax = 10.;
+          endstoda();
+          return;
+        }
+      }
+      // prediction + corrector
+      if (fabs(rc - 1.) > 0.3 /*ccmax*/) ipup = miter;
+      if (nst >= nslp + 20 /*msbp*/) ipup = miter;
+      tn += h;
+      predict();
+      const double pnorm = vmnorm(yh[1]);
+      const bool cfail = correction(pnorm, &del, &m);
+      bool efail = false;
+      if (!cfail) {
+        jcur = 0;
+        dsm = ((m == 0) ? del : vmnorm(acor)) / tq2;
+        efail = !(dsm <= 1.);
+      }
+      if (cfail || efail) {  // labels 430 / 500 start the same way
+        tn = told;
+        retract();
+        rmax = 2.;
+      }
+      if (cfail) {
+        ++ncf;
+        if (h == 0. || ncf == 10 /*mxncf*/) {
+          kflag = -2;
+          hold = h;
+          jstart = 1;
+          return;
+        }
+        rh = 0.25;
+        ipup = miter;
+        rescale = true;
+        continue;
+      }
+      double rhup = 0.;
+      if (!efail) {
         // successful step
         kflag = 0;
         ++nst;
@@ -675,7 +702,7 @@ struct Lsoda {
 #endif
         hu = h;
         nqu = nq;
-        tq2u = tq2;
+        rtq2u = rtq2;
         mused = meth;
 #pragma unroll
         for (int j = 1; j <= kF + 1; ++j)
@@ -684,88 +711,84 @@ struct Lsoda {
 #pragma unroll
             for (int i = 0; i < N; ++i) yh[j][i] += r * acor[i];
           }
-        if (nq > kF)
+        if (PW_UNLIKELY(nq > kF))
+#pragma unroll 1
           for (int j = kF + 2; j <= l; ++j) {
             const double r = elp[j];
             for (int i = 0; i < N; ++i) yhs_[(j) * N + i] += r * acor[i];
           }
-        bool rescale = false;  // labels 175-180 + rmax = 10 before label 700
         --icount;
         if (icount < 0) {
           methodswitch(dsm, pnorm, &pdh, &rh);
-          if (meth != mused) rescale = true;
-        }
-        if (!rescale) {
-          --ialth;
-          if (ialth == 0) {
-            double rhup = 0.;
-            if (l != lmax) {
-              double top[N];
-              row_get(lmax, top);
-#pragma unroll
-              for (int i = 0; i < N; ++i) savf[i] = acor[i] - top[i];
-              const double dup = vmnorm(savf) / tq3;
-              rhup = 1. / (1.4 * pw_root(dup, l + 1) + 0.0000014);
-            }
-            int orderflag;
-            orderswitch(rhup, dsm, &pdh, &rh, &orderflag);
-            if (orderflag == 2) resetcoeff();
-            if (orderflag != 0) rescale = true;
-          } else if (!(ialth > 1 || l == lmax)) {
-            row_set(lmax, acor);
+          if (meth != mused) {
+            rescale = true;
+            finish = true;
+            continue;
           }
         }
-        if (rescale) {
-          rh = fmax(rh, 0.0 / fabs(h));
-          scaleh(&rh, &pdh);
-          rmax = 10.;
+        --ialth;
+        if (ialth != 0) {
+          if (!(ialth > 1 || l == lmax)) row_set(lmax, acor);
+          endstoda();
+          return;
         }
-        endstoda();
-        return;
+        if (l != lmax) {
+          double top[N];
+          row_get(lmax, top);
+#pragma unroll
+          for (int i = 0; i < N; ++i) savf[i] = acor[i] - top[i];
+          const double dup = vmnorm(savf) / tq3;
+          rhup = 1. / (1.4 * pw_root(dup, l + 1) + 0.0000014);
+        }
+      } else {
+        // error test failed (label 500)
+        --kflag;
+        if (h == 0.) {
+          kflag = -1; hold = h; jstart = 1;
+          return;
+        }
+        if (kflag <= -3) {
+          // three or more failures: reset to order 1 (label 640)
+          if (kflag == -10) {
+            kflag = -1; hold = h; jstart = 1;
+            return;
+          }
+          rh = 0.1;
+          h *= rh;
+#pragma unroll
+          for (int i = 0; i < N; ++i) y[i] = yh[1][i];
+          f.at_cold(tn);
+          f.eval_cold(y, savf);
+          ++nfe;
+#pragma unroll
+          for (int i = 0; i < N; ++i) yh[2][i] = h * savf[i];
+          ipup = miter;
+          ialth = 5;
+          if (nq != 1) {
+            nq = 1;
+            l = 2;
+            reload = true;
+          }
+          continue;
+        }
       }
-      // error test failed (label 500)
-      --kflag;
-      tn = told;
-      retract();
-      rmax = 2.;
-      if (fabs(h) <= 0.0 /*hmin*/ * 1.00001) {
-        kflag = -1; hold = h; jstart = 1;
-        return;
-      }
-      if (kflag > -3) {
-        int orderflag;
-        orderswitch(0., dsm, &pdh, &rh, &orderflag);
+      // order / step-size selection (labels 540-630), after a success with ialth = 0 or
+      // after a first or second error-test failure
+      int orderflag;
+      orderswitch(rhup, dsm, &pdh, &rh, &orderflag);
+      if (!efail) {
         if (orderflag == 0) {
-          // label 610 reached from a failed step: "ialth = 3; go to 700" cannot
-          // happen here because kflag < 0 skips the 10 percent test
-          rh = fmin(rh, 0.2);
+          endstoda();
+          return;
         }
-        if (orderflag == 2) resetcoeff();
-        rh = fmax(rh, 0.0 / fabs(h));
-        scaleh(&rh, &pdh);
-        continue;
+        finish = true;
+      } else if (orderflag == 0) {
+        // label 610 reached from a failed step: "ialth = 3; go to 700" cannot
+        // happen here because kflag < 0 skips the 10 percent test
+        rh = (rh < 0.2) ? rh : 0.2;
       }
-      // three or more failures: reset to order 1 (label 640)
-      if (kflag == -10) {
-        kflag = -1; hold = h; jstart = 1;
-        return;
-      }
-      rh = 0.1;
-      rh = fmax(0.0 / fabs(h), rh);
-      h *= rh;
-#pragma unroll
-      for (int i = 0; i < N; ++i) y[i] = yh[1][i];
-      f.at_cold(tn);
-      f.eval(y, savf);
-      ++nfe;
-#pragma unroll
-      for (int i = 0; i < N; ++i) yh[2][i] = h * savf[i];
-      ipup = miter;
-      ialth = 5;
-      if (nq == 1) continue;
-      nq = 1;
-      l = 2;
-      resetcoeff();
+      if (orderflag == 2) reload = true;
+      rescale = true;
     }
   }
 
@@ -776,7 +799,7 @@ struct Lsoda {
     const double s = (t - tn) / h;
 #pragma unroll
     for (int i = 0; i < N; ++i) dky[i] = 0.;
-    if (nq > kF) {
+    if (PW_UNLIKELY(nq > kF)) {
       for (int i = 0; i < N; ++i) dky[i] = yhs_[(l) * N + i];
 #pragma unroll 1
       for (int j = l - 1; j >= kF + 2; --j)
@@ -818,7 +841,7 @@ struct Lsoda {
 #pragma unroll
     for (int i = 0; i < N; ++i) { y[i] = y0[i]; yh[1][i] = y0[i]; }
     f.at_cold(tn);
-    f.eval(y, yh[2]);
+    f.eval_cold(y, yh[2]);
     nfe = 1;
     nq = 1;
     h = 1.;

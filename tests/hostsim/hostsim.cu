@@ -81,9 +81,9 @@ int hs_he_population(const double* model, const double* opts, const double* rate
   p.max_n_relax = (int)opts[4]; p.convergence = opts[5]; p.method = (int)opts[6];
   p.rtol = opts[7]; p.atol = opts[8]; p.first_step = opts[9]; p.max_step = opts[10];
   for (int i = 0; i < 6; ++i) p.rates[i] = rates[i];
-  std::vector<double> buf(10 * nr);
+  std::vector<double> buf(kHeWorkPerRadius * nr);
   double* b = buf.data();
-  HeWork w{b, b + nr, b + 2 * nr, b + 3 * nr, b + 4 * nr, b + 5 * nr};
+  HeWork w{b, b + nr, b + 2 * nr, b + 3 * nr, b + 4 * nr, b + 5 * nr, b + 10 * nr};
   int status = 0;
   HeOut o{f1, f3, scal, rates_out, &status};
   if (p.method == PW_HE_RK45) he_population_model<true>(p, tab, r, v, rho, f_h, nr, w, o);
@@ -106,6 +106,7 @@ struct VdpRhs {
   double mu;
   PW_HD void at(double) {}
   PW_HD void at_cold(double) {}
+  PW_HD void eval_cold(const double* y, double* d) const { eval(y, d); }
   PW_HD void eval(const double* y, double* d) const {
     d[0] = y[1];
     d[1] = mu * ((1.0 - y[0] * y[0]) * y[1]) - y[0];
@@ -181,6 +182,10 @@ void hs_tau_average(const double* r, const double* n, const double* v, const dou
 }  // extern "C"
 
 #include "../../p_winds_b200/csrc/pw_draw.cuh"
+
+extern "C" void hs_root_newton(const double* a, const int* k, int n, double* out) {
+  for (int i = 0; i < n; ++i) out[i] = pw::pw_root_newton(a[i], k[i]);
+}
 
 extern "C" void hs_pil_ellipse_rows(double x0, double y0, double x1, double y1, int n, int* lo, int* hi) {
   pw::pil_ellipse_rows(x0, y0, x1, y1, n, lo, hi);

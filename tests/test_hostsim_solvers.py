@@ -85,3 +85,22 @@ def test_lsoda_coefficient_tables(hostsim):
     # Adams-Moulton order 2 (trapezoid): el = [1/2, 1, 1/2]
     assert np.allclose(elco[0, 2, 1:4], [0.5, 1.0, 0.5], rtol=1e-15)
     assert tesco[0, 1, 2] == 2.0 and tesco[1, 1, 2] == 2.0
+
+
+def test_step_selection_root(hostsim):
+    """pw_root_newton (the device's a**(1/k): float seed + two Newton steps) against pow,
+    over the range LSODA's step / order selection feeds it (error ratios, k = 2..13)."""
+    rng = np.random.default_rng(3)
+    a = np.concatenate([10 ** rng.uniform(-29, 29, 20000), 10 ** rng.uniform(-12, 2, 20000),
+                        [1.0, 1e-30, 1e30, 0.0, 1e-200, 3e200]])
+    k = rng.integers(1, 14, a.size).astype(np.int32)
+    out = np.zeros_like(a)
+    hostsim.hs_root_newton.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    hostsim.hs_root_newton(P(a), P(k), a.size, P(out))
+    ref = a ** (1.0 / k)
+    m = ref > 0
+    assert np.array_equal(out[~m], ref[~m])
+    newton = m & (a > 1e-30) & (a < 1e30)          # the range the Newton path serves
+    # (pow(a, 1.0 / k) itself carries |ln a| * eps from the rounded exponent)
+    assert np.max(np.abs(out[newton] / ref[newton] - 1)) < 2e-15
+    assert np.max(np.abs(out[m] / ref[m] - 1)) < 1e-13   # exp(log(a)/k) outside it
