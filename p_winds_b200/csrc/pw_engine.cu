@@ -157,7 +157,7 @@ k_helium(int B, int lanes, const double* __restrict__ T, const double* __restric
          const double* __restrict__ vs, const double* __restrict__ rs, const double* __restrict__ rhos,
          int sstride, const double* __restrict__ r, int nr, const double* __restrict__ v,
          const double* __restrict__ rho, const double* __restrict__ f_h, pwb_he_opts o,
-         const LsodaTables* __restrict__ tab, double* work, double* f1, double* f3, double* scal,
+         const LsodaTables* __restrict__ tab, double* work, size_t wstride, double* f1, double* f3, double* scal,
          double* rates, int* status) {
   const int lane = threadIdx.x;
   if (lane >= lanes) return;
@@ -176,8 +176,9 @@ k_helium(int B, int lanes, const double* __restrict__ T, const double* __restric
   p.relax = o.relax_solution; p.max_n_relax = o.max_n_relax; p.convergence = o.convergence;
   for (int k = 0; k < 6; ++k) p.rates[k] = o.rates[k];
   p.method = o.method; p.rtol = o.rtol; p.atol = o.atol; p.first_step = o.first_step; p.max_step = o.max_step;
-  double* wb = work + (size_t)b * kHeWorkPerRadius * nr;
-  HeWork w{wb, wb + nr, wb + 2 * nr, wb + 3 * nr, wb + 4 * nr, wb + 5 * nr, wb + 10 * nr};
+  double* wb = work + (size_t)b * wstride;
+  HeWork w{wb, wb + nr, wb + 2 * nr, wb + 3 * nr, wb + 4 * nr, wb + 5 * nr, wb + 10 * nr,
+           wstride > (size_t)kHeWorkPerRadius * nr ? wb + kHeWorkPerRadius * nr : nullptr};
   HeOut out{f1 + (size_t)b * nr, f3 + (size_t)b * nr, scal + (size_t)b * 4,
             rates ? rates + (size_t)b * 11 * nr : nullptr, status + b};
   he_population_model<kRk45>(p, *tab, r, v + (size_t)b * nr, rho + (size_t)b * nr, f_h + (size_t)b * nr, nr, w, out);
@@ -685,13 +686,14 @@ static int launch_helium(pwb_ctx* c, cudaStream_t s, int B, int lanes, const dou
                          const pwb_he_opts* o, double* work, double* d_f1, double* d_f3, double* d_scal,
                          double* d_rates, int* d_status) {
   const int blocks = (B + lanes - 1) / lanes;
+  const size_t ws = he_work_doubles(Nr, o->relax_solution, o->max_n_relax, o->method);
   if (o->method == PW_HE_RK45)
     k_helium<true><<<blocks, 32, 0, s>>>(B, lanes, d_T, d_hfrac, d_vs, d_rs, d_rhos, sstride, d_r, Nr, d_v, d_rho,
-                                         d_f_h, *o, c->lsoda_tab.as<LsodaTables>(), work, d_f1, d_f3, d_scal,
+                                         d_f_h, *o, c->lsoda_tab.as<LsodaTables>(), work, ws, d_f1, d_f3, d_scal,
                                          d_rates, d_status);
   else
     k_helium<false><<<blocks, 32, 0, s>>>(B, lanes, d_T, d_hfrac, d_vs, d_rs, d_rhos, sstride, d_r, Nr, d_v, d_rho,
-                                          d_f_h, *o, c->lsoda_tab.as<LsodaTables>(), work, d_f1, d_f3, d_scal,
+                                          d_f_h, *o, c->lsoda_tab.as<LsodaTables>(), work, ws, d_f1, d_f3, d_scal,
                                           d_rates, d_status);
   c->launches++;
   PWB_CUDA(c, cudaGetLastError());
@@ -708,7 +710,8 @@ int pwb_he_population_batch(pwb_ctx* c, int B, const double* d_T, const double* 
   if (B <= 0) return 0;
   if (Nr < 2) return fail(c, "pwb_he_population_batch: radius profile needs >= 2 points");
   if (o->method < 0 || o->method > 2) return fail(c, "pwb_he_population_batch: unsupported method");
-  if (c->he_work.ensure(sizeof(double) * kHeWorkPerRadius * (size_t)Nr * B)) return fail(c, "out of device memory");
+  if (c->he_work.ensure(sizeof(double) * he_work_doubles(Nr, o->relax_solution, o->max_n_relax, o->method) * B))
+    return fail(c, "out of device memory");
   return launch_helium(c, (cudaStream_t)stream, B, he_lanes(c, B), d_T, d_hfrac, d_vs, d_rs, d_rhos, sstride, d_r,
                        Nr, d_v, d_rho, d_f_h, o, c->he_work.as<double>(), d_f1, d_f3, d_scal, d_rates, d_status);
 }
@@ -826,7 +829,7 @@ int pwb_forward_batch(pwb_ctx* c, int B, const double* d_T, const double* d_mdot
   if (c->fw_f.ensure(sizeof(double) * (bn * 5 + B)) || c->fw_scal.ensure(sizeof(double) * (size_t)B * 8) ||
       c->fw_he.ensure(sizeof(double) * (size_t)B * 4) || c->fw_n.ensure(sizeof(double) * bn) ||
       c->fw_v.ensure(sizeof(double) * bn) || c->fw_T.ensure(sizeof(double) * B) ||
-      c->he_work.ensure(sizeof(double) * kHeWorkPerRadius * bn) || c->rt_ncol.ensure(sizeof(double) * bn) ||
+      c->he_work.ensure(sizeof(double) * he_work_doubles(Nr, heopts->relax_solution, heopts->max_n_relax, heopts->method) * B) || c->rt_ncol.ensure(sizeof(double) * bn) ||
       c->rt_sums.ensure(sizeof(double) * (size_t)B * 4) ||
       (nsplit > 1 && c->rt_partial.ensure(sizeof(double) * (size_t)B * nsplit * Nw)) ||
       (rtopts->wind_broadening_method == 1 && c->rt_tau.ensure(sizeof(double) * bn * Nw)))
@@ -872,7 +875,7 @@ int pwb_forward_batch(pwb_ctx* c, int B, const double* d_T, const double* d_mdot
     if (species == 0) {
       if (launch_helium(c, cs, nb, lanes, d_T + o1, d_hfrac + o1, hscal + o1 * 8 + 1, hscal + o1 * 8 + 2,
                         hscal + o1 * 8 + 3, 8, d_r, Nr, v + oN, rho + oN, f_r + oN, heopts,
-                        c->he_work.as<double>() + kHeWorkPerRadius * oN, f1 + oN, f3 + oN, hescal + o1 * 4, nullptr, d_status + o1))
+                        c->he_work.as<double>() + he_work_doubles(Nr, heopts->relax_solution, heopts->max_n_relax, heopts->method) * o1, f1 + oN, f3 + oN, hescal + o1 * 4, nullptr, d_status + o1))
         return -1;
     }
     k_he_density<<<(unsigned)(((size_t)nb * Nr + 255) / 256), 256, 0, cs>>>(

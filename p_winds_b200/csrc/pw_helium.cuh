@@ -184,8 +184,14 @@ struct HeWork {
   double *rn, *tau1, *tau3, *tau1h, *tau3h;
   double* w;      // 5*Nr: [0,Nr) dr*density, [Nr,3Nr) previous profiles, [3Nr,5Nr) RK45 output staging
   double* slope;  // 5*Nr: np.interp slopes (fp[j+1]-fp[j])/(xp[j+1]-xp[j]) of v, rho, fh, tau1, tau3
+  double* hist;   // (max_n_relax+1)*2*Nr or null: the profiles after every pass (he_relax_cycle)
 };
-constexpr int kHeWorkPerRadius = 15;  // doubles of HeWork per radius and model
+constexpr int kHeWorkPerRadius = 15;  // doubles of HeWork per radius and model, without `hist`
+// doubles of scratch per model: the fixed part + the per-pass history of the relax loop
+PW_HD size_t he_work_doubles(int nr, int relax, int max_n_relax, int method) {
+  const bool hist = relax && max_n_relax + 1 > 3 && max_n_relax + 1 <= 32 && method == 0 /*PW_HE_ODEINT*/;
+  return (size_t)nr * (kHeWorkPerRadius + (hist ? 2 * (max_n_relax + 1) : 0));
+}
 
 // slope table of one interpolated profile, exactly as numpy forms each slope
 PW_HD_NOINLINE void he_slopes(const double* xp, const double* fp, int n, double* out) {
@@ -254,6 +260,34 @@ PW_HD bool he_solve(const HeParams& p, HeRhs& rhs, const LsodaTables& tab, int n
   for (int q = k; q < nr; ++q) { f1[q] = 0.0; f3[q] = 0.0; }
   *nfe += s.nfe; *nst += s.nst; *nje += s.nje;
   return ok;
+}
+
+// Exact shortcut of the relax loop (helium.py:723-763).  A pass maps the clamped profiles
+// (f1, f3) of the previous pass to new ones and nothing else carries over, so when the
+// profiles after pass `it` are bit-for-bit those after an earlier pass j the loop has entered
+// a cycle of period P = it - j: every later pass repeats one already made, including its
+// (failed) convergence test, and the reference runs on to max_n_relax.  This happens where
+// odeint gives up in the first interval of a relax pass (all-zero rows -> the same optical
+// depths as the last time) -- the models that would otherwise cost 2-4x any other.  Returns
+// the earlier pass j whose profiles equal those of pass `it`, or -1.
+constexpr int kHeMaxPass = 32;
+PW_HD_NOINLINE int he_relax_cycle(const double* hist, const unsigned long long* hh, int it, int nr) {
+  for (int j = it - 1; j >= 0; --j) {
+    if (hh[j] != hh[it]) continue;
+    const double* a = hist + (size_t)j * 2 * nr;
+    const double* b = hist + (size_t)it * 2 * nr;
+    bool same = true;
+    for (int i = 0; i < 2 * nr && same; ++i) same = (a[i] == b[i]);
+    if (same) return j;
+  }
+  return -1;
+}
+
+PW_HD unsigned long long he_hash_mix(unsigned long long h, double x) {
+  union { double d; unsigned long long u; } c;
+  c.d = x;
+  h ^= c.u + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2);
+  return h;
 }
 
 // `r` radius profile in planetary radii (shared), v / rho / f_h per model.
@@ -328,7 +362,11 @@ PW_HD void he_population_model(const HeParams& p, const LsodaTables& tab, const 
   // pass 0 = the first solve (helium.py:688-718); passes 1..max_n_relax = the relax loop
   // (:723-763).  One call site keeps a single copy of the integrator in the kernel.
   const int n_pass = p.relax ? p.max_n_relax + 1 : 1;
+  const bool track = (w.hist != nullptr) && n_pass > 3 && n_pass <= kHeMaxPass && p.method == PW_HE_ODEINT;
+  unsigned long long hh[kHeMaxPass];
+  int cnt[kHeMaxPass][3];
   for (int it = 0; it < n_pass; ++it) {
+    const int nfe0 = nfe, nst0 = nst, nje0 = nje;
     double s1 = 0.0, s3 = 0.0;
     if (it > 0) {
       ++n_relax;
@@ -359,6 +397,34 @@ PW_HD void he_population_model(const HeParams& p, const LsodaTables& tab, const 
       for (int i = 0; i < nr; ++i) { d1 += f1[i] - p1[i]; d3 += f3[i] - p3[i]; }
       const double rel1 = fabs(d1) / s1, rel3 = fabs(d3) / s3;
       if (rel1 < p.convergence && rel3 < p.convergence) break;
+    }
+    if (track) {
+      double* hrow = w.hist + (size_t)it * 2 * nr;
+      unsigned long long hv = 0;
+      for (int i = 0; i < nr; ++i) {
+        hrow[i] = f1[i]; hrow[nr + i] = f3[i];
+        hv = he_hash_mix(he_hash_mix(hv, f1[i]), f3[i]);
+      }
+      hh[it] = hv;
+      cnt[it][0] = nfe - nfe0; cnt[it][1] = nst - nst0; cnt[it][2] = nje - nje0;
+      const int j = (it >= 1 && it < n_pass - 1) ? he_relax_cycle(w.hist, hh, it, nr) : -1;
+      if (j >= 0) {
+        // the remaining passes m = it+1 .. n_pass-1 repeat passes of the cycle (pass m does the
+        // work of pass j + (m-j) mod P, P = it - j; of pass `it` when that is j itself, since
+        // it starts from the profiles of pass it-1): same work counters, and the loop ends
+        // on the profiles of the pass that n_pass-1 maps to (status already carries the
+        // odeint warning, set in one of the repeated passes)
+        const int P = it - j;
+        for (int m = it + 1; m < n_pass; ++m) {
+          const int rr = (m - j) % P, src = (rr == 0) ? it : j + rr;
+          nfe += cnt[src][0]; nst += cnt[src][1]; nje += cnt[src][2];
+        }
+        const int fin = j + (n_pass - 1 - j) % P;
+        const double* hf = w.hist + (size_t)fin * 2 * nr;
+        for (int i = 0; i < nr; ++i) { f1[i] = hf[i]; f3[i] = hf[nr + i]; }
+        n_relax = p.max_n_relax;
+        break;
+      }
     }
   }
   if (status == PW_FAIL_HE_SOLVER) {

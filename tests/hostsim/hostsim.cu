@@ -67,6 +67,8 @@ int hs_h_ion_fraction(const double* model /*T, mdot, h, mu0*/, const double* opt
 
 extern "C" {
 
+int hs_no_relax_cycle = 0;  // set to 1 by tests to run every relax pass literally
+
 // model: [T, h_fraction, vs, rs, rhos]; opts: [r_pl, y0_0, y0_1, relax, max_n_relax, convergence,
 //   method, rtol, atol, first_step, max_step]; rates[6]
 int hs_he_population(const double* model, const double* opts, const double* rates, const double* r,
@@ -81,9 +83,12 @@ int hs_he_population(const double* model, const double* opts, const double* rate
   p.max_n_relax = (int)opts[4]; p.convergence = opts[5]; p.method = (int)opts[6];
   p.rtol = opts[7]; p.atol = opts[8]; p.first_step = opts[9]; p.max_step = opts[10];
   for (int i = 0; i < 6; ++i) p.rates[i] = rates[i];
-  std::vector<double> buf(kHeWorkPerRadius * nr);
+  // opts[11] (optional, default on): 0 disables the relax-cycle shortcut (no pass history)
+  const size_t ws = he_work_doubles(nr, p.relax, p.max_n_relax, p.method);
+  std::vector<double> buf(ws);
   double* b = buf.data();
-  HeWork w{b, b + nr, b + 2 * nr, b + 3 * nr, b + 4 * nr, b + 5 * nr, b + 10 * nr};
+  HeWork w{b, b + nr, b + 2 * nr, b + 3 * nr, b + 4 * nr, b + 5 * nr, b + 10 * nr,
+           (ws > (size_t)kHeWorkPerRadius * nr && !hs_no_relax_cycle) ? b + kHeWorkPerRadius * nr : nullptr};
   int status = 0;
   HeOut o{f1, f3, scal, rates_out, &status};
   if (p.method == PW_HE_RK45) he_population_model<true>(p, tab, r, v, rho, f_h, nr, w, o);

@@ -213,3 +213,26 @@ def test_pil_ellipse_spans_against_pillow(hostsim, oracle):
         ImageDraw.Draw(im).ellipse([(cx - rad, cy - rad), (cx + rad, cy + rad)], outline=1, fill=1)
         assert np.array_equal(mask, np.array(im).astype(float)), (cx, cy, rad, n)
         assert np.array_equal(mask, oracle._disk((cx, cy), rad, n))
+
+
+@pytest.mark.parametrize('T0,md', [(10428.571428571428, 10 ** 11.365079365079366),      # period-3 cycle
+                                   (12714.285714285714, 10 ** 11.642857142857142),      # period-4 cycle
+                                   (10619.047619047618, 10 ** 11.365079365079366),      # fails once, then converges
+                                   (11500., 1e11)])                                      # ordinary model
+def test_helium_relax_cycle_shortcut_is_exact(hostsim, oracle, sed, T0, md):
+    """he_relax_cycle: where odeint gives up inside the relax loop the loop repeats itself
+    bit for bit; cutting the repetition short must change nothing -- profiles, status,
+    n_relax and the work counters are those of running all max_n_relax passes."""
+    rates = np.array(oracle.he_radiative_processes(sed))
+    f_r, vs, rs, rhos, v, rho = _he_inputs(oracle, sed, T0, md, False)
+    flag = C.c_int.in_dll(hostsim, 'hs_no_relax_cycle')
+    try:
+        flag.value = 1
+        st0, a1, a3, sc0 = _he_host(hostsim, rates, T0, 0.9, vs, rs, rhos, R, v, rho, f_r)
+        flag.value = 0
+        st1, b1, b3, sc1 = _he_host(hostsim, rates, T0, 0.9, vs, rs, rhos, R, v, rho, f_r)
+    finally:
+        flag.value = 0
+    assert st0 == st1
+    assert np.array_equal(a1, b1) and np.array_equal(a3, b3)
+    assert np.array_equal(sc0, sc1)
