@@ -151,8 +151,11 @@ k_hydrogen(int B, const double* __restrict__ T, const double* __restrict__ mdot,
 
 // One thread per model; `lanes` models share a warp (latency-bound regime: fewer lanes
 // per warp spread the independent serial solves over more warp schedulers).
+#ifndef PW_HE_MINBLOCKS
+#define PW_HE_MINBLOCKS 1   // CTAs (= warps) per SM the register allocation has to leave room for
+#endif
 template <bool kRk45>
-__global__ void __launch_bounds__(32, 1)
+__global__ void __launch_bounds__(32, PW_HE_MINBLOCKS)
 k_helium(int B, int lanes, const double* __restrict__ T, const double* __restrict__ hfrac,
          const double* __restrict__ vs, const double* __restrict__ rs, const double* __restrict__ rhos,
          int sstride, const double* __restrict__ r, int nr, const double* __restrict__ v,

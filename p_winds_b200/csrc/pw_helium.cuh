@@ -143,8 +143,8 @@ struct HeRhs {
     const double term_31 = (1 - f_1 - f_3) * c[1];
     const double term_33 = f_3 * phi3 * e3;
     if (dydx) {
-      dydx[0] = (term_11 + term_12 - term_13 - term_14 + term_15 + term_16 + term_17 - term_18 + term_19) / vv;
-      dydx[1] = (term_31 - term_12 - term_33 + term_14 - term_15 - term_16 - term_17) / vv;
+      dydx[0] = PW_DIV(term_11 + term_12 - term_13 - term_14 + term_15 + term_16 + term_17 - term_18 + term_19, vv);
+      dydx[1] = PW_DIV(term_31 - term_12 - term_33 + term_14 - term_15 - term_16 - term_17, vv);
     }
     if (terms) {
       terms[0] = term_13; terms[1] = term_33; terms[2] = term_11; terms[3] = term_31;

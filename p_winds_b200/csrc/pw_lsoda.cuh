@@ -182,7 +182,7 @@ struct Lsoda {
     for (int i = 0; i < N; ++i) {
       const double e = o.rtol * fabs(yc[i]) + o.atol;
       if (!(e > 0.0)) ok = false;
-      ewt[i] = 1.0 / e;
+      ewt[i] = PW_DIV(1.0, e);
     }
     return ok;
   }
@@ -231,18 +231,18 @@ struct Lsoda {
     tq1 = tq[1]; tq2 = tq[2]; tq3 = tq[3];
     rtq2 = tab.rtesco2[meth_tab - 1][nq];
     const double el1 = elp[1];
-    rc = rc * el1 / el0;
+    rc = PW_DIV(rc * el1, el0);
     el0 = el1;
-    conit = 0.5 / (double)(nq + 2);
+    conit = PW_DIV(0.5, (double)(nq + 2));
   }
   PW_HD void scaleh(double* rh, double* pdh) {  // stoda labels 175-180
     *rh = fmin(*rh, rmax);
-    *rh = *rh / fmax(1., fabs(h) * hmxi * (*rh));
+    *rh = PW_DIV(*rh, fmax(1., fabs(h) * hmxi * (*rh)));
     if (meth == 1) {
       irflag = 0;
       *pdh = fmax(fabs(h) * pdlast, 0.000001);
       if ((*rh * *pdh * 1.00001) >= sm1(nq)) {
-        *rh = sm1(nq) / *pdh;
+        *rh = PW_DIV(sm1(nq), *pdh);
         irflag = 1;
       }
     }
@@ -311,11 +311,11 @@ struct Lsoda {
         yj = (i == j) ? y[i] : yj;
         ej = (i == j) ? ewt[i] : ej;
       }
-      const double r = fmax(srur * fabs(yj), r0 / ej);
+      const double r = fmax(srur * fabs(yj), PW_DIV(r0, ej));
       double yp[N], ftem[N];
 #pragma unroll
       for (int i = 0; i < N; ++i) yp[i] = (i == j) ? yj + r : y[i];
-      fac = -hl0 / r;
+      fac = PW_DIV(-hl0, r);
       f.eval(yp, ftem);
 #pragma unroll
       for (int i = 0; i < N; ++i) {
@@ -331,10 +331,10 @@ struct Lsoda {
     for (int i = 0; i < N; ++i) {
       double sum = 0.;
 #pragma unroll
-      for (int j = 0; j < N; ++j) sum += fabs(wm[i][j]) / ewt[j];
+      for (int j = 0; j < N; ++j) sum += PW_DIV(fabs(wm[i][j]), ewt[j]);
       an = fmax(an, sum * ewt[i]);
     }
-    pdnorm = an / fabs(hl0);
+    pdnorm = PW_DIV(an, fabs(hl0));
 #pragma unroll
     for (int i = 0; i < N; ++i) wm[i][i] += 1.;
     // dgefa: Gaussian elimination with partial pivoting, multipliers stored negated.
@@ -356,7 +356,7 @@ struct Lsoda {
       for (int i = k + 1; i < N; ++i)
         if (i == lp) wm[i][k] = wm[k][k];
       wm[k][k] = piv;
-      const double t = -1. / piv;
+      const double t = PW_DIV(-1., piv);
 #pragma unroll
       for (int i = k + 1; i < N; ++i) wm[i][k] *= t;
 #pragma unroll
@@ -390,7 +390,7 @@ struct Lsoda {
 #pragma unroll
     for (int kb = 0; kb < N; ++kb) {
       const int k = N - 1 - kb;
-      b[k] /= wm[k][k];
+      b[k] = PW_DIV(b[k], wm[k][k]);
       const double t = -b[k];
 #pragma unroll
       for (int i = 0; i < k; ++i) b[i] += t * wm[i][k];
@@ -449,15 +449,15 @@ struct Lsoda {
       if (m != 0 || meth != 1) {
         if (m != 0) {
           double rm = 1024.;
-          if (del <= (1024. * delp)) rm = del / delp;
+          if (del <= (1024. * delp)) rm = PW_DIV(del, delp);
           rate = (rm > rate) ? rm : rate;
           const double c2 = 0.2 * crate;
           crate = (rm > c2) ? rm : c2;
         }
         const double c15 = 1.5 * crate;
-        const double dcon = del * ((c15 < 1.) ? c15 : 1.) / (tq2 * conit);
+        const double dcon = PW_DIV(del * ((c15 < 1.) ? c15 : 1.), tq2 * conit);
         if (dcon <= 1.) {
-          const double pd = rate / fabs(h * el0);
+          const double pd = PW_DIV(rate, fabs(h * el0));
           pdest = (pd > pdest) ? pd : pdest;
           if (pdest != 0.) pdlast = pdest;
           break;
@@ -490,14 +490,14 @@ struct Lsoda {
         rh2 = 2.;
         nqm2 = nq < mxords ? nq : mxords;
       } else {
-        double rh1 = 1. / (1.2 * pw_root(dsm, l) + 0.0000012);
+        double rh1 = PW_DIV(1., 1.2 * pw_root(dsm, l) + 0.0000012);
         double rh1it = 2. * rh1;
         *pdh = pdlast * fabs(h);
-        if ((*pdh * rh1) > 0.00001) rh1it = sm1(nq) / *pdh;
+        if ((*pdh * rh1) > 0.00001) rh1it = PW_DIV(sm1(nq), *pdh);
         rh1 = fmin(rh1, rh1it);
         // (ODEPACK's branch for nq > mxords cannot be taken: nq <= 5 = mxords here)
-        const double dm2 = dsm * (tab.cm1[nq] / tab.cm2[nq]);
-        rh2 = 1. / (1.2 * pw_root(dm2, l) + 0.0000012);
+        const double dm2 = dsm * PW_DIV(tab.cm1[nq], tab.cm2[nq]);
+        rh2 = PW_DIV(1., 1.2 * pw_root(dm2, l) + 0.0000012);
         nqm2 = nq;
         if (rh2 < ratio * rh1) return;
       }
@@ -519,14 +519,14 @@ struct Lsoda {
     *pdh = pdnorm * fabs(h);
     if (ratio == 5. && *pdh >= 1.) return;
     // (ODEPACK's branch for mxordn < nq cannot be taken: nq <= 5 < 12 = mxordn here)
-    double dm1 = dsm * (tab.cm2[nq] / tab.cm1[nq]);
-    double rh1 = 1. / (1.2 * pw_root(dm1, l) + 0.0000012);
+    double dm1 = dsm * PW_DIV(tab.cm2[nq], tab.cm1[nq]);
+    double rh1 = PW_DIV(1., 1.2 * pw_root(dm1, l) + 0.0000012);
     const int nqm1 = nq, lm1 = l;
     double rh1it = 2. * rh1;
     *pdh = pdnorm * fabs(h);
-    if ((*pdh * rh1) > 0.00001) rh1it = sm1(nqm1) / *pdh;
+    if ((*pdh * rh1) > 0.00001) rh1it = PW_DIV(sm1(nqm1), *pdh);
     rh1 = fmin(rh1, rh1it);
-    const double rh2 = 1. / (1.2 * pw_root(dsm, l) + 0.0000012);
+    const double rh2 = PW_DIV(1., 1.2 * pw_root(dsm, l) + 0.0000012);
     if ((rh1 * ratio) < (5. * rh2)) return;
     const double alpha = fmax(0.001, rh1);
     dm1 *= pw_root(alpha, lm1);
@@ -543,19 +543,19 @@ struct Lsoda {
   // labels 540-630.  orderflag: 0 no change, 1 h changes, 2 h and nq change
   PW_HD void orderswitch(double rhup, double dsm, double* pdh, double* rh, int* orderflag) {
     *orderflag = 0;
-    double rhsm = 1. / (1.2 * pw_root(dsm, l) + 0.0000012);
+    double rhsm = PW_DIV(1., 1.2 * pw_root(dsm, l) + 0.0000012);
     double rhdn = 0.;
     if (nq != 1) {
       double top[N];
       row_get(l, top);
-      const double ddn = vmnorm(top) / tq1;
-      rhdn = 1. / (1.3 * pw_root(ddn, nq) + 0.0000013);
+      const double ddn = PW_DIV(vmnorm(top), tq1);
+      rhdn = PW_DIV(1., 1.3 * pw_root(ddn, nq) + 0.0000013);
     }
     if (meth == 1) {
       *pdh = fmax(fabs(h) * pdlast, 0.000001);
-      if (l < lmax) rhup = fmin(rhup, sm1(l) / *pdh);
-      rhsm = fmin(rhsm, sm1(nq) / *pdh);
-      if (nq > 1) rhdn = fmin(rhdn, sm1(nq - 1) / *pdh);
+      if (l < lmax) rhup = fmin(rhup, PW_DIV(sm1(l), *pdh));
+      rhsm = fmin(rhsm, PW_DIV(sm1(nq), *pdh));
+      if (nq > 1) rhdn = fmin(rhdn, PW_DIV(sm1(nq - 1), *pdh));
       pdest = 0.;
     }
     int newq;
@@ -576,7 +576,7 @@ struct Lsoda {
       } else {
         *rh = rhup;
         if (*rh >= 1.1) {
-          const double r = elp[l] / (double)l;
+          const double r = PW_DIV(elp[l], (double)l);
           nq = l;
           l = nq + 1;
           double top[N];
@@ -642,7 +642,7 @@ struct Lsoda {
         reload = true;
       }
       if (h != hold) {
-        rh = h / hold;
+        rh = PW_DIV(h, hold);
         h = hold;
         rescale = true;
       }
@@ -671,7 +671,7 @@ struct Lsoda {
       bool efail = false;
       if (!cfail) {
         jcur = 0;
-        dsm = ((m == 0) ? del : vmnorm(acor)) / tq2;
+        dsm = PW_DIV((m == 0) ? del : vmnorm(acor), tq2);
         efail = !(dsm <= 1.);
       }
       if (cfail || efail) {  // labels 430 / 500 start the same way
@@ -737,8 +737,8 @@ struct Lsoda {
           row_get(lmax, top);
 #pragma unroll
           for (int i = 0; i < N; ++i) savf[i] = acor[i] - top[i];
-          const double dup = vmnorm(savf) / tq3;
-          rhup = 1. / (1.4 * pw_root(dup, l + 1) + 0.0000014);
+          const double dup = PW_DIV(vmnorm(savf), tq3);
+          rhup = PW_DIV(1., 1.4 * pw_root(dup, l + 1) + 0.0000014);
         }
       } else {
         // error test failed (label 500)
@@ -796,7 +796,7 @@ struct Lsoda {
   PW_HD int intdy(double t, double* dky) const {
     const double tp = tn - hu - 100. * kEps * copysign(fabs(tn) + fabs(hu), hu);
     if ((t - tp) * (t - tn) > 0.) return -2;
-    const double s = (t - tn) / h;
+    const double s = PW_DIV(t - tn, h);
 #pragma unroll
     for (int i = 0; i < N; ++i) dky[i] = 0.;
     if (PW_UNLIKELY(nq > kF)) {
