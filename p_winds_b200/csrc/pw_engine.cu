@@ -72,7 +72,7 @@ struct pwb_ctx {
   cudaStream_t streams[kMaxChunks] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev_start = nullptr, ev_done[kMaxChunks] = {nullptr, nullptr, nullptr, nullptr};
   // scratch
-  DevBuf he_work, rt_ncol, rt_sums, rt_partial, rt_tau, fw_f, fw_scal, fw_he, fw_n, fw_v, fw_T, misc;
+  DevBuf he_order, he_work, rt_ncol, rt_sums, rt_partial, rt_tau, fw_f, fw_scal, fw_he, fw_n, fw_v, fw_T, misc;
 };
 
 static int fail(pwb_ctx* c, const char* fmt, const char* a = "") {
@@ -149,23 +149,92 @@ k_hydrogen(int B, const double* __restrict__ T, const double* __restrict__ mdot,
   h_ion_fraction_model(p, t, r, nr, w, out);
 }
 
-// One thread per model; `lanes` models share a warp (latency-bound regime: fewer lanes
-// per warp spread the independent serial solves over more warp schedulers).
+// Cost-ordered schedule of the helium stage.  A model's cost (LSODA steps x relax passes)
+// grows ~5x with the column density of the wind, and the kernel is a batch of independent
+// serial solves: what matters is when the *last* one ends.  k_he_order sorts the models by a
+// cost proxy (rho_s * r_s, descending; bucket sort in one CTA, order inside a bucket is
+// irrelevant).  The launch then walks the sorted list in up to four segments with a
+// growing number of models per warp: the expensive head runs one model per warp (no
+// divergence, scheduled first), the cheap tail is packed (its warps take as long as the
+// head's even though the lanes of a warp serialise where their paths differ).  Placement
+// never changes a model's result: models share nothing.
+struct HeSched {
+  int nseg;
+  int slot0[5];  // first sorted slot of segment s (slot0[nseg] = B)
+  int warp0[5];  // first warp (CTA) of segment s (warp0[nseg] = number of CTAs)
+  int lanes[4];  // models per warp in segment s
+};
+
+constexpr int kHeBuckets = 4096;
+__global__ void __launch_bounds__(1024, 1)
+k_he_order(int B, const double* __restrict__ rs, const double* __restrict__ rhos, int sstride,
+           const int* __restrict__ status, int* __restrict__ order) {
+  __shared__ int hist[kHeBuckets];
+  __shared__ unsigned long long s_lo, s_hi;
+  const int t = threadIdx.x;
+  auto key_bits = [&](int b) -> unsigned long long {
+    if (status[b] != PW_OK) return 0ull;  // nothing to integrate: last
+    const double k = rhos[(size_t)b * sstride] * rs[(size_t)b * sstride];
+    return (k > 0.0) ? (unsigned long long)__double_as_longlong(k) : 1ull;  // positive doubles order like their bits
+  };
+  if (t == 0) { s_lo = ~0ull; s_hi = 0ull; }
+  for (int i = t; i < kHeBuckets; i += blockDim.x) hist[i] = 0;
+  __syncthreads();
+  unsigned long long lo = ~0ull, hi = 0ull;
+  for (int b = t; b < B; b += blockDim.x) {
+    const unsigned long long k = key_bits(b);
+    lo = k < lo ? k : lo;
+    hi = k > hi ? k : hi;
+  }
+  atomicMin(&s_lo, lo);
+  atomicMax(&s_hi, hi);
+  __syncthreads();
+  lo = s_lo; hi = s_hi;
+  const double scale = (hi > lo) ? (double)(kHeBuckets - 1) / (double)(hi - lo) : 0.0;
+  auto bucket = [&](int b) { return (kHeBuckets - 1) - (int)((double)(key_bits(b) - lo) * scale); };  // 0 = costliest
+  for (int b = t; b < B; b += blockDim.x) atomicAdd(&hist[bucket(b)], 1);
+  __syncthreads();
+  // exclusive scan of the histogram (4 buckets per thread + block scan through shared memory)
+  {
+    const int per = kHeBuckets / 1024;
+    int loc[per], sum = 0;
+    for (int q = 0; q < per; ++q) { loc[q] = hist[t * per + q]; sum += loc[q]; }
+    __shared__ int part[1024];
+    part[t] = sum;
+    __syncthreads();
+    for (int off = 1; off < 1024; off <<= 1) {
+      const int v = (t >= off) ? part[t - off] : 0;
+      __syncthreads();
+      part[t] += v;
+      __syncthreads();
+    }
+    int run = part[t] - sum;
+    for (int q = 0; q < per; ++q) { hist[t * per + q] = run; run += loc[q]; }
+  }
+  __syncthreads();
+  for (int b = t; b < B; b += blockDim.x) order[atomicAdd(&hist[bucket(b)], 1)] = b;
+}
+
 #ifndef PW_HE_MINBLOCKS
 #define PW_HE_MINBLOCKS 1   // CTAs (= warps) per SM the register allocation has to leave room for
 #endif
 template <bool kRk45>
 __global__ void __launch_bounds__(32, PW_HE_MINBLOCKS)
-k_helium(int B, int lanes, const double* __restrict__ T, const double* __restrict__ hfrac,
+k_helium(int B, HeSched sched, const int* __restrict__ order, const double* __restrict__ T, const double* __restrict__ hfrac,
          const double* __restrict__ vs, const double* __restrict__ rs, const double* __restrict__ rhos,
          int sstride, const double* __restrict__ r, int nr, const double* __restrict__ v,
          const double* __restrict__ rho, const double* __restrict__ f_h, pwb_he_opts o,
          const LsodaTables* __restrict__ tab, double* work, size_t wstride, double* f1, double* f3, double* scal,
          double* rates, int* status) {
-  const int lane = threadIdx.x;
-  if (lane >= lanes) return;
-  const int b = blockIdx.x * lanes + lane;
-  if (b >= B) return;
+  const int lane = threadIdx.x, warp = blockIdx.x;
+  int seg = 0;
+#pragma unroll
+  for (int q = 1; q < 4; ++q)
+    if (q < sched.nseg && warp >= sched.warp0[q]) seg = q;
+  if (lane >= sched.lanes[seg]) return;
+  const int slot = sched.slot0[seg] + (warp - sched.warp0[seg]) * sched.lanes[seg] + lane;
+  if (slot >= sched.slot0[seg + 1]) return;
+  const int b = order ? order[slot] : slot;
   if (status[b] != PW_OK) {  // upstream failure: propagate NaNs
     const double nan_ = nan("");
     for (int i = 0; i < nr; ++i) { f1[(size_t)b * nr + i] = nan_; f3[(size_t)b * nr + i] = nan_; }
@@ -587,7 +656,7 @@ void pwb_destroy(pwb_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   DevBuf* bufs[] = {&c->sed_gw, &c->sed_sh, &c->sed_she, &c->sed_scal, &c->lsoda_tab, &c->px_lo, &c->px_whi,
-                    &c->px_wlo, &c->px_i0, &c->px_meta, &c->geo_r, &c->he_work, &c->rt_ncol, &c->rt_sums,
+                    &c->px_wlo, &c->px_i0, &c->px_meta, &c->geo_r, &c->he_order, &c->he_work, &c->rt_ncol, &c->rt_sums,
                     &c->rt_partial, &c->rt_tau, &c->fw_f, &c->fw_scal, &c->fw_he, &c->fw_n, &c->fw_v, &c->fw_T, &c->misc};
   for (DevBuf* b : bufs) b->release();
   for (int i = 0; i < pwb_ctx::kMaxChunks; ++i) {
@@ -669,33 +738,77 @@ int pwb_h_ion_fraction_batch(pwb_ctx* c, int B, const double* d_T, const double*
   return 0;
 }
 
-static int he_lanes(pwb_ctx* c, int B) {
-  // Models per warp.  The solve is a long dependent chain (latency bound), so small
-  // batches are spread one warp per scheduler (4 per SM) before models are packed into
-  // the lanes of a warp; measured on B200 for 4096 models: 6-12 lanes 136-139 ms,
-  // 1 lane 167 ms (issue/I-cache contention), 32 lanes 180 ms (divergence).
-  const long long target_warps = (long long)c->sm_count * 4;
-  long long lanes = (B + target_warps - 1) / target_warps;
-  if (lanes < 1) lanes = 1;
-  if (lanes > 32) lanes = 32;
-  const char* e = getenv("PWB_HE_LANES");
-  if (e) { int v = atoi(e); if (v >= 1 && v <= 32) lanes = v; }
-  return (int)lanes;
+// Models per warp along the cost-sorted list (see HeSched).  `frac[s]` of the models, from the
+// costliest down, run `lanes[s]` to a warp.  The default pattern -- 1 % alone, 9 % in pairs,
+// 40 % in threes, the cheap half eight to a warp -- equalises the predicted warp times of the
+// 64 x 64 retrieval grid on one B200 (measured); all lane counts are scaled up together when the
+// batch would otherwise need more warps than the GPU keeps resident (8 per SM at 255 registers).
+// PWB_HE_SCHED="f:L,f:L,..." overrides the pattern, PWB_HE_LANES=L forces one lane count and the
+// caller's order.
+static HeSched he_schedule(pwb_ctx* c, int B, bool* sorted) {
+  double frac[4] = {0.01, 0.09, 0.40, 0.50};
+  int lanes[4] = {1, 2, 3, 8};
+  int nseg = 4;
+  *sorted = true;
+  if (const char* e = getenv("PWB_HE_SCHED")) {
+    int n = 0;
+    const char* q = e;
+    while (*q && n < 4) {
+      double f = 0; int l = 0; int used = 0;
+      if (sscanf(q, "%lf:%d%n", &f, &l, &used) != 2 || l < 1 || l > 32) break;
+      frac[n] = f; lanes[n] = l; ++n;
+      q += used;
+      if (*q == ',') ++q;
+    }
+    if (n > 0) nseg = n;
+  }
+  if (const char* e = getenv("PWB_HE_LANES")) {
+    const int v = atoi(e);
+    if (v >= 1 && v <= 32) { nseg = 1; frac[0] = 1.0; lanes[0] = v; *sorted = false; }
+  } else if (!getenv("PWB_HE_SCHED")) {
+    const double capacity = 8.0 * c->sm_count;
+    double warps = 0;
+    for (int s = 0; s < nseg; ++s) warps += frac[s] * B / lanes[s];
+    if (warps > capacity) {
+      const double scale = warps / capacity;
+      for (int s = 0; s < nseg; ++s) lanes[s] = std::min(32, (int)std::ceil(lanes[s] * scale));
+    }
+  }
+  HeSched h;
+  h.nseg = nseg;
+  int slot = 0, warp = 0;
+  for (int s = 0; s < nseg; ++s) {
+    int n = (s == nseg - 1) ? B - slot : std::min(B - slot, (int)std::llround(frac[s] * B));
+    if (n < 0) n = 0;
+    h.slot0[s] = slot; h.warp0[s] = warp; h.lanes[s] = lanes[s];
+    slot += n;
+    warp += (n + lanes[s] - 1) / lanes[s];
+  }
+  for (int s = nseg; s <= 4; ++s) { h.slot0[s] = slot; h.warp0[s] = warp; }
+  for (int s = nseg; s < 4; ++s) h.lanes[s] = 1;
+  return h;
 }
 
-static int launch_helium(pwb_ctx* c, cudaStream_t s, int B, int lanes, const double* d_T, const double* d_hfrac,
+static int launch_helium(pwb_ctx* c, cudaStream_t s, int B, const double* d_T, const double* d_hfrac,
                          const double* d_vs, const double* d_rs, const double* d_rhos, int sstride,
                          const double* d_r, int Nr, const double* d_v, const double* d_rho, const double* d_f_h,
-                         const pwb_he_opts* o, double* work, double* d_f1, double* d_f3, double* d_scal,
+                         const pwb_he_opts* o, double* work, int* order, double* d_f1, double* d_f3, double* d_scal,
                          double* d_rates, int* d_status) {
-  const int blocks = (B + lanes - 1) / lanes;
+  bool sorted = true;
+  const HeSched sched = he_schedule(c, B, &sorted);
+  if (sorted) {
+    k_he_order<<<1, 1024, 0, s>>>(B, d_rs, d_rhos, sstride, d_status, order);
+    c->launches++;
+  }
+  const int* ord = sorted ? order : nullptr;
+  const int blocks = sched.warp0[sched.nseg];
   const size_t ws = he_work_doubles(Nr, o->relax_solution, o->max_n_relax, o->method);
   if (o->method == PW_HE_RK45)
-    k_helium<true><<<blocks, 32, 0, s>>>(B, lanes, d_T, d_hfrac, d_vs, d_rs, d_rhos, sstride, d_r, Nr, d_v, d_rho,
+    k_helium<true><<<blocks, 32, 0, s>>>(B, sched, ord, d_T, d_hfrac, d_vs, d_rs, d_rhos, sstride, d_r, Nr, d_v, d_rho,
                                          d_f_h, *o, c->lsoda_tab.as<LsodaTables>(), work, ws, d_f1, d_f3, d_scal,
                                          d_rates, d_status);
   else
-    k_helium<false><<<blocks, 32, 0, s>>>(B, lanes, d_T, d_hfrac, d_vs, d_rs, d_rhos, sstride, d_r, Nr, d_v, d_rho,
+    k_helium<false><<<blocks, 32, 0, s>>>(B, sched, ord, d_T, d_hfrac, d_vs, d_rs, d_rhos, sstride, d_r, Nr, d_v, d_rho,
                                           d_f_h, *o, c->lsoda_tab.as<LsodaTables>(), work, ws, d_f1, d_f3, d_scal,
                                           d_rates, d_status);
   c->launches++;
@@ -713,10 +826,12 @@ int pwb_he_population_batch(pwb_ctx* c, int B, const double* d_T, const double* 
   if (B <= 0) return 0;
   if (Nr < 2) return fail(c, "pwb_he_population_batch: radius profile needs >= 2 points");
   if (o->method < 0 || o->method > 2) return fail(c, "pwb_he_population_batch: unsupported method");
-  if (c->he_work.ensure(sizeof(double) * he_work_doubles(Nr, o->relax_solution, o->max_n_relax, o->method) * B))
+  if (c->he_work.ensure(sizeof(double) * he_work_doubles(Nr, o->relax_solution, o->max_n_relax, o->method) * B) ||
+      c->he_order.ensure(sizeof(int) * (size_t)B))
     return fail(c, "out of device memory");
-  return launch_helium(c, (cudaStream_t)stream, B, he_lanes(c, B), d_T, d_hfrac, d_vs, d_rs, d_rhos, sstride, d_r,
-                       Nr, d_v, d_rho, d_f_h, o, c->he_work.as<double>(), d_f1, d_f3, d_scal, d_rates, d_status);
+  return launch_helium(c, (cudaStream_t)stream, B, d_T, d_hfrac, d_vs, d_rs, d_rhos, sstride, d_r, Nr, d_v, d_rho,
+                       d_f_h, o, c->he_work.as<double>(), c->he_order.as<int>(), d_f1, d_f3, d_scal, d_rates,
+                       d_status);
 }
 
 int pwb_set_geometry(pwb_ctx* c, const double* d_i0, const double* d_r_map, int npix,
@@ -832,7 +947,8 @@ int pwb_forward_batch(pwb_ctx* c, int B, const double* d_T, const double* d_mdot
   if (c->fw_f.ensure(sizeof(double) * (bn * 5 + B)) || c->fw_scal.ensure(sizeof(double) * (size_t)B * 8) ||
       c->fw_he.ensure(sizeof(double) * (size_t)B * 4) || c->fw_n.ensure(sizeof(double) * bn) ||
       c->fw_v.ensure(sizeof(double) * bn) || c->fw_T.ensure(sizeof(double) * B) ||
-      c->he_work.ensure(sizeof(double) * he_work_doubles(Nr, heopts->relax_solution, heopts->max_n_relax, heopts->method) * B) || c->rt_ncol.ensure(sizeof(double) * bn) ||
+      c->he_work.ensure(sizeof(double) * he_work_doubles(Nr, heopts->relax_solution, heopts->max_n_relax, heopts->method) * B) ||
+      c->he_order.ensure(sizeof(int) * (size_t)B) || c->rt_ncol.ensure(sizeof(double) * bn) ||
       c->rt_sums.ensure(sizeof(double) * (size_t)B * 4) ||
       (nsplit > 1 && c->rt_partial.ensure(sizeof(double) * (size_t)B * nsplit * Nw)) ||
       (rtopts->wind_broadening_method == 1 && c->rt_tau.ensure(sizeof(double) * bn * Nw)))
@@ -859,7 +975,6 @@ int pwb_forward_batch(pwb_ctx* c, int B, const double* d_T, const double* d_mdot
   nchunk = 1;  // measured on B200 (64x64 grid): 1 chunk 175 ms, 2 chunks 197 ms, 4 chunks 191 ms -- the H stage of
                // the next chunk steals issue slots from the latency-critical helium warps; kept as a knob
   { const char* e = getenv("PWB_CHUNKS"); if (e) { int q = atoi(e); if (q >= 1 && q <= pwb_ctx::kMaxChunks) nchunk = q; } }
-  const int lanes = he_lanes(c, B);
   const int per = (B + nchunk - 1) / nchunk;
   PWB_CUDA(c, cudaEventRecord(c->ev_start, s));
   for (int q = 0; q < nchunk; ++q) {
@@ -876,9 +991,11 @@ int pwb_forward_batch(pwb_ctx* c, int B, const double* d_T, const double* d_mdot
     c->launches++;
     PWB_CUDA(c, cudaGetLastError());
     if (species == 0) {
-      if (launch_helium(c, cs, nb, lanes, d_T + o1, d_hfrac + o1, hscal + o1 * 8 + 1, hscal + o1 * 8 + 2,
+      if (launch_helium(c, cs, nb, d_T + o1, d_hfrac + o1, hscal + o1 * 8 + 1, hscal + o1 * 8 + 2,
                         hscal + o1 * 8 + 3, 8, d_r, Nr, v + oN, rho + oN, f_r + oN, heopts,
-                        c->he_work.as<double>() + he_work_doubles(Nr, heopts->relax_solution, heopts->max_n_relax, heopts->method) * o1, f1 + oN, f3 + oN, hescal + o1 * 4, nullptr, d_status + o1))
+                        c->he_work.as<double>() +
+                            he_work_doubles(Nr, heopts->relax_solution, heopts->max_n_relax, heopts->method) * o1,
+                        c->he_order.as<int>() + o1, f1 + oN, f3 + oN, hescal + o1 * 4, nullptr, d_status + o1))
         return -1;
     }
     k_he_density<<<(unsigned)(((size_t)nb * Nr + 255) / 256), 256, 0, cs>>>(

@@ -17,6 +17,8 @@ w = lines.he_3_properties()
 rto = Engine.rt_opts(w[:3], w[3:6], [w[6]] * 3, 4 * 1.67262192369e-27)
 T0 = np.linspace(10000, 13000, N); Md = np.logspace(9.5, 12, N)
 TT, MM = np.meshgrid(T0, Md, indexing='ij'); T = TT.ravel(); md = MM.ravel(); hf = np.full(T.size, 0.9)
+if os.environ.get('SORTED'):
+    o = np.argsort(-md * np.sqrt(T), kind='stable'); T = T[o]; md = md[o]
 Td, mdd, hfd = eng.dev(T), eng.dev(md), eng.dev(hf)
 ho = Engine.h_opts(1.39, 0.73, relax_solution=True, exact_phi=True)
 heo = Engine.he_opts(1.39, rates, (1.0, 0.0), True)
