@@ -739,15 +739,16 @@ int pwb_h_ion_fraction_batch(pwb_ctx* c, int B, const double* d_T, const double*
 }
 
 // Models per warp along the cost-sorted list (see HeSched).  `frac[s]` of the models, from the
-// costliest down, run `lanes[s]` to a warp.  The default pattern -- 1 % alone, 9 % in pairs,
-// 40 % in threes, the cheap half eight to a warp -- equalises the predicted warp times of the
-// 64 x 64 retrieval grid on one B200 (measured); all lane counts are scaled up together when the
+// costliest down, run `lanes[s]` to a warp.  The default pattern -- 5 % alone, 25 % in pairs,
+// 40 % in fours, the cheapest 30 % eight to a warp -- is the measured optimum for the 64 x 64
+// retrieval grid on one B200 (scripts/sweep_sched.py: 62.6 ms, flat within 3 % around it; one
+// lane count for all: 75-90 ms); all lane counts are scaled up together when the
 // batch would otherwise need more warps than the GPU keeps resident (8 per SM at 255 registers).
 // PWB_HE_SCHED="f:L,f:L,..." overrides the pattern, PWB_HE_LANES=L forces one lane count and the
 // caller's order.
 static HeSched he_schedule(pwb_ctx* c, int B, bool* sorted) {
-  double frac[4] = {0.01, 0.09, 0.40, 0.50};
-  int lanes[4] = {1, 2, 3, 8};
+  double frac[4] = {0.05, 0.25, 0.40, 0.30};
+  int lanes[4] = {1, 2, 4, 8};
   int nseg = 4;
   *sorted = true;
   if (const char* e = getenv("PWB_HE_SCHED")) {
