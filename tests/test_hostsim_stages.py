@@ -236,3 +236,18 @@ def test_helium_relax_cycle_shortcut_is_exact(hostsim, oracle, sed, T0, md):
     assert st0 == st1
     assert np.array_equal(a1, b1) and np.array_equal(a3, b3)
     assert np.array_equal(sc0, sc1)
+
+
+def test_exp_neg(hostsim):
+    """pw_exp_neg (table + degree-6 series, the e^{-tau} of the pixel sum) against numpy."""
+    rng = np.random.default_rng(5)
+    x = -np.concatenate([10 ** rng.uniform(-12, 2.85, 200000), rng.uniform(0, 40, 200000),
+                         [0.0, 1e-300, 707.9, 708.0, 708.5, 745.0, 800.0, np.inf]])
+    out = np.zeros_like(x)
+    hostsim.hs_exp_neg.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    hostsim.hs_exp_neg(P(x), x.size, P(out))
+    ref = np.exp(x)
+    live = x > -708.0
+    assert np.max(np.abs(out[live] / ref[live] - 1)) < 3e-16
+    assert np.all(out[~live] == 0.0)
+    assert out[0 + 400000] == 1.0
