@@ -415,6 +415,7 @@ k_rt_sum(int B, int nw, int nr, pwb_rt_opts o, const double* __restrict__ wl, co
   __shared__ double s_np[PW_RT_CHUNK], s_i0[PW_RT_CHUNK];
   __shared__ double s_e2[32];
   if (threadIdx.x < 32) s_e2[threadIdx.x] = kExp2TabDev[threadIdx.x];
+  const unsigned e2 = (unsigned)__cvta_generic_to_shared(s_e2);
   const int b = blockIdx.x, split = blockIdx.y;
   const int k = blockIdx.z * blockDim.x + threadIdx.x;  // wavelength index
   const bool bad = status && status[b] != PW_OK && status[b] != PW_WARN_HE_RELAX;
@@ -435,7 +436,7 @@ k_rt_sum(int B, int nw, int nr, pwb_rt_opts o, const double* __restrict__ wl, co
       for (int q = p0; q < p1; ++q) {
         const int lo = px_lo[q];
         const double t = px_whi[q] * tb[(size_t)(lo + 1) * nw] + px_wlo[q] * tb[(size_t)lo * nw];
-        acc = pw_fma(px_i0[q], pw_exp_neg(-t, s_e2), acc);
+        acc = pw_fma(px_i0[q], pw_exp_neg_sh(-t, e2), acc);
       }
       if (split == 0) acc += meta[1];
       out[((size_t)b * nsplit + split) * nw + k] = acc;
@@ -478,8 +479,10 @@ k_rt_sum(int B, int nw, int nr, pwb_rt_opts o, const double* __restrict__ wl, co
     }
     __syncthreads();
     const int cnt = min(PW_RT_CHUNK, p1 - start);
+    if (k < nw) {  // (the warps past the last wavelength only help staging)
 #pragma unroll 4
-    for (int j = 0; j < cnt; ++j) acc = pw_fma(s_i0[j], pw_exp_neg(-(s_np[j] * phi), s_e2), acc);
+      for (int j = 0; j < cnt; ++j) acc = pw_fma(s_i0[j], pw_exp_neg_sh(-(s_np[j] * phi), e2), acc);
+    }
   }
   if (k < nw) {
     if (split == 0) acc += meta[1];  // pixels with tau = 0
