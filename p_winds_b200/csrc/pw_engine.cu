@@ -3,7 +3,9 @@
 //
 // Kernel map (one retrieval-grid model = one (T0, Mdot, h_fraction) triple):
 //   k_sed_setup     1 CTA       cross-section tables + SED integrals   (per context)
-//   k_hydrogen      1 CTA/model Parker + exact photoionisation + RK45 + relax loop
+//   k_h_fields      1 CTA/model and pass: Parker + exact photoionisation integrals
+//   k_h_solve       1 thread/model and pass: RK45 + mu-bar + relax-loop test
+//   k_h_finish      1 CTA/model: outputs
 //   k_helium        1 thread/model LSODA (Adams/BDF) + relax loop
 //   k_he_density    elementwise  n(He 2^3S) / n(H I) and v in SI for the RT stage
 //   k_rt_los        1 CTA/model LOS projection: column densities + broadening moments
@@ -72,7 +74,7 @@ struct pwb_ctx {
   cudaStream_t streams[kMaxChunks] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev_start = nullptr, ev_done[kMaxChunks] = {nullptr, nullptr, nullptr, nullptr};
   // scratch
-  DevBuf he_order, he_work, rt_ncol, rt_sums, rt_partial, rt_tau, fw_f, fw_scal, fw_he, fw_n, fw_v, fw_T, misc;
+  DevBuf h_state, h_fields, he_order, he_work, rt_ncol, rt_sums, rt_partial, rt_tau, fw_f, fw_scal, fw_he, fw_n, fw_v, fw_T, misc;
 };
 
 static int fail(pwb_ctx* c, const char* fmt, const char* a = "") {
@@ -112,16 +114,44 @@ __global__ void k_parker_tidal(const double* __restrict__ r, int n, double cs, d
   if (i < n) parker_point_tidal(c, r[i], &v[i], &rho[i]);
 }
 
-// One CTA per model.  Dynamic shared memory: [3*n_h tables (optional)] [10*Nr work] [40 red]
+// ---- hydrogen stage: three kernels per batch instead of one CTA per model --------------
+// k_h_fields  one CTA per model and pass: normalisation, Parker structure, Nr x N_lambda
+//             photoionisation integrals; all 128 lanes busy.  Dynamic shared memory:
+//             [3*n_h tables (optional)] [10*Nr work] [40 red]
+// k_h_solve   one *thread* per model and pass: the RK45 solve (serial by nature), mu-bar,
+//             convergence test; 32 independent models per warp
+// k_h_finish  one CTA per model: outputs, Parker structure for the helium stage
+// State between passes lives in global memory: HState per model + kHFieldsPerRadius*Nr doubles
+// (rn, v, rho, phi, tau, f, fprev).  The host enqueues max_n_relax + 1 rounds; a finished
+// model's CTA / thread returns at once.
+constexpr int kHFieldsPerRadius = 7;
+
+__device__ __forceinline__ HParams h_params(const pwb_h_opts& o, double T, double mdot, double hfrac, double mu0) {
+  HParams p;
+  p.T = T; p.mdot = mdot; p.h_fraction = hfrac; p.mu0 = mu0;
+  p.r_pl = o.planet_radius; p.m_pl = o.planet_mass; p.m_star = o.star_mass; p.a_au = o.semimajor_axis;
+  p.initial_f_ion = o.initial_f_ion; p.convergence = o.convergence; p.max_n_relax = o.max_n_relax;
+  p.relax = o.relax_solution; p.exact_phi = o.exact_phi; p.phi_abs = o.phi_abs; p.a0 = o.a_0;
+  p.ivp.rtol = o.rtol; p.ivp.atol = o.atol; p.ivp.first_step = o.first_step; p.ivp.max_step = o.max_step;
+  p.out_tidal = o.structure_tidal;
+  return p;
+}
+
 __global__ void __launch_bounds__(128)
-k_hydrogen(int B, const double* __restrict__ T, const double* __restrict__ mdot,
+k_h_fields(int B, int pass, const double* __restrict__ T, const double* __restrict__ mdot,
            const double* __restrict__ hfrac, const double* __restrict__ mu0,
            const double* __restrict__ r, int nr, pwb_h_opts o, const double* __restrict__ gw,
            const double* __restrict__ s_h, const double* __restrict__ s_he, int n_h, int tables_in_smem,
-           double* f_r, double* v, double* rho, double* scal, int* status) {
+           HState* __restrict__ state, double* __restrict__ fields) {
   extern __shared__ double smem[];
   const int b = blockIdx.x;
   if (b >= B) return;
+  const HParams p = h_params(o, T[b], mdot[b], hfrac[b], mu0[b]);
+  if (pass == 0) {
+    if (threadIdx.x == 0) h_state_init(p, &state[b]);
+  } else if (state[b].done) {
+    return;
+  }
   double* base = smem;
   SedTables t;
   t.n_h = n_h; t.i1 = 0; t.i0 = 0;
@@ -137,16 +167,45 @@ k_hydrogen(int B, const double* __restrict__ T, const double* __restrict__ mdot,
   w.rn = base; w.v = base + nr; w.rho = base + 2 * nr; w.phi = base + 3 * nr; w.tau = base + 4 * nr;
   w.f = base + 5 * nr; w.fprev = base + 6 * nr; w.colh = base + 7 * nr; w.colhe = base + 8 * nr;
   w.rcm = base + 9 * nr; w.red = base + 10 * nr;
+  double* g = fields + (size_t)b * kHFieldsPerRadius * nr;
+  if (pass > 0)
+    for (int i = threadIdx.x; i < nr; i += blockDim.x) w.f[i] = g[5 * nr + i];
   __syncthreads();
-  HParams p;
-  p.T = T[b]; p.mdot = mdot[b]; p.h_fraction = hfrac[b]; p.mu0 = mu0[b];
-  p.r_pl = o.planet_radius; p.m_pl = o.planet_mass; p.m_star = o.star_mass; p.a_au = o.semimajor_axis;
-  p.initial_f_ion = o.initial_f_ion; p.convergence = o.convergence; p.max_n_relax = o.max_n_relax;
-  p.relax = o.relax_solution; p.exact_phi = o.exact_phi; p.phi_abs = o.phi_abs; p.a0 = o.a_0;
-  p.ivp.rtol = o.rtol; p.ivp.atol = o.atol; p.ivp.first_step = o.first_step; p.ivp.max_step = o.max_step;
-  p.out_tidal = o.structure_tidal;
+  const double mu = (pass == 0) ? p.mu0 : state[b].mu;
+  h_pass_fields(p, t, r, nr, w, pass, mu);
+  for (int i = threadIdx.x; i < nr; i += blockDim.x) {
+    g[i] = w.rn[i]; g[nr + i] = w.v[i]; g[2 * nr + i] = w.rho[i];
+    g[3 * nr + i] = w.phi[i]; g[4 * nr + i] = w.tau[i];
+  }
+}
+
+__global__ void __launch_bounds__(64)
+k_h_solve(int B, int pass, const double* __restrict__ T, const double* __restrict__ mdot,
+          const double* __restrict__ hfrac, const double* __restrict__ mu0, const double* __restrict__ r,
+          int nr, pwb_h_opts o, HState* __restrict__ state, double* __restrict__ fields) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  HState s = state[b];
+  if (s.done) return;
+  const HParams p = h_params(o, T[b], mdot[b], hfrac[b], mu0[b]);
+  double* g = fields + (size_t)b * kHFieldsPerRadius * nr;
+  HWork w;
+  w.rn = g; w.v = g + nr; w.rho = g + 2 * nr; w.phi = g + 3 * nr; w.tau = g + 4 * nr;
+  w.f = g + 5 * nr; w.fprev = g + 6 * nr; w.colh = nullptr; w.colhe = nullptr; w.rcm = nullptr; w.red = nullptr;
+  h_pass_solve(p, r, nr, w, pass, &s);
+  state[b] = s;
+}
+
+__global__ void __launch_bounds__(128)
+k_h_finish(int B, const double* __restrict__ T, const double* __restrict__ mdot,
+           const double* __restrict__ hfrac, const double* __restrict__ mu0, const double* __restrict__ r,
+           int nr, pwb_h_opts o, const HState* __restrict__ state, const double* __restrict__ fields,
+           double* f_r, double* v, double* rho, double* scal, int* status) {
+  const int b = blockIdx.x;
+  if (b >= B) return;
+  const HParams p = h_params(o, T[b], mdot[b], hfrac[b], mu0[b]);
   HOut out{f_r + (size_t)b * nr, v + (size_t)b * nr, rho + (size_t)b * nr, scal + (size_t)b * 8, status + b};
-  h_ion_fraction_model(p, t, r, nr, w, out);
+  h_finish(p, r, nr, fields + (size_t)b * kHFieldsPerRadius * nr + 5 * nr, state[b], out);
 }
 
 // Cost-ordered schedule of the helium stage.  A model's cost (LSODA steps x relax passes)
@@ -651,7 +710,7 @@ int pwb_create(int device, pwb_ctx** out) {
     cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming);
   }
   cudaEventCreateWithFlags(&c->ev_start, cudaEventDisableTiming);
-  cudaFuncSetAttribute(k_hydrogen, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(k_h_fields, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   cudaFuncSetAttribute(k_rt_los, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
   cudaFuncSetAttribute(k_rt_formal_tau, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
   *out = c;
@@ -662,7 +721,7 @@ void pwb_destroy(pwb_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   DevBuf* bufs[] = {&c->sed_gw, &c->sed_sh, &c->sed_she, &c->sed_scal, &c->lsoda_tab, &c->px_lo, &c->px_whi,
-                    &c->px_wlo, &c->px_i0, &c->px_meta, &c->geo_r, &c->he_order, &c->he_work, &c->rt_ncol, &c->rt_sums,
+                    &c->px_wlo, &c->px_i0, &c->px_meta, &c->geo_r, &c->h_state, &c->h_fields, &c->he_order, &c->he_work, &c->rt_ncol, &c->rt_sums,
                     &c->rt_partial, &c->rt_tau, &c->fw_f, &c->fw_scal, &c->fw_he, &c->fw_n, &c->fw_v, &c->fw_T, &c->misc};
   for (DevBuf* b : bufs) b->release();
   for (int i = 0; i < pwb_ctx::kMaxChunks; ++i) {
@@ -722,6 +781,34 @@ int pwb_parker_structure_tidal(pwb_ctx* c, const double* d_r, int n, double cs, 
   return 0;
 }
 
+static int launch_hydrogen(pwb_ctx* c, cudaStream_t s, int B, const double* d_T, const double* d_mdot,
+                           const double* d_hfrac, const double* d_mu0, const double* d_r, int Nr,
+                           const pwb_h_opts* o, double* d_f_r, double* d_v, double* d_rho, double* d_scal,
+                           int* d_status) {
+  const int n_h = c->sed_ready ? c->sed_nh : 0;
+  const size_t work = sizeof(double) * (10 * (size_t)Nr + 40), tab = sizeof(double) * 3 * (size_t)n_h;
+  const int in_smem = (o->exact_phi && work + tab <= 160 * 1024) ? 1 : 0;
+  const size_t smem = work + (in_smem ? tab : 0);
+  if (smem > 200 * 1024) return fail(c, "hydrogen stage: radius profile too long for shared memory");
+  if (c->h_state.ensure(sizeof(HState) * (size_t)B) ||
+      c->h_fields.ensure(sizeof(double) * kHFieldsPerRadius * (size_t)Nr * B))
+    return fail(c, "out of device memory");
+  HState* st = c->h_state.as<HState>();
+  double* fields = c->h_fields.as<double>();
+  const int n_pass = o->relax_solution ? o->max_n_relax + 1 : 1;
+  for (int pass = 0; pass < n_pass; ++pass) {
+    k_h_fields<<<B, 128, smem, s>>>(B, pass, d_T, d_mdot, d_hfrac, d_mu0, d_r, Nr, *o, c->sed_gw.as<double>(),
+                                    c->sed_sh.as<double>(), c->sed_she.as<double>(), n_h, in_smem, st, fields);
+    k_h_solve<<<(B + 63) / 64, 64, 0, s>>>(B, pass, d_T, d_mdot, d_hfrac, d_mu0, d_r, Nr, *o, st, fields);
+    c->launches += 2;
+  }
+  k_h_finish<<<B, 128, 0, s>>>(B, d_T, d_mdot, d_hfrac, d_mu0, d_r, Nr, *o, st, fields, d_f_r, d_v, d_rho, d_scal,
+                               d_status);
+  c->launches++;
+  PWB_CUDA(c, cudaGetLastError());
+  return 0;
+}
+
 int pwb_h_ion_fraction_batch(pwb_ctx* c, int B, const double* d_T, const double* d_mdot,
                              const double* d_hfrac, const double* d_mu0, const double* d_r, int Nr,
                              const pwb_h_opts* o, double* d_f_r, double* d_v, double* d_rho,
@@ -730,18 +817,8 @@ int pwb_h_ion_fraction_batch(pwb_ctx* c, int B, const double* d_T, const double*
   if (B <= 0) return 0;
   if (Nr < 2) return fail(c, "pwb_h_ion_fraction_batch: radius profile needs >= 2 points");
   if (o->exact_phi && !c->sed_ready) return fail(c, "pwb_h_ion_fraction_batch: exact_phi needs pwb_set_sed");
-  const int n_h = c->sed_ready ? c->sed_nh : 0;
-  size_t work = sizeof(double) * (10 * (size_t)Nr + 40);
-  size_t tab = sizeof(double) * 3 * (size_t)n_h;
-  int in_smem = (o->exact_phi && work + tab <= 160 * 1024) ? 1 : 0;
-  size_t smem = work + (in_smem ? tab : 0);
-  if (smem > 200 * 1024) return fail(c, "pwb_h_ion_fraction_batch: radius profile too long for shared memory");
-  k_hydrogen<<<B, 128, smem, (cudaStream_t)stream>>>(
-      B, d_T, d_mdot, d_hfrac, d_mu0, d_r, Nr, *o, c->sed_gw.as<double>(), c->sed_sh.as<double>(),
-      c->sed_she.as<double>(), n_h, in_smem, d_f_r, d_v, d_rho, d_scal, d_status);
-  c->launches++;
-  PWB_CUDA(c, cudaGetLastError());
-  return 0;
+  return launch_hydrogen(c, (cudaStream_t)stream, B, d_T, d_mdot, d_hfrac, d_mu0, d_r, Nr, o, d_f_r, d_v, d_rho,
+                         d_scal, d_status);
 }
 
 // Models per warp along the cost-sorted list (see HeSched).  `frac[s]` of the models, from the
@@ -1008,58 +1085,25 @@ int pwb_forward_batch(pwb_ctx* c, int B, const double* d_T, const double* d_mdot
   double* mu0 = base + 5 * bn;  // [B]
   double* hscal = d_hscal ? d_hscal : c->fw_scal.as<double>();
   double* hescal = d_hescal ? d_hescal : c->fw_he.as<double>();
-  const int n_h = c->sed_ready ? c->sed_nh : 0;
-  const size_t work = sizeof(double) * (10 * (size_t)Nr + 40), tab = sizeof(double) * 3 * (size_t)n_h;
-  const int in_smem = (hopts->exact_phi && work + tab <= 160 * 1024) ? 1 : 0;
-  const size_t smem = work + (in_smem ? tab : 0);
-  if (smem > 200 * 1024) return fail(c, "pwb_forward_batch: radius profile too long for shared memory");
-
-  // The helium stage is a long serial solve per model whose slowest members leave most
-  // of the GPU idle; cutting the batch into chunks on separate streams lets the H and RT
-  // stages of one chunk run under the helium tail of another.
-  int nchunk = std::min<int>(pwb_ctx::kMaxChunks, std::max(1, B / 512));
-  nchunk = 1;  // measured on B200 (64x64 grid): 1 chunk 175 ms, 2 chunks 197 ms, 4 chunks 191 ms -- the H stage of
-               // the next chunk steals issue slots from the latency-critical helium warps; kept as a knob
-  { const char* e = getenv("PWB_CHUNKS"); if (e) { int q = atoi(e); if (q >= 1 && q <= pwb_ctx::kMaxChunks) nchunk = q; } }
-  const int per = (B + nchunk - 1) / nchunk;
-  PWB_CUDA(c, cudaEventRecord(c->ev_start, s));
-  for (int q = 0; q < nchunk; ++q) {
-    const int b0 = q * per, nb = std::min(per, B - b0);
-    if (nb <= 0) { nchunk = q; break; }
-    cudaStream_t cs = (nchunk == 1) ? s : c->streams[q];
-    if (nchunk > 1) PWB_CUDA(c, cudaStreamWaitEvent(cs, c->ev_start, 0));
-    const size_t o1 = (size_t)b0, oN = (size_t)b0 * Nr;
-    k_mu0<<<(nb + 255) / 256, 256, 0, cs>>>(nb, d_hfrac + o1, mu0 + o1);   // quickstart.ipynb cell 2
-    c->launches++;
-    k_hydrogen<<<nb, 128, smem, cs>>>(nb, d_T + o1, d_mdot + o1, d_hfrac + o1, mu0 + o1, d_r, Nr, *hopts,
-                                      c->sed_gw.as<double>(), c->sed_sh.as<double>(), c->sed_she.as<double>(), n_h,
-                                      in_smem, f_r + oN, v + oN, rho + oN, hscal + o1 * 8, d_status + o1);
-    c->launches++;
-    PWB_CUDA(c, cudaGetLastError());
-    if (species == 0) {
-      if (launch_helium(c, cs, nb, d_T + o1, d_hfrac + o1, hscal + o1 * 8 + 1, hscal + o1 * 8 + 2,
-                        hscal + o1 * 8 + 3, 8, d_r, Nr, v + oN, rho + oN, f_r + oN, heopts,
-                        c->he_work.as<double>() +
-                            he_work_doubles(Nr, heopts->relax_solution, heopts->max_n_relax, heopts->method) * o1,
-                        c->he_order.as<int>() + o1, f1 + oN, f3 + oN, hescal + o1 * 4, nullptr, d_status + o1))
-        return -1;
-    }
-    k_he_density<<<(unsigned)(((size_t)nb * Nr + 255) / 256), 256, 0, cs>>>(
-        nb, Nr, species, d_hfrac + o1, hscal + o1 * 8, f_r + oN, f3 + oN, rho + oN, v + oN, d_T + o1,
-        c->fw_n.as<double>() + oN, c->fw_v.as<double>() + oN, c->fw_T.as<double>() + o1);
-    c->launches++;
-    PWB_CUDA(c, cudaGetLastError());
-    if (launch_rt(c, cs, nb, c->fw_n.as<double>() + oN, c->fw_v.as<double>() + oN, c->fw_T.as<double>() + o1, d_wl,
-                  Nw, rtopts, d_status + o1, d_spectrum + o1 * Nw, nullptr, c->rt_ncol.as<double>() + oN,
-                  c->rt_sums.as<double>() + o1 * 4, c->rt_partial.as<double>() + o1 * nsplit * Nw,
-                  c->rt_tau.as<double>() + oN * Nw))
+  // hydrogen -> helium -> line-of-sight + pixel sum, all on the caller's stream.  (Cutting the
+  // batch into chunks on separate streams to overlap the stages was measured slower on B200:
+  // another chunk's hydrogen stage steals issue slots from the latency-critical helium warps.)
+  k_mu0<<<(B + 255) / 256, 256, 0, s>>>(B, d_hfrac, mu0);   // quickstart.ipynb cell 2
+  c->launches++;
+  if (launch_hydrogen(c, s, B, d_T, d_mdot, d_hfrac, mu0, d_r, Nr, hopts, f_r, v, rho, hscal, d_status)) return -1;
+  if (species == 0) {
+    if (launch_helium(c, s, B, d_T, d_hfrac, hscal + 1, hscal + 2, hscal + 3, 8, d_r, Nr, v, rho, f_r, heopts,
+                      c->he_work.as<double>(), c->he_order.as<int>(), f1, f3, hescal, nullptr, d_status))
       return -1;
-    if (nchunk > 1) {
-      PWB_CUDA(c, cudaEventRecord(c->ev_done[q], cs));
-      PWB_CUDA(c, cudaStreamWaitEvent(s, c->ev_done[q], 0));
-    }
   }
-  return 0;
+  k_he_density<<<(unsigned)((bn + 255) / 256), 256, 0, s>>>(B, Nr, species, d_hfrac, hscal, f_r, f3, rho, v, d_T,
+                                                             c->fw_n.as<double>(), c->fw_v.as<double>(),
+                                                             c->fw_T.as<double>());
+  c->launches++;
+  PWB_CUDA(c, cudaGetLastError());
+  return launch_rt(c, s, B, c->fw_n.as<double>(), c->fw_v.as<double>(), c->fw_T.as<double>(), d_wl, Nw, rtopts,
+                   d_status, d_spectrum, nullptr, c->rt_ncol.as<double>(), c->rt_sums.as<double>(),
+                   c->rt_partial.as<double>(), c->rt_tau.as<double>());
 }
 
 int pwb_chi2_batch(pwb_ctx* c, int B, const double* d_spectrum, int Nw, const double* d_data,

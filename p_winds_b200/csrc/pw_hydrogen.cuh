@@ -122,95 +122,123 @@ struct HRhs {
   }
 };
 
-// One model, one CTA.  `r` is the radius profile in planetary radii (global).
-PW_HD void h_ion_fraction_model(const HParams& p, const SedTables& sed, const double* __restrict__ r,
-                                int nr, const HWork& w, const HOut& out) {
+// ---------------------------------------------------------------------------------------
+// hydrogen.ion_fraction (hydrogen.py:227-573) cut into the pieces the engine schedules:
+//   h_state_init   before the first pass
+//   h_pass_fields  block-cooperative: sonic-point normalisation, Parker structure over the
+//                  radii, exact photoionisation integrals (Nr x N_lambda exps) or the
+//                  rectangle-rule optical depth                       (:387-425, :480-501)
+//   h_pass_solve   one thread: solve_ivp RK45, mu-bar, convergence test (:451-476, :504-538)
+//   h_finish       block-cooperative: outputs + the structure handed to the helium stage
+// A batch runs them as separate kernels -- fields: one CTA per model, every lane busy;
+// solve: one *thread* per model -- instead of parking 127 lanes of a CTA at a barrier while
+// lane 0 integrates.  h_ion_fraction_model strings them together for one model (host
+// build of the tests; same code, same arithmetic).
+// ---------------------------------------------------------------------------------------
+struct HState {
+  double mu;       // mean molecular weight the next pass normalises with
+  double mu_bar;   // of the last solution
+  double vs_amw;   // `vs` average_molecular_weight is called with (hydrogen.py:351, rebound at :480 if exact)
+  int n_relax, nfev_total, n_solves, status;
+  int done;        // no further passes: converged, single pass, or failed
+};
+
+struct HPassScal {
+  double vs, rs, rhos, phi_unit, k1, k2;
+};
+
+PW_HD void h_state_init(const HParams& p, HState* s) {
+  s->mu = p.mu0;
+  s->mu_bar = 0.0;
+  s->vs_amw = sound_speed(p.T, p.mu0);
+  s->n_relax = 0; s->nfev_total = 0; s->n_solves = 0; s->status = PW_OK; s->done = 0;
+}
+
+// _normalize(phi_abs, k1_abs, k2_abs, r, mu)  (hydrogen.py:387-412)
+PW_HD HPassScal h_pass_scalars(const HParams& p, double mu) {
   const double alpha_rec = 2.59E-13 * pw_pow(p.T / 1E4, -0.7);  // hydrogen.py:207-223
   const double he_fraction = 1 - p.h_fraction;
-  const double he_h = he_fraction / p.h_fraction;
   const double a_0 = p.exact_phi ? 0. : p.a0;
   const double k1_abs = p.h_fraction * a_0 / (p.h_fraction + 4 * he_fraction) / kMH;
   const double k2_abs = p.h_fraction / (p.h_fraction + 4 * he_fraction) * alpha_rec / kMH;
+  HPassScal q;
+  q.vs = sound_speed(p.T, mu);
+  q.rs = radius_sonic_point_tidal(p.m_pl, q.vs, p.m_star, p.a_au);
+  q.rhos = density_sonic_point(p.mdot, q.rs, q.vs);
+  q.phi_unit = q.vs * 1E5 / q.rs / 7.1492E+09;
+  const double k1_unit = 1 / (q.rhos * q.rs * 7.1492E+09);
+  const double k2_unit = q.vs * 1E5 / q.rs / 7.1492E+09 / q.rhos;
+  q.k1 = k1_abs / k1_unit;
+  q.k2 = k2_abs / k2_unit;
+  return q;
+}
 
+// All threads of the CTA.  Reads w.f (solution of the previous pass) when pass > 0; leaves
+// rn, v, rho and phi (exact) or tau (approximate) in w.
+PW_HD void h_pass_fields(const HParams& p, const SedTables& sed, const double* __restrict__ r, int nr,
+                         const HWork& w, int pass, double mu) {
   for (int i = PW_TID; i < nr; i += PW_NT)
     w.rcm[i] = r[i] * p.r_pl * (7.1492e7 / 1e-2);  // (r * R_pl * u.Rjup).to(u.cm)
-
-  double mu = p.mu0;
-  double vs_amw = sound_speed(p.T, p.mu0);  // `vs` of hydrogen.py:351, rebound at :480 only if exact
-  double mu_bar = 0.0;
-  int n_relax = 0, nfev_total = 0, n_solves = 0, status = PW_OK;
-  const int n_pass = p.relax ? p.max_n_relax + 1 : 1;
-
-  for (int pass = 0; pass < n_pass; ++pass) {
-    // ---- _normalize(phi_abs, k1_abs, k2_abs, r, mu)  (hydrogen.py:387-412)
-    const double vs = sound_speed(p.T, mu);
-    const double rs = radius_sonic_point_tidal(p.m_pl, vs, p.m_star, p.a_au);
-    const double rhos = density_sonic_point(p.mdot, rs, vs);
-    if (p.exact_phi) vs_amw = vs;
-    const double phi_unit = vs * 1E5 / rs / 7.1492E+09;
-    const double k1_unit = 1 / (rhos * rs * 7.1492E+09);
-    const double k2_unit = vs * 1E5 / rs / 7.1492E+09 / rhos;
-    const double k1 = k1_abs / k1_unit, k2 = k2_abs / k2_unit;
-    const TidalCoef tc = tidal_coef(vs, rs, p.m_pl, p.m_star, p.a_au);
-    for (int i = PW_TID; i < nr; i += PW_NT) {
-      const double x = r[i] * p.r_pl / rs;
-      w.rn[i] = x;
-      parker_point_tidal(tc, x, &w.v[i], &w.rho[i]);
-    }
-    PW_SYNC();
-    if (p.exact_phi) {
-      // hydrogen.py:355-363 (pass 0, f = 0) and :480-490 (relax passes, f = f_r)
-      phi_exact(sed, w, nr, w.rho, rhos, pass == 0 ? nullptr : w.f, p.h_fraction);
-      for (int i = PW_TID; i < nr; i += PW_NT) w.phi[i] = w.phi[i] / phi_unit;
-    } else if (PW_TID == 0) {
-      // rectangle-rule column density, local cell included (hydrogen.py:424-425, :499-501)
-      double c = 0.0;
-      for (int i = nr - 1; i >= 0; --i) {
-        const double dr = (i < nr - 1) ? (w.rn[i + 1] - w.rn[i]) : (w.rn[nr - 1] - w.rn[nr - 2]);
-        const double wgt = (pass == 0) ? dr * w.rho[i] : dr * w.rho[i] * (1 - w.f[i]);
-        c += wgt;
-        w.tau[i] = k1 * c;
-      }
-    }
-    PW_SYNC();
-    // ---- solve_ivp(_fun, (r[0], r[-1]), [initial_f_ion], t_eval=r)  (:451, :504)
-    if (PW_TID == 0) {
-      for (int i = 0; i < nr; ++i) w.fprev[i] = w.f[i];
-      HRhs rhs{w.rn, w.phi, w.v, w.rho, w.tau, nr, p.exact_phi, 0, k2, p.phi_abs / phi_unit};
-      Rk45Stats st{0, 0, 0};
-      const double y0 = p.initial_f_ion;
-      const int got = rk45_solve<1>(rhs, w.rn, nr, &y0, p.ivp, w.f, &st);
-      nfev_total += st.nfev;
-      ++n_solves;
-      int flag = 0;  // 0 continue relaxing, 1 converged/stop, 2 failed
-      if (got != nr) {
-        flag = 2;  // len(f_r) != len(r) -> RuntimeError (:458-460, :511-513)
-      } else {
-        mu_bar = average_molecular_weight(w.f, r, p.r_pl, w.v, vs_amw, nr, p.m_pl, p.T, he_h);
-        if (pass > 0) {
-          double sd = 0.0, sp = 0.0;
-          for (int i = 0; i < nr; ++i) { sd += w.f[i] - w.fprev[i]; sp += w.fprev[i]; }
-          if (fabs(sd / sp) < p.convergence) flag = 1;
-        }
-      }
-      w.red[34] = (double)flag;
-      w.red[35] = mu_bar;
-      w.red[36] = (double)nfev_total;
-      w.red[37] = (double)n_solves;
-    }
-    PW_SYNC();
-    const int flag = (int)w.red[34];
-    mu_bar = w.red[35];
-    nfev_total = (int)w.red[36];
-    n_solves = (int)w.red[37];
-    PW_SYNC();
-    if (pass > 0) n_relax = pass;
-    if (flag == 2) { status = PW_FAIL_H_SOLVER; break; }
-    if (flag == 1) break;
-    mu = mu_bar;
+  const HPassScal q = h_pass_scalars(p, mu);
+  const TidalCoef tc = tidal_coef(q.vs, q.rs, p.m_pl, p.m_star, p.a_au);
+  for (int i = PW_TID; i < nr; i += PW_NT) {
+    const double x = r[i] * p.r_pl / q.rs;
+    w.rn[i] = x;
+    parker_point_tidal(tc, x, &w.v[i], &w.rho[i]);
   }
+  PW_SYNC();
+  if (p.exact_phi) {
+    // hydrogen.py:355-363 (pass 0, f = 0) and :480-490 (relax passes, f = f_r)
+    phi_exact(sed, w, nr, w.rho, q.rhos, pass == 0 ? nullptr : w.f, p.h_fraction);
+    for (int i = PW_TID; i < nr; i += PW_NT) w.phi[i] = w.phi[i] / q.phi_unit;
+  } else if (PW_TID == 0) {
+    // rectangle-rule column density, local cell included (hydrogen.py:424-425, :499-501)
+    double c = 0.0;
+    for (int i = nr - 1; i >= 0; --i) {
+      const double dr = (i < nr - 1) ? (w.rn[i + 1] - w.rn[i]) : (w.rn[nr - 1] - w.rn[nr - 2]);
+      const double wgt = (pass == 0) ? dr * w.rho[i] : dr * w.rho[i] * (1 - w.f[i]);
+      c += wgt;
+      w.tau[i] = q.k1 * c;
+    }
+  }
+  PW_SYNC();
+}
 
-  // ---- outputs + the structure the helium stage needs (quickstart.ipynb cell 7)
+// One thread.  solve_ivp(_fun, (r[0], r[-1]), [initial_f_ion], t_eval=r) (:451, :504) on the
+// fields of this pass, then mu-bar and the relax-loop bookkeeping (:462-476, :515-538).
+PW_HD void h_pass_solve(const HParams& p, const double* __restrict__ r, int nr, const HWork& w, int pass,
+                        HState* s) {
+  const HPassScal q = h_pass_scalars(p, s->mu);
+  if (p.exact_phi) s->vs_amw = q.vs;
+  const double he_h = (1 - p.h_fraction) / p.h_fraction;
+  for (int i = 0; i < nr; ++i) w.fprev[i] = w.f[i];
+  HRhs rhs{w.rn, w.phi, w.v, w.rho, w.tau, nr, p.exact_phi, 0, q.k2, p.phi_abs / q.phi_unit};
+  Rk45Stats st{0, 0, 0};
+  const double y0 = p.initial_f_ion;
+  const int got = rk45_solve<1>(rhs, w.rn, nr, &y0, p.ivp, w.f, &st);
+  s->nfev_total += st.nfev;
+  ++s->n_solves;
+  if (pass > 0) s->n_relax = pass;
+  if (got != nr) {
+    s->status = PW_FAIL_H_SOLVER;  // len(f_r) != len(r) -> RuntimeError (:458-460, :511-513)
+    s->done = 1;
+    return;
+  }
+  s->mu_bar = average_molecular_weight(w.f, r, p.r_pl, w.v, s->vs_amw, nr, p.m_pl, p.T, he_h);
+  if (pass > 0) {
+    double sd = 0.0, sp = 0.0;
+    for (int i = 0; i < nr; ++i) { sd += w.f[i] - w.fprev[i]; sp += w.fprev[i]; }
+    if (fabs(sd / sp) < p.convergence) s->done = 1;
+  }
+  if (!p.relax || pass >= p.max_n_relax) s->done = 1;
+  s->mu = s->mu_bar;
+}
+
+// All threads of the CTA: outputs + the structure the helium stage needs (quickstart.ipynb cell 7)
+PW_HD void h_finish(const HParams& p, const double* __restrict__ r, int nr, const double* __restrict__ f,
+                    const HState& s, const HOut& out) {
+  const double mu_bar = s.mu_bar;
+  int status = s.status;
   const double vs_f = sound_speed(p.T, mu_bar);
   double rs_f, rhos_f;
   if (status == PW_OK && !(mu_bar == mu_bar)) status = PW_FAIL_NAN;
@@ -225,7 +253,7 @@ PW_HD void h_ion_fraction_model(const HParams& p, const SedTables& sed, const do
       double vv, rr;
       if (p.out_tidal) parker_point_tidal(tcf, x, &vv, &rr);
       else parker_point(x, &vv, &rr);
-      out.f_r[i] = w.f[i];
+      out.f_r[i] = f[i];
       out.v[i] = vv;
       out.rho[i] = rr;
     } else {
@@ -235,10 +263,34 @@ PW_HD void h_ion_fraction_model(const HParams& p, const SedTables& sed, const do
   if (PW_TID == 0) {
     out.scal[0] = (status == PW_OK) ? mu_bar : nan_;
     out.scal[1] = vs_f; out.scal[2] = rs_f; out.scal[3] = rhos_f;
-    out.scal[4] = (double)n_relax; out.scal[5] = (double)nfev_total; out.scal[6] = (double)n_solves;
+    out.scal[4] = (double)s.n_relax; out.scal[5] = (double)s.nfev_total; out.scal[6] = (double)s.n_solves;
     out.scal[7] = 0.0;
     *out.status = status;
   }
+}
+
+// One model, one CTA (or one host thread).  `r` is the radius profile in planetary radii.
+PW_HD void h_ion_fraction_model(const HParams& p, const SedTables& sed, const double* __restrict__ r,
+                                int nr, const HWork& w, const HOut& out) {
+  HState s;
+  h_state_init(p, &s);
+  const int n_pass = p.relax ? p.max_n_relax + 1 : 1;
+  for (int pass = 0; pass < n_pass; ++pass) {
+    h_pass_fields(p, sed, r, nr, w, pass, s.mu);
+    if (PW_TID == 0) {
+      h_pass_solve(p, r, nr, w, pass, &s);
+      w.red[34] = s.mu; w.red[35] = s.mu_bar; w.red[36] = s.vs_amw;
+      w.red[37] = (double)s.n_relax; w.red[38] = (double)s.nfev_total; w.red[39] = (double)s.n_solves;
+      w.red[33] = (double)(2 * s.status + s.done);
+    }
+    PW_SYNC();
+    s.mu = w.red[34]; s.mu_bar = w.red[35]; s.vs_amw = w.red[36];
+    s.n_relax = (int)w.red[37]; s.nfev_total = (int)w.red[38]; s.n_solves = (int)w.red[39];
+    s.status = (int)w.red[33] >> 1; s.done = (int)w.red[33] & 1;
+    PW_SYNC();
+    if (s.done) break;
+  }
+  h_finish(p, r, nr, w.f, s, out);
 }
 
 }  // namespace pw
