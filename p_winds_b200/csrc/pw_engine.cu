@@ -144,8 +144,10 @@ k_h_fields(int B, int pass, const double* __restrict__ T, const double* __restri
            const double* __restrict__ s_h, const double* __restrict__ s_he, int n_h, int tables_in_smem,
            HState* __restrict__ state, double* __restrict__ fields) {
   extern __shared__ double smem[];
+  __shared__ double s_e2[32];
   const int b = blockIdx.x;
   if (b >= B) return;
+  if (threadIdx.x < 32) s_e2[threadIdx.x] = kExp2TabDev[threadIdx.x];
   const HParams p = h_params(o, T[b], mdot[b], hfrac[b], mu0[b]);
   if (pass == 0) {
     if (threadIdx.x == 0) h_state_init(p, &state[b]);
@@ -172,18 +174,19 @@ k_h_fields(int B, int pass, const double* __restrict__ T, const double* __restri
     for (int i = threadIdx.x; i < nr; i += blockDim.x) w.f[i] = g[5 * nr + i];
   __syncthreads();
   const double mu = (pass == 0) ? p.mu0 : state[b].mu;
-  h_pass_fields(p, t, r, nr, w, pass, mu);
+  h_pass_fields(p, t, r, nr, w, pass, mu, (unsigned)__cvta_generic_to_shared(s_e2));
   for (int i = threadIdx.x; i < nr; i += blockDim.x) {
     g[i] = w.rn[i]; g[nr + i] = w.v[i]; g[2 * nr + i] = w.rho[i];
     g[3 * nr + i] = w.phi[i]; g[4 * nr + i] = w.tau[i];
   }
 }
 
-__global__ void __launch_bounds__(64)
-k_h_solve(int B, int pass, const double* __restrict__ T, const double* __restrict__ mdot,
+__global__ void __launch_bounds__(32)
+k_h_solve(int B, int lanes, int pass, const double* __restrict__ T, const double* __restrict__ mdot,
           const double* __restrict__ hfrac, const double* __restrict__ mu0, const double* __restrict__ r,
           int nr, pwb_h_opts o, HState* __restrict__ state, double* __restrict__ fields) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if ((int)threadIdx.x >= lanes) return;
+  const int b = blockIdx.x * lanes + threadIdx.x;
   if (b >= B) return;
   HState s = state[b];
   if (s.done) return;
@@ -796,10 +799,14 @@ static int launch_hydrogen(pwb_ctx* c, cudaStream_t s, int B, const double* d_T,
   HState* st = c->h_state.as<HState>();
   double* fields = c->h_fields.as<double>();
   const int n_pass = o->relax_solution ? o->max_n_relax + 1 : 1;
+  // models per warp of the solve kernel: spread a small batch over all warp schedulers
+  // (the solve is latency bound), pack a large one
+  int lanes = (int)std::min<long long>(32, std::max<long long>(1, ((long long)B + 4LL * c->sm_count - 1) / (4LL * c->sm_count)));
+  if (const char* e = getenv("PWB_H_LANES")) { const int v = atoi(e); if (v >= 1 && v <= 32) lanes = v; }
   for (int pass = 0; pass < n_pass; ++pass) {
     k_h_fields<<<B, 128, smem, s>>>(B, pass, d_T, d_mdot, d_hfrac, d_mu0, d_r, Nr, *o, c->sed_gw.as<double>(),
                                     c->sed_sh.as<double>(), c->sed_she.as<double>(), n_h, in_smem, st, fields);
-    k_h_solve<<<(B + 63) / 64, 64, 0, s>>>(B, pass, d_T, d_mdot, d_hfrac, d_mu0, d_r, Nr, *o, st, fields);
+    k_h_solve<<<(B + lanes - 1) / lanes, 32, 0, s>>>(B, lanes, pass, d_T, d_mdot, d_hfrac, d_mu0, d_r, Nr, *o, st, fields);
     c->launches += 2;
   }
   k_h_finish<<<B, 128, 0, s>>>(B, d_T, d_mdot, d_hfrac, d_mu0, d_r, Nr, *o, st, fields, d_f_r, d_v, d_rho, d_scal,

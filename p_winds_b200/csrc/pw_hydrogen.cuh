@@ -57,7 +57,7 @@ struct HOut {
 // hydrogen.radiative_processes_exact for all radii; f_h == nullptr means the
 // scalar f_h_r = 0.0 of the first pass (hydrogen.py:359-363).
 PW_HD void phi_exact(const SedTables& t, const HWork& w, int nr, const double* rho_abs_scale,
-                     double rhos, const double* f_h, double h_fraction) {
+                     double rhos, const double* f_h, double h_fraction, unsigned e2tab = 0) {
   const double he_to_h = (1 - h_fraction) / h_fraction;
   // number densities (hydrogen.py:84-94); staged in tau/phi as scratch
   double* n_h = w.tau;
@@ -94,7 +94,11 @@ PW_HD void phi_exact(const SedTables& t, const HWork& w, int nr, const double* r
     double acc = 0.0;
     for (int j = PW_LANE; j < t.n_h; j += PW_NLANE) {
       const double tau = ch * t.s_h[j] + che * t.s_he[j];
-      acc += t.gw[j] * exp(-tau);
+#if defined(__CUDA_ARCH__)
+      acc += t.gw[j] * pw_exp_neg_sh(-tau, e2tab);
+#else
+      acc += t.gw[j] * pw_exp_neg(-tau, kExp2Tab);
+#endif
     }
     acc = warp_sum(acc);
     if (PW_LANE == 0) w.phi[i] = fabs(acc);
@@ -175,8 +179,9 @@ PW_HD HPassScal h_pass_scalars(const HParams& p, double mu) {
 
 // All threads of the CTA.  Reads w.f (solution of the previous pass) when pass > 0; leaves
 // rn, v, rho and phi (exact) or tau (approximate) in w.
+// `e2tab`: 32-bit shared-memory address of the CTA's copy of kExp2Tab (device build).
 PW_HD void h_pass_fields(const HParams& p, const SedTables& sed, const double* __restrict__ r, int nr,
-                         const HWork& w, int pass, double mu) {
+                         const HWork& w, int pass, double mu, unsigned e2tab = 0) {
   for (int i = PW_TID; i < nr; i += PW_NT)
     w.rcm[i] = r[i] * p.r_pl * (7.1492e7 / 1e-2);  // (r * R_pl * u.Rjup).to(u.cm)
   const HPassScal q = h_pass_scalars(p, mu);
@@ -189,7 +194,7 @@ PW_HD void h_pass_fields(const HParams& p, const SedTables& sed, const double* _
   PW_SYNC();
   if (p.exact_phi) {
     // hydrogen.py:355-363 (pass 0, f = 0) and :480-490 (relax passes, f = f_r)
-    phi_exact(sed, w, nr, w.rho, q.rhos, pass == 0 ? nullptr : w.f, p.h_fraction);
+    phi_exact(sed, w, nr, w.rho, q.rhos, pass == 0 ? nullptr : w.f, p.h_fraction, e2tab);
     for (int i = PW_TID; i < nr; i += PW_NT) w.phi[i] = w.phi[i] / q.phi_unit;
   } else if (PW_TID == 0) {
     // rectangle-rule column density, local cell included (hydrogen.py:424-425, :499-501)
