@@ -64,7 +64,7 @@ struct HeRhs {
   // cache
   int j;
   double xc;
-  double c[8], e1, e3, vv;
+  double c[8], e1, e3, vv, rvv;  // rvv = 1 / vv (PW_RDIV)
   double sl[5], x0, b0[5];
   int jc;
 
@@ -125,6 +125,7 @@ struct HeRhs {
     e1 = exp(-t1);
     e3 = exp(-t3);
     vv = v_;
+    rvv = PW_DIV(1., v_);
     xc = x;
   }
 
@@ -143,8 +144,8 @@ struct HeRhs {
     const double term_31 = (1 - f_1 - f_3) * c[1];
     const double term_33 = f_3 * phi3 * e3;
     if (dydx) {
-      dydx[0] = PW_DIV(term_11 + term_12 - term_13 - term_14 + term_15 + term_16 + term_17 - term_18 + term_19, vv);
-      dydx[1] = PW_DIV(term_31 - term_12 - term_33 + term_14 - term_15 - term_16 - term_17, vv);
+      dydx[0] = PW_RDIV(term_11 + term_12 - term_13 - term_14 + term_15 + term_16 + term_17 - term_18 + term_19, vv, rvv);
+      dydx[1] = PW_RDIV(term_31 - term_12 - term_33 + term_14 - term_15 - term_16 - term_17, vv, rvv);
     }
     if (terms) {
       terms[0] = term_13; terms[1] = term_33; terms[2] = term_11; terms[3] = term_31;

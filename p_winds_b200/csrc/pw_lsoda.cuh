@@ -30,6 +30,7 @@ struct LsodaTables {
   double elco[2][13][14];
   double tesco[2][13][4];
   double rtesco2[2][13];  // 1 / tesco[meth][nq][2] (label 700 scales acor by it)
+  double rtesco1[2][13], rtesco3[2][13];  // 1 / tesco[meth][nq][1], [3] (PW_RDIV)
   double cm1[13], cm2[6];
   double sm1[13];  // Adams stability-region bounds used by the switching logic
 };
@@ -92,7 +93,11 @@ PW_HD void lsoda_tables_init(LsodaTables* t) {
     }
   }
   for (int m = 0; m < 2; ++m)
-    for (int a = 0; a < 13; ++a) t->rtesco2[m][a] = (t->tesco[m][a][2] != 0.) ? 1. / t->tesco[m][a][2] : 0.;
+    for (int a = 0; a < 13; ++a) {
+      t->rtesco2[m][a] = (t->tesco[m][a][2] != 0.) ? 1. / t->tesco[m][a][2] : 0.;
+      t->rtesco1[m][a] = (t->tesco[m][a][1] != 0.) ? 1. / t->tesco[m][a][1] : 0.;
+      t->rtesco3[m][a] = (t->tesco[m][a][3] != 0.) ? 1. / t->tesco[m][a][3] : 0.;
+    }
   for (int i = 1; i <= 5; ++i) t->cm2[i] = t->tesco[1][i][2] * t->elco[1][i][i + 1];
   for (int i = 1; i <= 12; ++i) t->cm1[i] = t->tesco[0][i][2] * t->elco[0][i][i + 1];
   const double s[13] = {0., 0.5, 0.575, 0.55, 0.45, 0.35, 0.25, 0.2, 0.15, 0.1, 0.075, 0.05, 0.025};
@@ -158,6 +163,8 @@ struct Lsoda {
   const double* elp;     // elco[meth_tab][nq] in force (ODEPACK: el(1..l))
   double tq1, tq2, tq3;  // tesco(nq, 1..3) of the same table row
   double rtq2, rtq2u;    // 1 / tesco(nq, 2); the same for (nqu, table in force) as label 700 reads it
+  double rtq1, rtq3, rtc;  // 1 / tesco(nq, 1), 1 / tesco(nq, 3), 1 / (tesco(nq, 2) * conit)   (PW_RDIV)
+  double rdiag[N];       // 1 / diagonal of the LU factors (PW_RDIV in solsy)
   double tn, h, hu, hold, rc, el0, crate, conit, rmax, pdnorm, pdest, pdlast, ratio, hmxi, tsw;
   int nq, l, lmax, meth, mused, meth_tab, miter, jtyp, maxord, mxordn, mxords;
   int ialth, ipup, nslp, icount, irflag, jstart, kflag, jcur, ierpj, iersl;
@@ -230,10 +237,13 @@ struct Lsoda {
     const double* tq = tab.tesco[meth_tab - 1][nq];
     tq1 = tq[1]; tq2 = tq[2]; tq3 = tq[3];
     rtq2 = tab.rtesco2[meth_tab - 1][nq];
+    rtq1 = tab.rtesco1[meth_tab - 1][nq];
+    rtq3 = tab.rtesco3[meth_tab - 1][nq];
     const double el1 = elp[1];
     rc = PW_DIV(rc * el1, el0);
     el0 = el1;
     conit = PW_DIV(0.5, (double)(nq + 2));
+    rtc = PW_DIV(1., tq2 * conit);
   }
   PW_HD void scaleh(double* rh, double* pdh) {  // stoda labels 175-180
     *rh = fmin(*rh, rmax);
@@ -372,6 +382,8 @@ struct Lsoda {
     }
     ipvt[N - 1] = N - 1;
     if (wm[N - 1][N - 1] == 0.) ierpj = 1;
+#pragma unroll
+    for (int k = 0; k < N; ++k) rdiag[k] = PW_DIV(1., wm[k][k]);
   }
   // solsy -> dgesl (job = 0)
   PW_HD void solsy(double* b) {
@@ -390,7 +402,7 @@ struct Lsoda {
 #pragma unroll
     for (int kb = 0; kb < N; ++kb) {
       const int k = N - 1 - kb;
-      b[k] = PW_DIV(b[k], wm[k][k]);
+      b[k] = PW_RDIV(b[k], wm[k][k], rdiag[k]);
       const double t = -b[k];
 #pragma unroll
       for (int i = 0; i < k; ++i) b[i] += t * wm[i][k];
@@ -455,7 +467,7 @@ struct Lsoda {
           crate = (rm > c2) ? rm : c2;
         }
         const double c15 = 1.5 * crate;
-        const double dcon = PW_DIV(del * ((c15 < 1.) ? c15 : 1.), tq2 * conit);
+        const double dcon = PW_RDIV(del * ((c15 < 1.) ? c15 : 1.), tq2 * conit, rtc);
         if (dcon <= 1.) {
           const double pd = PW_DIV(rate, fabs(h * el0));
           pdest = (pd > pdest) ? pd : pdest;
@@ -548,7 +560,7 @@ struct Lsoda {
     if (nq != 1) {
       double top[N];
       row_get(l, top);
-      const double ddn = PW_DIV(vmnorm(top), tq1);
+      const double ddn = PW_RDIV(vmnorm(top), tq1, rtq1);
       rhdn = PW_DIV(1., 1.3 * pw_root(ddn, nq) + 0.0000013);
     }
     if (meth == 1) {
@@ -671,7 +683,7 @@ struct Lsoda {
       bool efail = false;
       if (!cfail) {
         jcur = 0;
-        dsm = PW_DIV((m == 0) ? del : vmnorm(acor), tq2);
+        dsm = PW_RDIV((m == 0) ? del : vmnorm(acor), tq2, rtq2);
         efail = !(dsm <= 1.);
       }
       if (cfail || efail) {  // labels 430 / 500 start the same way
@@ -737,7 +749,7 @@ struct Lsoda {
           row_get(lmax, top);
 #pragma unroll
           for (int i = 0; i < N; ++i) savf[i] = acor[i] - top[i];
-          const double dup = PW_DIV(vmnorm(savf), tq3);
+          const double dup = PW_RDIV(vmnorm(savf), tq3, rtq3);
           rhup = PW_DIV(1., 1.4 * pw_root(dup, l + 1) + 0.0000014);
         }
       } else {
