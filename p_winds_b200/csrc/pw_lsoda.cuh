@@ -279,24 +279,48 @@ struct Lsoda {
   // above kF the run-time rows are advanced out of line first (lsoda_pascal_hi); what the
   // register rows need from them -- row kF+2 as it stands before each of the last kF+1
   // passes -- comes back in `hand`.
+  // order known at compile time: straight-line code, no guards
+  template <int kSign, int Q>
+  PW_HD void pascal_q() {
+#pragma unroll
+    for (int j = Q; j >= 1; --j)
+#pragma unroll
+      for (int i1 = j; i1 <= Q; ++i1)
+#pragma unroll
+        for (int i = 0; i < N; ++i) yh[i1][i] += kSign * yh[i1 + 1][i];
+  }
   template <int kSign>
   PW_HD void pascal() {
+    static_assert(kF == 5, "one case per register-resident order");
+    switch (nq) {  // the register-resident orders, one unguarded body each
+      case 1: pascal_q<kSign, 1>(); return;
+      case 2: pascal_q<kSign, 2>(); return;
+      case 3: pascal_q<kSign, 3>(); return;
+      case 4: pascal_q<kSign, 4>(); return;
+      case 5: pascal_q<kSign, 5>(); return;
+      default: break;
+    }
     double hand[(kF + 1) * N];
-    if (PW_UNLIKELY(nq > kF)) lsoda_pascal_hi<N>(yhs_, nq, kF, (double)kSign, hand);
+    lsoda_pascal_hi<N>(yhs_, nq, kF, (double)kSign, hand);
 #pragma unroll
-    for (int j = kF + 1; j >= 1; --j)
-      if (j <= nq) {
+    for (int j = kF + 1; j >= 1; --j) {
 #pragma unroll
-        for (int i1 = j; i1 <= kF; ++i1)
-          if (i1 <= nq) {
+      for (int i1 = j; i1 <= kF; ++i1) {
 #pragma unroll
-            for (int i = 0; i < N; ++i) yh[i1][i] += kSign * yh[i1 + 1][i];
-          }
-        if (PW_UNLIKELY(nq > kF)) {
-#pragma unroll
-          for (int i = 0; i < N; ++i) yh[kF + 1][i] += kSign * hand[(kF + 1 - j) * N + i];
-        }
+        for (int i = 0; i < N; ++i) yh[i1][i] += kSign * yh[i1 + 1][i];
       }
+#pragma unroll
+      for (int i = 0; i < N; ++i) yh[kF + 1][i] += kSign * hand[(kF + 1 - j) * N + i];
+    }
+  }
+  template <int Q>
+  PW_HD void correct_q() {
+#pragma unroll
+    for (int j = 1; j <= Q + 1; ++j) {
+      const double r = elp[j];
+#pragma unroll
+      for (int i = 0; i < N; ++i) yh[j][i] += r * acor[i];
+    }
   }
   PW_HD void predict() { pascal<1>(); }
   PW_HD void retract() { pascal<-1>(); }
@@ -716,19 +740,20 @@ struct Lsoda {
         nqu = nq;
         rtq2u = rtq2;
         mused = meth;
-#pragma unroll
-        for (int j = 1; j <= kF + 1; ++j)
-          if (j <= l) {
-            const double r = elp[j];
-#pragma unroll
-            for (int i = 0; i < N; ++i) yh[j][i] += r * acor[i];
-          }
-        if (PW_UNLIKELY(nq > kF))
+        switch (nq) {  // yh(., j) += el(j) * acor for j = 1..l, unguarded per order
+          case 1: correct_q<1>(); break;
+          case 2: correct_q<2>(); break;
+          case 3: correct_q<3>(); break;
+          case 4: correct_q<4>(); break;
+          case 5: correct_q<5>(); break;
+          default:
+            correct_q<kF>();
 #pragma unroll 1
-          for (int j = kF + 2; j <= l; ++j) {
-            const double r = elp[j];
-            for (int i = 0; i < N; ++i) yhs_[(j) * N + i] += r * acor[i];
-          }
+            for (int j = kF + 2; j <= l; ++j) {
+              const double r = elp[j];
+              for (int i = 0; i < N; ++i) yhs_[(j) * N + i] += r * acor[i];
+            }
+        }
         --icount;
         if (icount < 0) {
           methodswitch(dsm, pnorm, &pdh, &rh);
