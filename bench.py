@@ -47,6 +47,16 @@ def grid(n_gpus):
     return TT.ravel(), MM.ravel(), HH.ravel()
 
 
+def grid_cfg3_share():
+    """One GPU's share (1/8, interleaved) of BASELINE configs[3]: 256 x 256 (T0, Mdot) x 3 h_fractions,
+    tidal Parker profile (M* = 1.07, a = 0.04634 au)."""
+    T0 = np.linspace(9000, 13000, 256)
+    md = np.logspace(9.5, 12, 256)
+    hf = np.array([0.85, 0.90, 0.95])
+    HH, TT, MM = np.meshgrid(hf, T0, md, indexing='ij')
+    return TT.ravel()[0::8].copy(), MM.ravel()[0::8].copy(), HH.ravel()[0::8].copy()
+
+
 def config(n_gpus):
     return {'workload': 'He-triplet retrieval grid 64x64 (T0, Mdot) per GPU (BASELINE configs[2]); '
                         'HD 209458 b, solar SED, Nr=100, G=100 (ss=10), Nw=200, 3 lines, exact_phi, '
@@ -255,24 +265,26 @@ def run_ours(args):
     sampler.join(2)
 
     # per-kernel device time of one step (CUDA events around each stage call)
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
-    barrier()
     Td, mdd, hfd = d_in[0], d_in[1], d_in[2]
     mu0 = (1 + 4 * (1 - hfd) / hfd) / (1 + (1 - hfd) / hfd)
-    ev[0].record()
-    h = eng.h_ion_fraction_batch(Td, mdd, hfd, mu0, rd, ho)
-    ev[1].record()
-    he = eng.he_population_batch(Td, hfd, h['scal'][:, 1].contiguous(), h['scal'][:, 2].contiguous(),
-                                 h['scal'][:, 3].contiguous(), rd, h['v'], h['rho'], h['f_r'], heo,
-                                 status=h['status'].clone())
-    ev[2].record()
-    nhe = h['rho'] * h['scal'][:, 3:4] * (1 - hfd[:, None]) / (hfd[:, None] + 4 * (1 - hfd[:, None])) \
-        / 1.67262192369e-24 * he['f_3'] * 1e6
-    vsi = h['v'] * h['scal'][:, 1:2] * 1000
-    ev[3].record()
-    eng.rt2d_batch(nhe, vsi, Td, wd, rto, status=he['status'])
-    ev[4].record()
-    barrier()
+    for _rep in range(2):  # first round warms the stage-level entry points (allocations), second is timed
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+        flush.fill_(1.0)
+        barrier()
+        ev[0].record()
+        h = eng.h_ion_fraction_batch(Td, mdd, hfd, mu0, rd, ho)
+        ev[1].record()
+        he = eng.he_population_batch(Td, hfd, h['scal'][:, 1].contiguous(), h['scal'][:, 2].contiguous(),
+                                     h['scal'][:, 3].contiguous(), rd, h['v'], h['rho'], h['f_r'], heo,
+                                     status=h['status'].clone())
+        ev[2].record()
+        nhe = h['rho'] * h['scal'][:, 3:4] * (1 - hfd[:, None]) / (hfd[:, None] + 4 * (1 - hfd[:, None])) \
+            / 1.67262192369e-24 * he['f_3'] * 1e6
+        vsi = h['v'] * h['scal'][:, 1:2] * 1000
+        ev[3].record()
+        eng.rt2d_batch(nhe, vsi, Td, wd, rto, status=he['status'])
+        ev[4].record()
+        barrier()
     t_h, t_he, t_rt = ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2]), ev[3].elapsed_time(ev[4])
     status = out['status'].cpu().numpy()
     nfe_he = float(he['scal'][:, 1].sum())
@@ -296,12 +308,16 @@ def run_ours(args):
     kernels = {
         'k_helium': {'ms': t_he, 'share_of_step': t_he / (t_h + t_he + t_rt), 'flop': w_he,
                      'achieved_tflops': w_he / (t_he * 1e-3) / 1e12,
-                     'note': 'latency bound: %.0f dependent RHS evaluations per model (max %.0f), one thread '
-                             'per model' % (nfe_he / B, float(he['scal'][:, 1].max()))},
-        'k_hydrogen': {'ms': t_h, 'share_of_step': t_h / (t_h + t_he + t_rt), 'flop': w_h,
+                     'note': 'latency bound: %.0f dependent RHS evaluations per model (max %.0f, counting the '
+                             'relax passes the cycle shortcut does not re-run), one thread per model, '
+                             'cost-ordered schedule' % (nfe_he / B, float(he['scal'][:, 1].max()))},
+        'k_h_fields+k_h_solve+k_h_finish': {'ms': t_h, 'share_of_step': t_h / (t_h + t_he + t_rt), 'flop': w_h,
                        'achieved_tflops': w_h / (t_h * 1e-3) / 1e12},
         'k_rt_los+k_rt_sum+k_rt_reduce': {'ms': t_rt, 'share_of_step': t_rt / (t_h + t_he + t_rt),
-                                           'flop': w_rt, 'achieved_tflops': w_rt / (t_rt * 1e-3) / 1e12},
+                                           'flop': w_rt, 'achieved_tflops': w_rt / (t_rt * 1e-3) / 1e12,
+                                           'note': 'flop = the reference algorithm (every lit pixel, 20-flop exp); '
+                                                   'the kernel merges equal-radius pixels (%d -> %d terms) and '
+                                                   'uses a 12-instruction exp' % (px, eng.n_active_pixels())},
     }
     dom = max(kernels, key=lambda k: kernels[k]['ms'])
     roofline = {'bound': 'fp64', 'kernel': dom, 'achieved': kernels[dom]['achieved_tflops'],
@@ -317,6 +333,33 @@ def run_ours(args):
                         'note': 'profiles + spectrum written per model; inputs (SED tables 22 KB, pixel table '
                                 '%d KB) stay L2 resident: HBM is not the bound' % (px * 28 // 1024)},
                 'kernels': kernels}
+
+    # the production-size batch: one GPU's share of the 256 x 256 x 3 tidal grid (24 576 models)
+    large = None
+    if rank == 0 and world == 1 and not args.no_large_batch:
+        Tl, ml, hl = (eng.dev(x) for x in grid_cfg3_share())
+        hol = Engine.h_opts(R_PL, M_PL, star_mass=1.07, semimajor_axis=0.04634, relax_solution=True,
+                            exact_phi=True, structure_tidal=True)
+        outl = eng.alloc_forward(Tl.numel(), NR, NW)
+        best = None
+        for _ in range(3):
+            flush.fill_(1.0)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            eng.forward_batch(Tl, ml, hl, rd, hol, heo, rto, wd, out=outl)
+            eng.chi2_batch(outl['spectrum'], data, sigma, norm, outl['status'])
+            e1.record()
+            torch.cuda.synchronize()
+            t = e0.elapsed_time(e1)
+            best = t if best is None else min(best, t)
+        stl = outl['status'].cpu().numpy()
+        large = {'workload': 'one GPU share (1/8, interleaved) of the 256x256x3 tidal He-triplet grid '
+                             '(BASELINE configs[3]): %d models' % Tl.numel(),
+                 'value': Tl.numel() / (best * 1e-3), 'unit': UNIT, 'ms_per_step': best,
+                 'models_ok_frac': float(((stl == 0) | (stl == 3)).mean()),
+                 'note': 'device-timed, inputs resident, best of 3 after L2 flush; not the headline config'}
+        del outl
 
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -337,7 +380,7 @@ def run_ours(args):
                         'api': 'p_winds_b200.engine.Engine.forward_batch + chi2_batch (C ABI pwb_forward_batch), '
                                'pinned host buffers in and out'},
                 'gpu_launches': int(launches), 'clocks': sampler.summary(), 'roofline': roofline,
-                'cpu_baseline': cpu_base,
+                'cpu_baseline': cpu_base, 'large_batch': large,
                 'models_ok_frac': n_ok / B, 'wall_s_timed_region': wall_dev}
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -352,6 +395,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-large-batch', action='store_true')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)

@@ -89,6 +89,9 @@ const char* pwb_last_error(pwb_ctx* ctx);
 const char* pwb_version(void);
 /* number of kernels this context has launched so far (bench.py `gpu_launches`) */
 long long pwb_launch_count(pwb_ctx* ctx);
+/* terms of the pixel sum of the current geometry (lit, in-range pixels after equal-radius
+ * pixels have been merged by pwb_set_geometry); 0 before pwb_set_geometry */
+int pwb_n_active_pixels(pwb_ctx* ctx);
 
 /* ---- per-context SED (spectrum dict after unit conversion: tools.py:405-408,
  *      hydrogen.py:57-61).  Builds sigma_H, sigma_He tables and Simpson weights on

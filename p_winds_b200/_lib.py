@@ -46,6 +46,7 @@ SYMBOLS = {
     'pwb_last_error': (C.c_char_p, [_VP]),
     'pwb_version': (C.c_char_p, []),
     'pwb_launch_count': (C.c_longlong, [_VP]),
+    'pwb_n_active_pixels': (_I, [_VP]),
     'pwb_set_sed': (_I, [_VP, _VP, _VP, _I, _VP]),
     'pwb_get_sed_scalars': (_I, [_VP, c_double_p]),
     'pwb_parker_structure': (_I, [_VP, _VP, _I, _VP, _VP, _VP]),

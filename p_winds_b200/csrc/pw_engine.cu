@@ -737,6 +737,7 @@ void pwb_destroy(pwb_ctx* c) {
 
 const char* pwb_last_error(pwb_ctx* c) { return c ? c->err.c_str() : "null context"; }
 long long pwb_launch_count(pwb_ctx* c) { return c ? c->launches : 0; }
+int pwb_n_active_pixels(pwb_ctx* c) { return (c && c->geo_ready) ? c->n_active : 0; }
 
 int pwb_set_sed(pwb_ctx* c, const double* d_wl, const double* d_flux, int n, void* stream) {
   if (!c) return -1;

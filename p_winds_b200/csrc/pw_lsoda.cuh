@@ -158,6 +158,7 @@ struct Lsoda {
   static constexpr int kHiDoubles = (kQ + 2) * N;
   double* yhs_;
   double y[N], ewt[N], savf[N], acor[N];
+  double ewi[N];  // rtol*|y| + atol, the quantity ewt is the reciprocal of (PW_RDIV)
   double wm[N][N];
   int ipvt[N];
   const double* elp;     // elco[meth_tab][nq] in force (ODEPACK: el(1..l))
@@ -189,6 +190,7 @@ struct Lsoda {
     for (int i = 0; i < N; ++i) {
       const double e = o.rtol * fabs(yc[i]) + o.atol;
       if (!(e > 0.0)) ok = false;
+      ewi[i] = e;
       ewt[i] = PW_DIV(1.0, e);
     }
     return ok;
@@ -339,13 +341,14 @@ struct Lsoda {
     // code); the column index only ever selects values, never addresses
 #pragma unroll 1
     for (int j = 0; j < N; ++j) {
-      double yj = 0., ej = 0.;
+      double yj = 0., ej = 0., eij = 0.;
 #pragma unroll
       for (int i = 0; i < N; ++i) {
         yj = (i == j) ? y[i] : yj;
         ej = (i == j) ? ewt[i] : ej;
+        eij = (i == j) ? ewi[i] : eij;
       }
-      const double r = fmax(srur * fabs(yj), PW_DIV(r0, ej));
+      const double r = fmax(srur * fabs(yj), PW_RDIV(r0, ej, eij));
       double yp[N], ftem[N];
 #pragma unroll
       for (int i = 0; i < N; ++i) yp[i] = (i == j) ? yj + r : y[i];
@@ -365,7 +368,7 @@ struct Lsoda {
     for (int i = 0; i < N; ++i) {
       double sum = 0.;
 #pragma unroll
-      for (int j = 0; j < N; ++j) sum += PW_DIV(fabs(wm[i][j]), ewt[j]);
+      for (int j = 0; j < N; ++j) sum += PW_RDIV(fabs(wm[i][j]), ewt[j], ewi[j]);
       an = fmax(an, sum * ewt[i]);
     }
     pdnorm = PW_DIV(an, fabs(hl0));

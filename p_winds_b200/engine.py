@@ -67,6 +67,10 @@ class Engine:
     def launch_count(self):
         return int(self.lib.pwb_launch_count(self.ctx))
 
+    def n_active_pixels(self):
+        """Terms of the pixel sum after merging equal-radius pixels (set_geometry)."""
+        return int(self.lib.pwb_n_active_pixels(self.ctx))
+
     # ---------------------------------------------------------------------- SED
     def set_sed(self, wavelength_angstrom, flux_cgs):
         wl, fl = self.dev(wavelength_angstrom), self.dev(flux_cgs)
