@@ -140,6 +140,17 @@ int pwb_he_population_batch(pwb_ctx* ctx, int B, const double* d_T, const double
 int pwb_set_geometry(pwb_ctx* ctx, const double* d_i0, const double* d_r_map, int npix,
                      const double* d_r_si, int Nr, void* stream);
 
+/* ---- phase-averaged transit (docs/source/advanced_tutorial.ipynb cell 11,
+ *      `transmission_model`): one geometry per sampled phase, slot 0..15, with the geometric
+ *      transit depth draw_transit returned for it.  After pwb_set_phase_count(n) the pixel
+ *      sum of pwb_rt2d_batch / pwb_forward_batch is
+ *          mean_{phase < n} ( sum_pixels I0 exp(-tau) + transit_depth_phase ),
+ *      i.e. numpy.mean(spectra, axis=0) of the notebook.  pwb_set_geometry = slot 0, depth 0,
+ *      one phase (transit.radiative_transfer_2d itself). */
+int pwb_set_geometry_phase(pwb_ctx* ctx, int slot, const double* d_i0, const double* d_r_map, int npix,
+                           const double* d_r_si, int Nr, double transit_depth, void* stream);
+int pwb_set_phase_count(pwb_ctx* ctx, int n_phases);
+
 /* ---- transit.radiative_transfer_2d, batched (transit.py:120-230) ----------------
  * inputs : d_n [B][Nr] number density (m^-3), d_v [B][Nr] velocity (m/s),
  *          d_T [B] (or [B][Nr] if temperature_is_profile), d_wl [Nw] (m);
@@ -169,6 +180,18 @@ int pwb_forward_batch(pwb_ctx* ctx, int B, const double* d_T, const double* d_md
 int pwb_chi2_batch(pwb_ctx* ctx, int B, const double* d_spectrum, int Nw, const double* d_data,
                    const double* d_sigma, double norm, const int* d_status, double* d_chi2,
                    void* stream);
+
+/* ---- instrumental broadening + likelihood of the retrieval loop (advanced_tutorial.ipynb
+ *      cells 13 and 15) ------------------------------------------------------------------
+ * pwb_convolve_extend_batch: astropy.convolution.convolve(spec_b, kernel, boundary='extend')
+ *      for every model; d_kernel [Nk], Nk odd, already normalised to unit sum
+ *      (normalize_kernel=True); d_out [B][Nw] may not alias d_spectrum.
+ * pwb_loglike_batch: out[b] = -0.5 * sum_k ((y_k - model_bk)^2 / yerr_k^2 + log(yerr_k^2));
+ *      failed models -> -inf (the notebook's `except RuntimeError: return -np.inf`). */
+int pwb_convolve_extend_batch(pwb_ctx* ctx, int B, const double* d_spectrum, int Nw, const double* d_kernel,
+                              int Nk, double* d_out, void* stream);
+int pwb_loglike_batch(pwb_ctx* ctx, int B, const double* d_model, int Nw, const double* d_y,
+                      const double* d_yerr, const int* d_status, double* d_out, void* stream);
 
 /* ---- transit.draw_transit (transit.py:20-116) with flatstar's rasteriser ---------
  * ld_law: 0 none, 1 linear, 2 quadratic, 3 square-root, 4 log, 5 exp, 6 s3, 7 c4

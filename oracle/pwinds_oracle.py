@@ -717,6 +717,52 @@ def radiative_transfer_2d(i0, r_map, r, n, v, w0, f, a_ij, wl, T, mass,
 
 
 # ----------------------------------------------------------------------------
+# The retrieval loop around the path (docs/source/advanced_tutorial.ipynb cells
+# 11, 13, 15): phase-averaged transmission spectrum, instrumental broadening,
+# log-likelihood.  Notebook code, restated; `astropy.convolution` is absent from
+# this image, so `convolve_extend` restates astropy's direct 1-D convolution
+# (convolve.py + src/convolve.c: kernel divided by its sum, array padded with its
+# edge values by half the kernel width, out[i] = sum_ii pad[i + ii] * g[nk-1-ii]):
+# PARITY UNPINNED against astropy itself; tests hold it to numpy.convolve on the
+# edge-padded array, which is the same mathematical definition.
+# ----------------------------------------------------------------------------
+def transmission_model(maps, r_si, n_si, v_si, w0, f, a_ij, wl, T, mass, v_wind=0.0):
+    """advanced_tutorial.ipynb cell 11: `maps` = [(flux_map, r_map, transit_depth), ...]
+    for the sampled phases -> mean over phases of (in-transit spectrum + depth)."""
+    spectra = []
+    for i0, r_map, depth in maps:
+        spec = radiative_transfer_2d(i0, r_map, r_si, n_si, v_si, w0, f, a_ij, wl, T, mass,
+                                     v_bulk=v_wind, method='average')
+        spectra.append(spec + depth)
+    return np.mean(np.array(spectra), axis=0)
+
+
+def convolve_extend(array, kernel):
+    """astropy.convolution.convolve(array, kernel, boundary='extend') for 1-D inputs
+    without NaNs (normalize_kernel=True)."""
+    array = np.asarray(array, dtype=float)
+    kernel = np.asarray(kernel, dtype=float)
+    if kernel.size % 2 == 0:
+        raise ValueError('Kernel size must be odd in all axes.')
+    g = kernel / kernel.sum()
+    nk, w = g.size, g.size // 2
+    pad = np.pad(array, w, mode='edge')
+    out = np.zeros_like(array)
+    for i in range(array.size):
+        top = 0.0
+        for ii in range(nk):
+            top += pad[i + ii] * g[nk - 1 - ii]
+        out[i] = top
+    return out
+
+
+def log_likelihood(model, y, yerr):
+    """advanced_tutorial.ipynb cell 15 (the RuntimeError -> -inf branch is the caller's)."""
+    sigma2 = yerr ** 2
+    return -0.5 * np.sum((y - model) ** 2 / sigma2 + np.log(sigma2))
+
+
+# ----------------------------------------------------------------------------
 # One forward model = the docs' cascading_model
 # (docs/source/quickstart.ipynb cells 4-12, advanced_tutorial.ipynb:226-345)
 # ----------------------------------------------------------------------------

@@ -56,6 +56,10 @@ SYMBOLS = {
     'pwb_he_population_batch': (_I, [_VP, _I, _VP, _VP, _VP, _VP, _VP, _I, _VP, _I, _VP, _VP, _VP,
                                      C.POINTER(HeOpts), _VP, _VP, _VP, _VP, _VP, _VP]),
     'pwb_set_geometry': (_I, [_VP, _VP, _VP, _I, _VP, _I, _VP]),
+    'pwb_set_geometry_phase': (_I, [_VP, _I, _VP, _VP, _I, _VP, _I, _D, _VP]),
+    'pwb_set_phase_count': (_I, [_VP, _I]),
+    'pwb_convolve_extend_batch': (_I, [_VP, _I, _VP, _I, _VP, _I, _VP, _VP]),
+    'pwb_loglike_batch': (_I, [_VP, _I, _VP, _I, _VP, _VP, _VP, _VP, _VP]),
     'pwb_rt2d_batch': (_I, [_VP, _I, _VP, _VP, _VP, _VP, _I, C.POINTER(RtOpts), _VP, _VP, _VP, _VP]),
     'pwb_forward_batch': (_I, [_VP, _I, _VP, _VP, _VP, _VP, _I, C.POINTER(HOpts), C.POINTER(HeOpts),
                                C.POINTER(RtOpts), _I, _VP, _I, _VP, _VP, _VP, _VP, _VP, _VP, _VP,

@@ -65,10 +65,19 @@ struct pwb_ctx {
   // LSODA coefficient tables
   DevBuf lsoda_tab;
   // geometry / pixel table
-  int npix = 0, n_active = 0, geo_nr = 0;
-  DevBuf px_lo, px_whi, px_wlo, px_i0, px_meta, geo_r;
-  double geo_s_out = 0.0;
-  bool geo_ready = false;
+  // One slot per transit phase (advanced_tutorial.ipynb cell 11 averages the spectrum over
+  // `sample_phases`); slot 0 alone is the single-geometry case of transit.radiative_transfer_2d.
+  static const int kMaxGeo = 16;
+  struct Geo {
+    DevBuf px_lo, px_whi, px_wlo, px_i0, px_meta;
+    int npix = 0, n_active = 0;
+    double s_out = 0.0;  // intensity of the lit pixels outside the radius grid (tau = 0)
+    double depth = 0.0;  // geometric transit depth added to the spectrum of this phase
+    bool ready = false;
+  } geo[kMaxGeo];
+  int n_geo = 1;         // phases the pixel sum averages over
+  int geo_nr = 0;
+  DevBuf geo_r;
   // internal streams for the chunked forward pipeline
   static const int kMaxChunks = 4;
   cudaStream_t streams[kMaxChunks] = {nullptr, nullptr, nullptr, nullptr};
@@ -552,12 +561,18 @@ k_rt_sum(int B, int nw, int nr, pwb_rt_opts o, const double* __restrict__ wl, co
   }
 }
 
-__global__ void k_rt_reduce(int B, int nw, int nsplit, const double* __restrict__ part, double* spec) {
+// Fixed-order sum of the pixel segments of one phase; `depth` (geometric transit depth of the
+// phase) is added, the result accumulated over phases and divided by their number at the end.
+__global__ void k_rt_reduce(int B, int nw, int nsplit, const double* __restrict__ part, double* spec, double depth,
+                            int accumulate, int divide_by) {
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (size_t)B * nw) return;
   const int b = (int)(idx / nw), k = (int)(idx % nw);
   double s = 0.0;
   for (int q = 0; q < nsplit; ++q) s += part[((size_t)b * nsplit + q) * nw + k];
+  if (depth != 0.0) s += depth;
+  if (accumulate) s = spec[idx] + s;
+  if (divide_by > 0) s /= (double)divide_by;
   spec[idx] = s;
 }
 
@@ -578,6 +593,52 @@ __global__ void k_chi2(int B, int nw, const double* __restrict__ spec, const dou
   }
 }
 
+
+// Instrumental broadening of the model spectrum: astropy.convolution.convolve(spec, kernel,
+// boundary='extend') as the retrieval of docs/source/advanced_tutorial.ipynb (cell 13) calls it.
+// astropy pads the array with its edge values by half the kernel width and evaluates the true
+// convolution out[i] = sum_ii pad[i + ii] * g[nk - 1 - ii], ii ascending; `kern` arrives already
+// divided by its sum (normalize_kernel=True, done with numpy on the host like astropy does).
+// One CTA per model, the spectrum staged in shared memory.
+__global__ void k_convolve_extend(int B, int nw, const double* __restrict__ spec, const double* __restrict__ kern,
+                                  int nk, double* __restrict__ out) {
+  extern __shared__ double sm[];  // nw spectrum + nk kernel
+  const int b = blockIdx.x;
+  double* sx = sm;
+  double* sk = sm + nw;
+  for (int i = threadIdx.x; i < nw; i += blockDim.x) sx[i] = spec[(size_t)b * nw + i];
+  for (int i = threadIdx.x; i < nk; i += blockDim.x) sk[i] = kern[i];
+  __syncthreads();
+  const int w = nk / 2;
+  for (int i = threadIdx.x; i < nw; i += blockDim.x) {
+    double top = 0.0;
+    for (int ii = 0; ii < nk; ++ii) {
+      int src = i + ii - w;
+      src = src < 0 ? 0 : (src > nw - 1 ? nw - 1 : src);
+      top += sx[src] * sk[nk - 1 - ii];
+    }
+    out[(size_t)b * nw + i] = top;
+  }
+}
+
+// log-likelihood of advanced_tutorial.ipynb cell 15: -0.5 * sum((y - m)^2 / yerr^2 + log(yerr^2)),
+// -inf where the model failed (the notebook's `except RuntimeError`)
+__global__ void k_loglike(int B, int nw, const double* __restrict__ model, const double* __restrict__ y,
+                          const double* __restrict__ yerr, const int* __restrict__ status, double* out) {
+  __shared__ double red[40];
+  const int b = blockIdx.x;
+  double s = 0.0;
+  for (int k = threadIdx.x; k < nw; k += blockDim.x) {
+    const double d = y[k] - model[(size_t)b * nw + k];
+    const double s2 = yerr[k] * yerr[k];
+    s += d * d / s2 + log(s2);
+  }
+  const double t = block_sum(s, red);
+  if (threadIdx.x == 0) {
+    const bool bad = status && status[b] != PW_OK && status[b] != PW_WARN_HE_RELAX;
+    out[b] = bad ? -(1.0 / 0.0) : -0.5 * t;
+  }
+}
 
 // ------------------------------------------------------------------------------------
 // transit.draw_transit (transit.py:20-116) with flatstar's rasteriser restated:
@@ -723,10 +784,12 @@ int pwb_create(int device, pwb_ctx** out) {
 void pwb_destroy(pwb_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
-  DevBuf* bufs[] = {&c->sed_gw, &c->sed_sh, &c->sed_she, &c->sed_scal, &c->lsoda_tab, &c->px_lo, &c->px_whi,
-                    &c->px_wlo, &c->px_i0, &c->px_meta, &c->geo_r, &c->h_state, &c->h_fields, &c->he_order, &c->he_work, &c->rt_ncol, &c->rt_sums,
+  DevBuf* bufs[] = {&c->sed_gw, &c->sed_sh, &c->sed_she, &c->sed_scal, &c->lsoda_tab, &c->geo_r, &c->h_state, &c->h_fields, &c->he_order, &c->he_work, &c->rt_ncol, &c->rt_sums,
                     &c->rt_partial, &c->rt_tau, &c->fw_f, &c->fw_scal, &c->fw_he, &c->fw_n, &c->fw_v, &c->fw_T, &c->misc};
   for (DevBuf* b : bufs) b->release();
+  for (auto& G : c->geo) {
+    G.px_lo.release(); G.px_whi.release(); G.px_wlo.release(); G.px_i0.release(); G.px_meta.release();
+  }
   for (int i = 0; i < pwb_ctx::kMaxChunks; ++i) {
     if (c->streams[i]) cudaStreamDestroy(c->streams[i]);
     if (c->ev_done[i]) cudaEventDestroy(c->ev_done[i]);
@@ -737,7 +800,7 @@ void pwb_destroy(pwb_ctx* c) {
 
 const char* pwb_last_error(pwb_ctx* c) { return c ? c->err.c_str() : "null context"; }
 long long pwb_launch_count(pwb_ctx* c) { return c ? c->launches : 0; }
-int pwb_n_active_pixels(pwb_ctx* c) { return (c && c->geo_ready) ? c->n_active : 0; }
+int pwb_n_active_pixels(pwb_ctx* c) { return (c && c->geo[0].ready) ? c->geo[0].n_active : 0; }
 
 int pwb_set_sed(pwb_ctx* c, const double* d_wl, const double* d_flux, int n, void* stream) {
   if (!c) return -1;
@@ -926,23 +989,27 @@ int pwb_he_population_batch(pwb_ctx* c, int B, const double* d_T, const double* 
                        d_status);
 }
 
-int pwb_set_geometry(pwb_ctx* c, const double* d_i0, const double* d_r_map, int npix,
-                     const double* d_r_si, int Nr, void* stream) {
+int pwb_set_geometry_phase(pwb_ctx* c, int slot, const double* d_i0, const double* d_r_map, int npix,
+                           const double* d_r_si, int Nr, double transit_depth, void* stream) {
   if (!c) return -1;
+  if (slot < 0 || slot >= pwb_ctx::kMaxGeo) return fail(c, "pwb_set_geometry_phase: slot out of range (0..15)");
+  if (slot > 0 && (!c->geo[0].ready || c->geo_nr != Nr))
+    return fail(c, "pwb_set_geometry_phase: set slot 0 first, with the same radius grid");
+  pwb_ctx::Geo& G = c->geo[slot];
   if (npix <= 0 || Nr < 2 || Nr > 1024) return fail(c, "pwb_set_geometry: bad sizes (need 2 <= Nr <= 1024)");
   cudaStream_t s = (cudaStream_t)stream;
-  if (c->px_lo.ensure(sizeof(int) * npix) || c->px_whi.ensure(sizeof(double) * npix) ||
-      c->px_wlo.ensure(sizeof(double) * npix) || c->px_i0.ensure(sizeof(double) * npix) ||
-      c->px_meta.ensure(sizeof(double) * 2) || c->geo_r.ensure(sizeof(double) * Nr))
+  if (G.px_lo.ensure(sizeof(int) * npix) || G.px_whi.ensure(sizeof(double) * npix) ||
+      G.px_wlo.ensure(sizeof(double) * npix) || G.px_i0.ensure(sizeof(double) * npix) ||
+      G.px_meta.ensure(sizeof(double) * 2) || c->geo_r.ensure(sizeof(double) * Nr))
     return fail(c, "pwb_set_geometry: out of device memory");
   PWB_CUDA(c, cudaMemcpyAsync(c->geo_r.p, d_r_si, sizeof(double) * Nr, cudaMemcpyDeviceToDevice, s));
-  k_pixel_table<<<1, 1024, 0, s>>>(d_i0, d_r_map, npix, c->geo_r.as<double>(), Nr, c->px_lo.as<int>(),
-                                   c->px_whi.as<double>(), c->px_wlo.as<double>(), c->px_i0.as<double>(),
-                                   c->px_meta.as<double>());
+  k_pixel_table<<<1, 1024, 0, s>>>(d_i0, d_r_map, npix, c->geo_r.as<double>(), Nr, G.px_lo.as<int>(),
+                                   G.px_whi.as<double>(), G.px_wlo.as<double>(), G.px_i0.as<double>(),
+                                   G.px_meta.as<double>());
   c->launches++;
   PWB_CUDA(c, cudaGetLastError());
   double meta[2];
-  PWB_CUDA(c, cudaMemcpyAsync(meta, c->px_meta.p, sizeof meta, cudaMemcpyDeviceToHost, s));
+  PWB_CUDA(c, cudaMemcpyAsync(meta, G.px_meta.p, sizeof meta, cudaMemcpyDeviceToHost, s));
   PWB_CUDA(c, cudaStreamSynchronize(s));
   int n_act = (int)meta[0];
   // Pixels at the same distance from the planet's centre see the same optical depth at every
@@ -955,10 +1022,10 @@ int pwb_set_geometry(pwb_ctx* c, const double* d_i0, const double* d_r_map, int 
   if (n_act > 1 && !getenv("PWB_NO_PIXEL_MERGE")) {
     std::vector<int> lo(n_act), idx(n_act);
     std::vector<double> whi(n_act), wlo(n_act), pi0(n_act);
-    PWB_CUDA(c, cudaMemcpy(lo.data(), c->px_lo.p, sizeof(int) * n_act, cudaMemcpyDeviceToHost));
-    PWB_CUDA(c, cudaMemcpy(whi.data(), c->px_whi.p, sizeof(double) * n_act, cudaMemcpyDeviceToHost));
-    PWB_CUDA(c, cudaMemcpy(wlo.data(), c->px_wlo.p, sizeof(double) * n_act, cudaMemcpyDeviceToHost));
-    PWB_CUDA(c, cudaMemcpy(pi0.data(), c->px_i0.p, sizeof(double) * n_act, cudaMemcpyDeviceToHost));
+    PWB_CUDA(c, cudaMemcpy(lo.data(), G.px_lo.p, sizeof(int) * n_act, cudaMemcpyDeviceToHost));
+    PWB_CUDA(c, cudaMemcpy(whi.data(), G.px_whi.p, sizeof(double) * n_act, cudaMemcpyDeviceToHost));
+    PWB_CUDA(c, cudaMemcpy(wlo.data(), G.px_wlo.p, sizeof(double) * n_act, cudaMemcpyDeviceToHost));
+    PWB_CUDA(c, cudaMemcpy(pi0.data(), G.px_i0.p, sizeof(double) * n_act, cudaMemcpyDeviceToHost));
     for (int i = 0; i < n_act; ++i) idx[i] = i;
     std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) {
       if (lo[a] != lo[b]) return lo[a] < lo[b];
@@ -977,26 +1044,45 @@ int pwb_set_geometry(pwb_ctx* c, const double* d_i0, const double* d_r_map, int 
     }
     n_act = (int)mlo.size();
     meta[0] = (double)n_act;
-    PWB_CUDA(c, cudaMemcpy(c->px_lo.p, mlo.data(), sizeof(int) * n_act, cudaMemcpyHostToDevice));
-    PWB_CUDA(c, cudaMemcpy(c->px_whi.p, mwhi.data(), sizeof(double) * n_act, cudaMemcpyHostToDevice));
-    PWB_CUDA(c, cudaMemcpy(c->px_wlo.p, mwlo.data(), sizeof(double) * n_act, cudaMemcpyHostToDevice));
-    PWB_CUDA(c, cudaMemcpy(c->px_i0.p, mi0.data(), sizeof(double) * n_act, cudaMemcpyHostToDevice));
-    PWB_CUDA(c, cudaMemcpy(c->px_meta.p, meta, sizeof meta, cudaMemcpyHostToDevice));
+    PWB_CUDA(c, cudaMemcpy(G.px_lo.p, mlo.data(), sizeof(int) * n_act, cudaMemcpyHostToDevice));
+    PWB_CUDA(c, cudaMemcpy(G.px_whi.p, mwhi.data(), sizeof(double) * n_act, cudaMemcpyHostToDevice));
+    PWB_CUDA(c, cudaMemcpy(G.px_wlo.p, mwlo.data(), sizeof(double) * n_act, cudaMemcpyHostToDevice));
+    PWB_CUDA(c, cudaMemcpy(G.px_i0.p, mi0.data(), sizeof(double) * n_act, cudaMemcpyHostToDevice));
+    PWB_CUDA(c, cudaMemcpy(G.px_meta.p, meta, sizeof meta, cudaMemcpyHostToDevice));
   }
-  c->npix = npix; c->n_active = n_act; c->geo_s_out = meta[1]; c->geo_nr = Nr;
-  c->geo_ready = true;
+  G.npix = npix; G.n_active = n_act; G.s_out = meta[1]; G.depth = transit_depth; G.ready = true;
+  c->geo_nr = Nr;
   return 0;
 }
+
+int pwb_set_geometry(pwb_ctx* c, const double* d_i0, const double* d_r_map, int npix,
+                     const double* d_r_si, int Nr, void* stream) {
+  if (!c) return -1;
+  c->n_geo = 1;
+  return pwb_set_geometry_phase(c, 0, d_i0, d_r_map, npix, d_r_si, Nr, 0.0, stream);
+}
+
+int pwb_set_phase_count(pwb_ctx* c, int n_phases) {
+  if (!c) return -1;
+  if (n_phases < 1 || n_phases > pwb_ctx::kMaxGeo) return fail(c, "pwb_set_phase_count: 1..16 phases");
+  for (int g = 0; g < n_phases; ++g)
+    if (!c->geo[g].ready) return fail(c, "pwb_set_phase_count: a phase slot has no geometry yet");
+  c->n_geo = n_phases;
+  return 0;
+}
+
 
 static int rt_nsplit(const pwb_ctx* c) {
   // The active pixels are always cut into the same segments, whatever the batch size,
   // so that a model's spectrum is bit-identical alone or inside a grid (the partial
   // sums are combined in a fixed order by k_rt_reduce).  <= 16 segments of >= 1024 pixels.
-  return std::min(16, std::max(1, (c->n_active + 1023) / 1024));
+  int n = 0;
+  for (int g = 0; g < c->n_geo; ++g) n = std::max(n, c->geo[g].n_active);
+  return std::min(16, std::max(1, (n + 1023) / 1024));
 }
 
 static int rt_check(pwb_ctx* c, const pwb_rt_opts* o) {
-  if (!c->geo_ready) return fail(c, "pwb_rt2d_batch: call pwb_set_geometry first");
+  if (!c->geo[0].ready) return fail(c, "pwb_rt2d_batch: call pwb_set_geometry first");
   if (o->n_lines < 1 || o->n_lines > 8) return fail(c, "pwb_rt2d_batch: 1..8 spectral lines supported");
   if (o->wind_broadening_method != 0 && o->wind_broadening_method != 1)
     return fail(c, "The chosen ``wind_broadening_method`` is not implemented.");
@@ -1010,7 +1096,9 @@ static int launch_rt(pwb_ctx* c, cudaStream_t s, int B, const double* d_n, const
   const int Nr = c->geo_nr;
   const int tiles = (Nw + 255) / 256;
   const int nsplit = rt_nsplit(c);
-  double* part = (nsplit > 1) ? partial : d_spectrum;
+  // one phase, no depth to add, one pixel segment: the sum goes straight to the spectrum
+  const bool direct = (nsplit == 1 && c->n_geo == 1 && c->geo[0].depth == 0.0);
+  double* part = direct ? d_spectrum : partial;
   if (o->wind_broadening_method == 1) {
     const size_t smem = sizeof(double) * (4 * (size_t)Nr + 4 * (size_t)o->z_grid_size);
     if (smem > 100 * 1024) return fail(c, "pwb_rt2d_batch: z_grid_size too large for the 'formal' kernel");
@@ -1026,16 +1114,22 @@ static int launch_rt(pwb_ctx* c, cudaStream_t s, int B, const double* d_n, const
     tau_tab = nullptr;
   }
   dim3 grid(B, nsplit, tiles);
-  k_rt_sum<<<grid, 256, 0, s>>>(B, Nw, Nr, *o, d_wl, d_T, ncol, sums, d_status, c->px_lo.as<int>(),
-                                c->px_whi.as<double>(), c->px_wlo.as<double>(), c->px_i0.as<double>(),
-                                c->px_meta.as<double>(), nsplit, part, d_tau, tau_tab);
-  c->launches++;
-  PWB_CUDA(c, cudaGetLastError());
-  if (nsplit > 1) {
-    const size_t tot = (size_t)B * Nw;
-    k_rt_reduce<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(B, Nw, nsplit, part, d_spectrum);
+  // spectrum = mean over the phases of (pixel sum + transit depth of the phase), summed in
+  // phase order and divided once, as numpy.mean(spectra, axis=0) does
+  for (int g = 0; g < c->n_geo; ++g) {
+    pwb_ctx::Geo& G = c->geo[g];
+    k_rt_sum<<<grid, 256, 0, s>>>(B, Nw, Nr, *o, d_wl, d_T, ncol, sums, d_status, G.px_lo.as<int>(),
+                                  G.px_whi.as<double>(), G.px_wlo.as<double>(), G.px_i0.as<double>(),
+                                  G.px_meta.as<double>(), nsplit, part, g == 0 ? d_tau : nullptr, tau_tab);
     c->launches++;
     PWB_CUDA(c, cudaGetLastError());
+    if (!direct) {
+      const size_t tot = (size_t)B * Nw;
+      k_rt_reduce<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(B, Nw, nsplit, part, d_spectrum, G.depth, g > 0,
+                                                                (g == c->n_geo - 1 && c->n_geo > 1) ? c->n_geo : 0);
+      c->launches++;
+      PWB_CUDA(c, cudaGetLastError());
+    }
   }
   return 0;
 }
@@ -1049,7 +1143,7 @@ int pwb_rt2d_batch(pwb_ctx* c, int B, const double* d_n, const double* d_v, cons
   const int Nr = c->geo_nr;
   const int nsplit = rt_nsplit(c);
   if (c->rt_ncol.ensure(sizeof(double) * (size_t)B * Nr) || c->rt_sums.ensure(sizeof(double) * (size_t)B * 4) ||
-      (nsplit > 1 && c->rt_partial.ensure(sizeof(double) * (size_t)B * nsplit * Nw)) ||
+      c->rt_partial.ensure(sizeof(double) * (size_t)B * nsplit * Nw) ||
       (o->wind_broadening_method == 1 && c->rt_tau.ensure(sizeof(double) * (size_t)B * Nr * Nw)))
     return fail(c, "out of device memory");
   return launch_rt(c, (cudaStream_t)stream, B, d_n, d_v, d_T, d_wl, Nw, o, d_status, d_spectrum, d_tau,
@@ -1081,7 +1175,7 @@ int pwb_forward_batch(pwb_ctx* c, int B, const double* d_T, const double* d_mdot
       c->he_work.ensure(sizeof(double) * he_work_doubles(Nr, heopts->relax_solution, heopts->max_n_relax, heopts->method) * B) ||
       c->he_order.ensure(sizeof(int) * (size_t)B) || c->rt_ncol.ensure(sizeof(double) * bn) ||
       c->rt_sums.ensure(sizeof(double) * (size_t)B * 4) ||
-      (nsplit > 1 && c->rt_partial.ensure(sizeof(double) * (size_t)B * nsplit * Nw)) ||
+      c->rt_partial.ensure(sizeof(double) * (size_t)B * nsplit * Nw) ||
       (rtopts->wind_broadening_method == 1 && c->rt_tau.ensure(sizeof(double) * bn * Nw)))
     return fail(c, "out of device memory");
   double* base = c->fw_f.as<double>();
@@ -1119,6 +1213,31 @@ int pwb_chi2_batch(pwb_ctx* c, int B, const double* d_spectrum, int Nw, const do
   if (!c) return -1;
   if (B <= 0) return 0;
   k_chi2<<<B, 128, 0, (cudaStream_t)stream>>>(B, Nw, d_spectrum, d_data, d_sigma, norm, d_status, d_chi2);
+  c->launches++;
+  PWB_CUDA(c, cudaGetLastError());
+  return 0;
+}
+
+int pwb_convolve_extend_batch(pwb_ctx* c, int B, const double* d_spectrum, int Nw, const double* d_kernel, int Nk,
+                              double* d_out, void* stream) {
+  if (!c) return -1;
+  if (B <= 0) return 0;
+  if (Nk < 1 || Nk % 2 == 0) return fail(c, "pwb_convolve_extend_batch: the kernel needs an odd number of samples");
+  const size_t smem = sizeof(double) * ((size_t)Nw + Nk);
+  if (smem > 200 * 1024) return fail(c, "pwb_convolve_extend_batch: spectrum + kernel exceed shared memory");
+  if (smem > 48 * 1024)
+    PWB_CUDA(c, cudaFuncSetAttribute(k_convolve_extend, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_convolve_extend<<<B, 256, smem, (cudaStream_t)stream>>>(B, Nw, d_spectrum, d_kernel, Nk, d_out);
+  c->launches++;
+  PWB_CUDA(c, cudaGetLastError());
+  return 0;
+}
+
+int pwb_loglike_batch(pwb_ctx* c, int B, const double* d_model, int Nw, const double* d_y, const double* d_yerr,
+                      const int* d_status, double* d_out, void* stream) {
+  if (!c) return -1;
+  if (B <= 0) return 0;
+  k_loglike<<<B, 128, 0, (cudaStream_t)stream>>>(B, Nw, d_model, d_y, d_yerr, d_status, d_out);
   c->launches++;
   PWB_CUDA(c, cudaGetLastError());
   return 0;

@@ -176,6 +176,52 @@ class Engine:
                                               r.numel(), self._stream()))
         self._geo_nr = r.numel()
 
+    def set_geometry_phases(self, maps, radius_profile_si):
+        """Phase-averaged transit (advanced_tutorial.ipynb cell 11): `maps` is a sequence of
+        (intensity_0, r_from_planet, transit_depth), one per sampled phase.  Afterwards the
+        spectra of rt2d_batch / forward_batch are mean_phase(sum_pixels I0 e^-tau + depth)."""
+        r = self.dev(radius_profile_si).reshape(-1)
+        if not 1 <= len(maps) <= 16:
+            raise ValueError('1 to 16 phases')
+        for slot, (i0, rm, depth) in enumerate(maps):
+            i0, rm = self.dev(i0).reshape(-1), self.dev(rm).reshape(-1)
+            if i0.numel() != rm.numel():
+                raise ValueError('intensity map and radius map must have the same shape')
+            self._check(self.lib.pwb_set_geometry_phase(self.ctx, slot, _ptr(i0), _ptr(rm), i0.numel(),
+                                                        _ptr(r), r.numel(), float(depth), self._stream()))
+        self._check(self.lib.pwb_set_phase_count(self.ctx, len(maps)))
+        self._geo_nr = r.numel()
+        self._geo_key = None
+
+    def convolve_extend_batch(self, spectrum, kernel):
+        """astropy.convolution.convolve(spec, kernel, boundary='extend') for every row of
+        `spectrum` (advanced_tutorial.ipynb cell 13).  The kernel is normalised to unit sum
+        here, with numpy, as astropy does before its C loop."""
+        spectrum = self.dev(spectrum)
+        if spectrum.ndim == 1:
+            spectrum = spectrum[None, :]
+        k = np.ascontiguousarray(kernel, dtype=float).ravel()
+        if k.size % 2 == 0:
+            raise ValueError('Kernel size must be odd in all axes.')   # astropy's KernelSizeError text
+        k = k / k.sum()
+        kd = self.dev(k)
+        out = torch.empty_like(spectrum)
+        B, nw = spectrum.shape
+        self._check(self.lib.pwb_convolve_extend_batch(self.ctx, B, _ptr(spectrum), nw, _ptr(kd), k.size,
+                                                       _ptr(out), self._stream()))
+        return out
+
+    def loglike_batch(self, model, y, yerr, status=None):
+        """-0.5 * sum((y - model)^2 / yerr^2 + log(yerr^2)) per model (advanced_tutorial.ipynb
+        cell 15); -inf for failed models."""
+        model = self.dev(model)
+        B, nw = model.shape
+        y, yerr = self.dev(y).reshape(-1), self.dev(yerr).reshape(-1)
+        out = torch.empty(B, dtype=torch.float64, device=self.device)
+        self._check(self.lib.pwb_loglike_batch(self.ctx, B, _ptr(model), nw, _ptr(y), _ptr(yerr), _ptr(status),
+                                               _ptr(out), self._stream()))
+        return out
+
     def set_geometry_cached(self, intensity_0, r_from_planet, radius_profile_si):
         a, b, c = (np.ascontiguousarray(x, dtype=float) for x in
                    (intensity_0, r_from_planet, radius_profile_si))

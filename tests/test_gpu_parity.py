@@ -478,3 +478,61 @@ def test_config5_size_radiative_transfer(eng, oracle):
         # linear in the intensity map, exactly (power-of-two scaling)
         s2 = transit.radiative_transfer_2d(2.0 * i0, rm, r, n, v, w0, f, a, wl, 9E3, mass, bulk_los_velocity=-2E3)
         assert np.array_equal(s2, 2.0 * s)
+
+
+# --------------------------------------------------------------------------- SURVEY 8(f-1)
+def test_retrieval_loop_phase_mean_convolution_likelihood(built, oracle):
+    """The step around the path in every retrieval (docs/source/advanced_tutorial.ipynb cells
+    11, 13, 15): spectrum averaged over sampled transit phases with the geometric depth added,
+    Gaussian instrumental profile by astropy-style `convolve(boundary='extend')`, Gaussian
+    log-likelihood.  Own engine instance: the phase slots are per-context state."""
+    from p_winds_b200.engine import Engine
+    from p_winds_b200 import lines
+    prof = golden('he_3_profile')
+    w = lines.he_3_properties()
+    w0, f, a = np.array(w[:3]), np.array(w[3:6]), np.array([w[6]] * 3)
+    wl = np.linspace(1.0826, 1.0834, 169) * 1E-6
+    r_si, n_si, v_si = prof['r'], prof['n'], prof['v']
+    r_phys = float(r_si[0])
+    phases = np.linspace(-0.5, 0.5, 5)
+    maps = [oracle.draw_transit(0.12086, r_phys, 0.499, ph, 60, 3) for ph in phases]
+    maps = [(m[0], m[2], m[1]) for m in maps]                      # (I0, r_map, depth)
+    eng = Engine(0)
+    eng.set_geometry_phases(maps, r_si)
+    rto = Engine.rt_opts(w0, f, a, M_HE, bulk_los_velocity=-2E3)
+    scale = np.array([1.0, 0.3, 3.0])
+    T = np.array([9000., 7000., 11000.])
+    spec = eng.rt2d_batch(n_si[None, :] * scale[:, None], np.tile(v_si, (3, 1)), T, wl, rto).cpu().numpy()
+    for b in range(3):
+        ref = oracle.transmission_model(maps, r_si, n_si * scale[b], v_si, w0, f, a, wl, T[b], M_HE, v_wind=-2E3)
+        assert np.max(_rel(spec[b], ref)) < 1e-10, b
+    assert np.all(spec > 0.9) and np.all(spec <= 1.0 + 1e-12)      # depth added back: continuum at 1
+    # one phase with its depth = radiative_transfer_2d + depth
+    eng.set_geometry_phases(maps[2:3], r_si)
+    one = eng.rt2d_batch(n_si[None, :], v_si[None, :], T[:1], wl, rto).cpu().numpy()[0]
+    ref = oracle.radiative_transfer_2d(maps[2][0], maps[2][1], r_si, n_si, v_si, w0, f, a, wl, 9000., M_HE,
+                                       v_bulk=-2E3) + maps[2][2]
+    assert np.max(_rel(one, ref)) < 1e-10
+    # instrumental profile (cell 3): Gaussian sampled on the wavelength grid, odd length
+    wl_a = wl * 1e10
+    sigma_wl = 3.7 / (2 * (2 * np.log(2)) ** 0.5) / 299792.458 * np.mean(wl_a)
+    kern = 1 / sigma_wl / (2 * np.pi) ** 0.5 * np.exp(-0.5 * (wl_a - np.mean(wl_a)) ** 2 / sigma_wl ** 2)
+    conv = eng.convolve_extend_batch(spec, kern).cpu().numpy()
+    for b in range(3):
+        assert np.max(np.abs(conv[b] - oracle.convolve_extend(spec[b], kern))) < 1e-14, b
+    asym = np.linspace(0.2, 1.0, 31)                               # kernel flip matters here
+    got = eng.convolve_extend_batch(spec[0], asym).cpu().numpy()[0]
+    assert np.max(np.abs(got - oracle.convolve_extend(spec[0], asym))) < 1e-14
+    with pytest.raises(ValueError, match='Kernel size must be odd'):
+        eng.convolve_extend_batch(spec, np.ones(4))
+    # log-likelihood (cell 15), failed models -> -inf
+    rng = np.random.default_rng(2)
+    y = conv[0] + 2e-4 * rng.standard_normal(169)
+    yerr = np.full(169, 2e-4) * rng.uniform(0.8, 1.2, 169)
+    import torch
+    status = torch.tensor([0, 2, 3], dtype=torch.int32, device='cuda')
+    ll = eng.loglike_batch(conv, y, yerr, status).cpu().numpy()
+    assert abs(ll[0] / oracle.log_likelihood(conv[0], y, yerr) - 1) < 1e-12
+    assert ll[1] == -np.inf
+    assert abs(ll[2] / oracle.log_likelihood(conv[2], y, yerr) - 1) < 1e-12
+    assert ll[0] > ll[2]                                            # the true model wins

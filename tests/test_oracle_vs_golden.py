@@ -137,3 +137,19 @@ def test_oracle_matches_live_reference(oracle, sed):
     oh = oracle.he_population(R, v, rho, f_r, 1.39, T0, h, vs, rs, rhos, sed=sed,
                               initial_state=np.array([1.0, 0.0]), relax_solution=True)
     assert np.array_equal(oh['f_1'], f1) and np.array_equal(oh['f_3'], f3)
+
+
+def test_convolve_extend_definition(oracle):
+    """The oracle's restatement of astropy.convolution.convolve(boundary='extend') equals the
+    textbook convolution of the edge-padded array with the unit-sum kernel (numpy.convolve),
+    for symmetric and asymmetric odd kernels."""
+    rng = np.random.default_rng(11)
+    x = 1.0 - 0.02 * np.exp(-0.5 * ((np.arange(169) - 70) / 6.0) ** 2) + 1e-4 * rng.standard_normal(169)
+    for k in (np.exp(-0.5 * ((np.arange(169) - 84) / 2.5) ** 2), rng.uniform(0.1, 1.0, 31), np.array([1.0])):
+        ref = np.convolve(np.pad(x, k.size // 2, mode='edge'), k / k.sum(), mode='valid')
+        got = oracle.convolve_extend(x, k)
+        assert got.shape == x.shape
+        assert np.max(np.abs(got - ref)) < 2e-15
+    with pytest.raises(ValueError):
+        oracle.convolve_extend(x, np.ones(4))
+    assert abs(oracle.log_likelihood(x, x, np.full_like(x, 0.1)) + 0.5 * 169 * np.log(0.01)) < 1e-10
