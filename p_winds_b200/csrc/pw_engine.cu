@@ -297,6 +297,9 @@ k_helium(int B, HeSched sched, const int* __restrict__ order, const double* __re
          const double* __restrict__ rho, const double* __restrict__ f_h, pwb_he_opts o,
          const LsodaTables* __restrict__ tab, double* work, size_t wstride, double* f1, double* f3, double* scal,
          double* rates, int* status) {
+  __shared__ double s_e2[32];
+  s_e2[threadIdx.x] = kExp2TabDev[threadIdx.x];
+  __syncwarp();
   const int lane = threadIdx.x, warp = blockIdx.x;
   int seg = 0;
 #pragma unroll
@@ -313,6 +316,7 @@ k_helium(int B, HeSched sched, const int* __restrict__ order, const double* __re
     return;
   }
   HeParams p;
+  p.e2tab = (unsigned)__cvta_generic_to_shared(s_e2);
   p.T = T[b]; p.h_fraction = hfrac[b];
   p.vs = vs[(size_t)b * sstride]; p.rs = rs[(size_t)b * sstride]; p.rhos = rhos[(size_t)b * sstride];
   p.r_pl = o.planet_radius; p.y0[0] = o.initial_state[0]; p.y0[1] = o.initial_state[1];

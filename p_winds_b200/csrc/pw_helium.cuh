@@ -17,6 +17,7 @@ namespace pw {
 enum { PW_HE_ODEINT = 0, PW_HE_LSODA = 1, PW_HE_RK45 = 2 };
 
 struct HeParams {
+  unsigned e2tab = 0;  // device: shared-memory address of kExp2Tab (pw_exp_neg_sh)
   double T, h_fraction, vs, rs, rhos;  // per model
   double r_pl;
   double y0[2];
@@ -56,6 +57,7 @@ PW_HD_NOINLINE void he_collision(double T, double* q13, double* q31a, double* q3
 struct HeRhs {
   const double *rn, *v, *rho, *fh, *tau1, *tau3;
   const double* slope;  // [5][n]: np.interp slopes of v, rho, fh, tau1, tau3 per cell (HeWork::slope)
+  unsigned e2tab;       // device: shared-memory address of the CTA's copy of kExp2Tab
   int n;
   double lk1;         // log(k1)
   double lc[8];       // log of alpha_rec_1, alpha_rec_3, q_13, q_31a, q_31b, Q_31, Q_He, Q_He+
@@ -122,8 +124,14 @@ struct HeRhs {
     c[6] = (kc[6] * rho_) * fh_;
     c[7] = (kc[7] * rho_) * (1 - fh_);
 #endif
-    e1 = exp(-t1);
-    e3 = exp(-t3);
+    // attenuation factors e^{-tau}: table + series exp (pw_exp_neg, <= 3e-16 relative)
+#if defined(__CUDA_ARCH__)
+    e1 = pw_exp_neg_sh(-t1, e2tab);
+    e3 = pw_exp_neg_sh(-t3, e2tab);
+#else
+    e1 = pw_exp_neg(-t1, kExp2Tab);
+    e3 = pw_exp_neg(-t3, kExp2Tab);
+#endif
     vv = v_;
     rvv = PW_DIV(1., v_);
     xc = x;
@@ -333,6 +341,7 @@ PW_HD void he_population_model(const HeParams& p, const LsodaTables& tab, const 
   HeRhs rhs;
   rhs.rn = w.rn; rhs.v = v; rhs.rho = rho; rhs.fh = f_h; rhs.tau1 = w.tau1; rhs.tau3 = w.tau3;
   rhs.slope = w.slope;
+  rhs.e2tab = p.e2tab;
   rhs.n = nr;
   he_slopes(w.rn, v, nr, w.slope);
   he_slopes(w.rn, rho, nr, w.slope + nr);

@@ -536,3 +536,42 @@ def test_retrieval_loop_phase_mean_convolution_likelihood(built, oracle):
     assert ll[1] == -np.inf
     assert abs(ll[2] / oracle.log_likelihood(conv[2], y, yerr) - 1) < 1e-12
     assert ll[0] > ll[2]                                            # the true model wins
+
+
+def test_config3_share_tidal_grid_properties(eng):
+    """BASELINE configs[3] at full size for one GPU: every 8th model (one rank's interleaved share)
+    of the 256 x 256 (T0, Mdot) x 3 h_fraction grid with the tidal Parker profile -- 24 576 models
+    in one call.  No oracle can run this in seconds; check what must hold at any size: the
+    result of a model does not depend on the batch it is in (cost-ordered helium schedule, packed
+    lanes, phase slots), statuses are the reference's classes, physical bounds."""
+    T0 = np.linspace(9000, 13000, 256)
+    md = np.logspace(9.5, 12, 256)
+    hf = np.array([0.85, 0.90, 0.95])
+    HH, TT, MM = np.meshgrid(hf, T0, md, indexing='ij')
+    T, M, H = TT.ravel()[0::8].copy(), MM.ravel()[0::8].copy(), HH.ravel()[0::8].copy()
+    assert T.size == 24576
+    big = _forward(eng, T, M, H, tidal=True)
+    st = big['status']
+    assert set(np.unique(st)) <= {0, 1, 2, 3}
+    ok = (st == 0) | (st == 3)
+    assert ok.mean() > 0.98
+    assert np.isfinite(big['spectrum'][ok]).all() and np.isnan(big['spectrum'][~ok]).all()
+    sp = big['spectrum'][ok] / float(golden('geometry')['i0'].sum())
+    assert sp.max() <= 1.0 + 1e-12 and sp.min() > 0.5
+    good = st == 0
+    for k in ('f_r', 'f_1', 'f_3'):
+        assert (big[k][good] >= 0).all() and (big[k][good] <= 1.0).all(), k
+    # a scattered sub-batch (different batch size, order and lane packing) gives the same bits
+    rng = np.random.default_rng(4)
+    pick = np.sort(rng.choice(T.size, 700, replace=False))[::-1].copy()
+    small = _forward(eng, T[pick], M[pick], H[pick], tidal=True)
+    assert np.array_equal(small['status'], st[pick])
+    for k in ('f_r', 'f_1', 'f_3', 'spectrum'):
+        assert np.array_equal(small[k], big[k][pick], equal_nan=True), k
+    # absorption grows with the mass-loss rate at fixed T0, h (monotone core depth), cool end of the grid
+    TTg, MMg = np.meshgrid(T0, md, indexing='ij')
+    sel = (np.isclose(H, 0.90)) & (T == T[np.isclose(H, 0.90)][0])
+    core = big['spectrum'][sel].min(axis=1)
+    good_sel = ok[sel]
+    assert good_sel.sum() > 5
+    assert np.all(np.diff(core[good_sel]) < 1e-9)
