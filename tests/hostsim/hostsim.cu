@@ -119,6 +119,36 @@ struct VdpRhs {
   PW_HD void operator()(double, const double* y, double* d) { eval(y, d); }
 };
 
+#include "../../p_winds_b200/csrc/pw_radau.cuh"
+
+// scalar stiff test problem for the N = 1 Radau path: y' = -lam * (y - cos(t)) - sin(t)
+struct CosRhs {
+  double lam;
+  PW_HD void operator()(double t, const double* y, double* d) { d[0] = -lam * (y[0] - cos(t)) - sin(t); }
+};
+
+extern "C" {
+// counters: [nfev, njev, nlu, naccept, njac_fev]
+int hs_radau_vdp(double mu, const double* y0, const double* t, int n, double rtol, double atol, double* yout,
+                 int* counters) {
+  VdpRhs rhs{mu};
+  Rk45Opts o{rtol, atol, 0., 0.};
+  RadauStats st{0, 0, 0, 0, 0};
+  const int got = radau_solve<2>(rhs, t, n, y0, o, yout, &st);
+  counters[0] = st.nfev; counters[1] = st.njev; counters[2] = st.nlu; counters[3] = st.naccept; counters[4] = st.njac_fev;
+  return got;
+}
+int hs_radau_cos(double lam, double y0, const double* t, int n, double rtol, double atol, double* yout,
+                 int* counters) {
+  CosRhs rhs{lam};
+  Rk45Opts o{rtol, atol, 0., 0.};
+  RadauStats st{0, 0, 0, 0, 0};
+  const int got = radau_solve<1>(rhs, t, n, &y0, o, yout, &st);
+  counters[0] = st.nfev; counters[1] = st.njev; counters[2] = st.nlu; counters[3] = st.naccept; counters[4] = st.njac_fev;
+  return got;
+}
+}
+
 extern "C" {
 // stats per output point: [nst, nfe, nje, nqu, mused, hu, tcur, tsw]
 int hs_lsoda_vdp(double mu, const double* y0, const double* t, int n, double rtol, double atol, int mxstep,

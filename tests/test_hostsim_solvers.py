@@ -104,3 +104,38 @@ def test_step_selection_root(hostsim):
     # (pow(a, 1.0 / k) itself carries |ln a| * eps from the rounded exponent)
     assert np.max(np.abs(out[newton] / ref[newton] - 1)) < 2e-15
     assert np.max(np.abs(out[m] / ref[m] - 1)) < 1e-13   # exp(log(a)/k) outside it
+
+
+@pytest.mark.parametrize('mu,tend,rtol,atol', [(1.0, 20., 1e-3, 1e-6), (50.0, 100., 1e-3, 1e-6),
+                                               (1000.0, 1500., 1e-3, 1e-6), (5.0, 30., 1e-8, 1e-10)])
+def test_radau_replica_trace_two_equations(hostsim, mu, tend, rtol, atol):
+    """scipy's Radau (radau.py) restated: identical nfev / njev / nlu / step count on a stiff
+    problem whose right-hand side is pure arithmetic; values to the rounding the step
+    controller amplifies."""
+    hostsim.hs_radau_vdp.argtypes = [C.c_double, C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_double,
+                                     C.c_void_p, C.c_void_p]
+    t = np.linspace(0, tend, 80)
+    y0 = np.array([2.0, 0.0])
+    s = solve_ivp(_vdp(mu), (t[0], t[-1]), y0, t_eval=t, method='Radau', rtol=rtol, atol=atol)
+    yo = np.zeros((80, 2))
+    cnt = np.zeros(5, dtype=np.int32)
+    got = hostsim.hs_radau_vdp(mu, P(y0), P(t), 80, rtol, atol, P(yo), P(cnt))
+    assert got == len(s.t) == 80
+    assert (cnt[0], cnt[1], cnt[2]) == (s.nfev, s.njev, s.nlu)
+    assert np.max(np.abs(yo - s.y.T)) < 1e-6 * max(1.0, np.max(np.abs(s.y)))
+
+
+@pytest.mark.parametrize('lam,rtol,atol', [(1e3, 1e-3, 1e-6), (1e6, 1e-3, 1e-6), (50.0, 1e-6, 1e-9)])
+def test_radau_replica_trace_one_equation(hostsim, lam, rtol, atol):
+    hostsim.hs_radau_cos.argtypes = [C.c_double, C.c_double, C.c_void_p, C.c_int, C.c_double, C.c_double,
+                                     C.c_void_p, C.c_void_p]
+    hostsim.hs_radau_cos.restype = C.c_int
+    t = np.linspace(0, 10.0, 50)
+    s = solve_ivp(lambda tt, y: [-lam * (y[0] - np.cos(tt)) - np.sin(tt)], (0, 10.0), [0.0], t_eval=t,
+                  method='Radau', rtol=rtol, atol=atol)
+    yo = np.zeros(50)
+    cnt = np.zeros(5, dtype=np.int32)
+    got = hostsim.hs_radau_cos(lam, 0.0, P(t), 50, rtol, atol, P(yo), P(cnt))
+    assert got == len(s.t) == 50
+    assert (cnt[0], cnt[1], cnt[2]) == (s.nfev, s.njev, s.nlu)
+    assert np.max(np.abs(yo - s.y[0])) < 1e-6
