@@ -67,6 +67,20 @@ typedef struct {
   double rtol, atol, first_step, max_step;
 } pwb_he_opts;
 
+/* Options of oxygen.ion_fraction (oxygen.py:186-191). */
+enum pwb_o_method { PWB_O_RADAU = 0, PWB_O_ODEINT = 1, PWB_O_RK45 = 2 };
+typedef struct {
+  double planet_radius;
+  double o_fraction;           /* 10 ** (8.69 - 12) = solar (oxygen.py:21-22) */
+  double initial_f_o_ion;
+  int relax_solution;
+  int max_n_relax;
+  double convergence;
+  double rates[4];             /* phi_oi, a_oi, a_h_oi, a_he (oxygen.radiative_processes, oxygen.py:99) */
+  int method;                  /* enum pwb_o_method; 'Radau' is the reference default */
+  double rtol, atol, first_step, max_step;
+} pwb_o_opts;
+
 /* Options of transit.radiative_transfer_2d (transit.py:120-126). */
 typedef struct {
   int n_lines;                       /* <= 8 */
@@ -132,6 +146,18 @@ int pwb_he_population_batch(pwb_ctx* ctx, int B, const double* d_T, const double
                             const double* d_rho, const double* d_f_h, const pwb_he_opts* opts,
                             double* d_f1, double* d_f3, double* d_scal, double* d_rates,
                             int* d_status, void* stream);
+
+/* ---- oxygen.ion_fraction, batched (oxygen.py:186-491) -----------
+ * Same per-model inputs as the helium stage plus d_f_he_ion [B][Nr] = 1 - f_1 - f_3.
+ * outputs: d_f_o [B][Nr]; d_scal [B][4] = n_relax, nfev, n_solves, -; d_rates (may be NULL)
+ *          [B][5][Nr] = photoionization, recombination, e_impact_ionization,
+ *          charge_exchange_HII, charge_exchange_HI (1/s); d_status in/out as for helium
+ *          (status 2 = the RuntimeError of oxygen.py:419-433). */
+int pwb_o_ion_fraction_batch(pwb_ctx* ctx, int B, const double* d_T, const double* d_hfrac,
+                             const double* d_vs, const double* d_rs, const double* d_rhos, int sstride,
+                             const double* d_r, int Nr, const double* d_v, const double* d_rho,
+                             const double* d_f_h, const double* d_f_he_ion, const pwb_o_opts* opts,
+                             double* d_f_o, double* d_scal, double* d_rates, int* d_status, void* stream);
 
 /* ---- transit geometry (output of transit.draw_transit, transit.py:113-116) plus the
  *      radius grid of the RT call; builds the per-pixel interpolation table used by

@@ -226,5 +226,67 @@ def main():
         np.savez_compressed(os.path.join(OUT, name + '.npz'), **d)
 
 
+def oxygen_fixture(sp):
+    """tests/golden/oxygen.npz: oxygen.radiative_processes and oxygen.ion_fraction of the
+    unmodified reference on profiles from its own H / He chain."""
+    from p_winds import oxygen
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        scal = np.array(oxygen.radiative_processes(sp))
+    cases, keep = [], {}
+    for (T0, md, h) in [(9100., 10 ** 10.27, 0.9), (9100., 1e11, 0.9), (11500., 10 ** 10.5, 0.85),
+                        (13000., 10 ** 11.6, 0.9)]:
+        he_h = (1 - h) / h
+        mu_0 = (1 + 4 * he_h) / (1 + he_h)
+        f_r, mu = hydrogen.ion_fraction(R, R_PL, T0, h, md, M_PL, mu_0, spectrum_at_planet=sp,
+                                        initial_f_ion=0.0, relax_solution=True, exact_phi=True, return_mu=True)
+        vs = parker.sound_speed(T0, mu)
+        rs = parker.radius_sonic_point(M_PL, vs)
+        rhos = parker.density_sonic_point(md, rs, vs)
+        v, rho = parker.structure(R * R_PL / rs)
+        f1, f3 = helium.population_fraction(R, v, rho, f_r, R_PL, T0, h, vs, rs, rhos, spectrum_at_planet=sp,
+                                            initial_state=np.array([1.0, 0.0]), relax_solution=True)
+        f_he_ion = 1 - f1 - f3
+        for kw in (dict(), dict(relax_solution=True), dict(relax_solution=True, rtol=1e-8, atol=1e-11),
+                   dict(relax_solution=True, method='odeint')):
+            with warnings.catch_warnings():
+                warnings.simplefilter('ignore')
+                try:
+                    f_o, rates = oxygen.ion_fraction(R, v, rho, f_r, f_he_ion, R_PL, T0, h, vs, rs, rhos, sp,
+                                                     return_rates=True, **kw)
+                    status = 0
+                except RuntimeError:
+                    f_o, rates, status = np.full(len(R), np.nan), None, 2
+            # the reference's own round-off noise floor (SURVEY.md 8(c) protocol): re-run it with
+            # 1-ulp noise on the density profile; the finite-difference Jacobian of scipy's Radau
+            # turns that into a different Newton / step sequence
+            noise = 0.0
+            if status == 0:
+                rng = np.random.default_rng(17)
+                for _ in range(6):
+                    rho_p = rho * (1 + 2.2e-16 * rng.standard_normal(len(rho)))
+                    with warnings.catch_warnings():
+                        warnings.simplefilter('ignore')
+                        f_p = oxygen.ion_fraction(R, v, rho_p, f_r, f_he_ion, R_PL, T0, h, vs, rs, rhos, sp, **kw)
+                    noise = max(noise, float(np.max(np.abs(f_p[1:] / f_o[1:] - 1))))
+            cases.append(dict(T0=T0, mdot=md, h_fraction=h, vs=vs, rs=rs, rhos=rhos, v=v, rho=rho, f_h=f_r, noise=noise,
+                              f_he_ion=f_he_ion, relax=int(kw.get('relax_solution', False)),
+                              method=kw.get('method', 'Radau'), rtol=kw.get('rtol', 1e-3), atol=kw.get('atol', 1e-6),
+                              f_o=f_o, status=status,
+                              rates=np.array([rates[k] for k in ('photoionization', 'recombination',
+                                                                 'e_impact_ionization', 'charge_exchange_HII',
+                                                                 'charge_exchange_HI')])
+                              if rates is not None else np.full((5, len(R)), np.nan)))
+            print('oxygen', T0, '%.3e' % md, h, kw, 'status', status, 'f_o[-1] %.6f' % f_o[-1],
+                  'self-noise %.1e' % noise, flush=True)
+    for k in cases[0]:
+        keep[k] = np.array([c[k] for c in cases])
+    np.savez_compressed(os.path.join(OUT, 'oxygen.npz'), scalars=scal, r=R, **keep)
+
+
 if __name__ == '__main__':
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == 'oxygen':
+        oxygen_fixture(spectrum_dict())
+    else:
+        main()
+        oxygen_fixture(spectrum_dict())

@@ -717,6 +717,168 @@ def radiative_transfer_2d(i0, r_map, r, n, v, w0, f, a_ij, wl, T, mass,
 
 
 # ----------------------------------------------------------------------------
+# Oxygen: oxygen.py, microphysics.general_cross_section
+# ----------------------------------------------------------------------------
+# microphysics.sigma_properties_v1996 (microphysics.py:300-318), Verner et al. 1996:
+# E_threshold, E_max, E_0, sigma_0, y_a, p, y_w, y_0, y_1
+_VERNER = {'O I': [1.362E1, 5.380E2, 1.240E0, 1.745E3, 3.784E0, 1.764E1, 7.589E-2, 8.698E0, 1.271E-1]}
+SOLAR_OXYGEN_FRACTION = 10 ** (8.69 - 12.00)      # oxygen.py:21-22
+
+
+def general_cross_section(wl, species):
+    """microphysics.py:224-281 with the unit algebra of the astropy stand-in written out:
+    energy = (c.h * c.c / wavelength / u.angstrom).to(u.eV).value."""
+    wl = np.asarray(wl, dtype=float)
+    energy = (_H_SI * _C_SI / wl) * ((1.0 / 1e-10) / _EV_J)
+    e_thr, e_max, e_0, sigma_0, y_a, p, y_w, y_0, y_1 = _VERNER[species]
+    x = energy / e_0 - y_0
+    y = (x ** 2 + y_1 ** 2) ** 0.5
+    term1 = (x - 1) ** 2 + y_w ** 2
+    term2 = y ** (0.5 * p - 5.5)
+    term3 = (1 + (y / y_a) ** 0.5) ** (-p)
+    cs = sigma_0 * (term1 * term2 * term3) * 1E-18
+    cs = np.array(cs, dtype=float)
+    cs[energy < e_thr] = 0.0
+    return cs
+
+
+def o_radiative_processes(sed):
+    """oxygen.py:26-99 -> phi_oi, a_oi, a_h_oi, a_he."""
+    wl, flux = sed.wl, sed.flux
+    energy = (_H_SI * ((_C_SI / wl) / 1.0 * (1.0 / 1e-10 / 1.0))) * (1.0 / _EV_J)
+    energy_erg = energy * (_EV_J / 1e-7)
+    wl_break_oi = 12398.42 / _VERNER['O I'][0]
+    i0 = nearest_index(wl, 504)
+    i1 = nearest_index(wl, wl_break_oi)
+    w0, f0 = wl[:i0], flux[:i0]
+    w1, f1, e1 = wl[:i1], flux[:i1], energy_erg[:i1]
+    a_l = general_cross_section(w1, 'O I')
+    a_oi = abs(simpson(f1 * a_l, x=w1) / simpson(f1, x=w1))
+    a_h_oi = abs(simpson(f1 * sigma_h(w1), x=w1) / simpson(f1, x=w1))
+    a_he = abs(simpson(f0 * sigma_he_total(w0), x=w0) / simpson(f0, x=w0))
+    phi_oi = abs(simpson(f1 * a_l / e1, x=w1))
+    return phi_oi, a_oi, a_h_oi, a_he
+
+
+def o_electron_impact_ionization(T):
+    """oxygen.py:103-126 (Voronov 1997)."""
+    ratio = 11.3 / (8.617333262145179e-05 * T)
+    return 3.59E-8 * (0.073 + ratio) ** (-1) * ratio ** 0.34 * np.exp(-ratio)
+
+
+def o_recombination(T):
+    """oxygen.py:130-149."""
+    return 3.25E-12 * (300 / T) ** 0.66
+
+
+def o_charge_transfer(T):
+    """oxygen.py:153-182 -> (O I + H+ -> O II, O II + H -> O I)."""
+    ct_oii_h = 5.66E-10 * (300 / T) ** (-0.36) * np.exp(8.6 / T)
+    ct_oi_hp = 7.31E-10 * (300 / T) ** (-0.23) * np.exp(-226 / T)
+    return ct_oi_hp, ct_oii_h
+
+
+def o_ion_fraction(r, v, rho, f_h, f_he_ion, r_pl, T, h_fraction, vs, rs, rhos, sed=None, rates=None,
+                   o_fraction=SOLAR_OXYGEN_FRACTION, initial_f_o_ion=0.0, relax_solution=False,
+                   convergence=0.01, max_n_relax=10, method='Radau', **options):
+    """oxygen.py:186-491 -> dict(f_o=..., status=0 ok / 2 solver failed, n_relax, nfev)."""
+    alpha_unit = ((rs * 7.1492E+09) ** 2 * vs * 1E5)
+    alpha_rec = o_recombination(T) / alpha_unit
+    m_h = 1.67262192E-24 / (rhos * (rs * 7.1492E+09) ** 3)
+    phi_unit = vs * 1E5 / rs / 7.1492E+09
+    phi_oi, a_oi, a_h_oi, a_he = rates if rates is not None else o_radiative_processes(sed)
+    phi_oi = phi_oi / phi_unit
+    a_oi = a_oi / (rs * 7.1492E+09) ** 2
+    a_h_oi = a_h_oi / (rs * 7.1492E+09) ** 2
+    a_he = a_he / (rs * 7.1492E+09) ** 2
+    ion_rate = o_electron_impact_ionization(T) / alpha_unit
+    ct_oi_hp, ct_oii_h = o_charge_transfer(T)
+    ct_oii_h = ct_oii_h / alpha_unit
+    ct_oi_hp = ct_oi_hp / alpha_unit
+    rn = r * r_pl / rs
+    dr = np.diff(rn)
+    dr = np.concatenate((dr, np.array([dr[-1], ])))
+    col = np.flip(np.cumsum(np.flip(dr * rho)))
+    col_h0 = np.flip(np.cumsum(np.flip(dr * rho * (1 - f_h))))
+    he_fraction = 1 - h_fraction
+    col_he0 = np.flip(np.cumsum(np.flip(dr * rho * he_fraction * (1 - f_he_ion))))
+    den = h_fraction + 4 * he_fraction + 16 * o_fraction
+    k1, k2, k3 = h_fraction / den / m_h, he_fraction / den / m_h, o_fraction / den / m_h
+    tau_h = k1 * a_h_oi * col_h0
+    tau_he = k2 * a_he * col_he0
+    state = {'tau': (1 - initial_f_o_ion) * k3 * a_oi * col + tau_h + tau_he}
+
+    def fun(x, y):
+        f_oii = y
+        _v = np.interp(x, rn, v)
+        _rho = np.interp(x, rn, rho)
+        fh = np.interp(x, rn, f_h)
+        fhe = np.interp(x, rn, f_he_ion)
+        lt1 = np.log(k1) + np.log(_rho)
+        lt2 = np.log(k2) + np.log(_rho)
+        ion_ne = np.exp(lt1 + np.log(ion_rate)) * fh + np.exp(lt2 + np.log(ion_rate)) * fhe
+        ct1 = np.exp(lt1 + np.log(ct_oi_hp)) * fh
+        rec_ne = np.exp(lt1 + np.log(alpha_rec)) * fh + np.exp(lt2 + np.log(alpha_rec)) * fhe
+        ct2 = np.exp(lt1 + np.log(ct_oii_h)) * (1 - fh)
+        t_oi = np.interp(x, rn, state['tau'])
+        term1 = (1 - f_oii) * phi_oi * np.exp(-t_oi)
+        term2 = (1 - f_oii) * ion_ne
+        term3 = (1 - f_oii) * ct1
+        term4 = f_oii * rec_ne
+        term5 = f_oii * ct2
+        return (term1 + term2 + term3 - term4 - term5) / _v
+
+    out = {'status': 0, 'n_relax': 0, 'nfev': []}
+
+    def solve():
+        if method == 'odeint':
+            with warnings.catch_warnings():
+                warnings.filterwarnings('error')
+                try:
+                    sol = odeint(fun, y0=initial_f_o_ion, t=rn, tfirst=True)
+                except Warning:
+                    return None
+            return np.copy(sol).T[0]
+        sol = solve_ivp(fun, (rn[0], rn[-1],), np.array([initial_f_o_ion, ]), t_eval=rn, method=method,
+                        **options)
+        out['nfev'].append(sol.nfev)
+        f = sol['y'][0]
+        return f if len(f) == len(rn) else None
+
+    f = solve()
+    if f is None:
+        out['status'] = 2
+        out['f_o'] = np.full(len(rn), np.nan)
+        return out
+    f[f < 0] = 1E-15
+    f[f > 1.0] = 1.0
+    if relax_solution is True:
+        for i in range(max_n_relax):
+            prev = np.copy(f)
+            state['tau'] = k3 * a_oi * np.flip(np.cumsum(np.flip(dr * rho * (1 - f)))) + tau_h + tau_he
+            if method == 'odeint':
+                with warnings.catch_warnings():
+                    warnings.simplefilter('ignore')
+                    f = np.copy(odeint(fun, y0=initial_f_o_ion, t=rn, tfirst=True)).T[0]
+            else:
+                sol = solve_ivp(fun, (rn[0], rn[-1],), np.array([initial_f_o_ion, ]), t_eval=rn,
+                                method=method, **options)
+                out['nfev'].append(sol.nfev)
+                f = sol['y'][0]
+                if len(f) != len(rn):     # the reference would crash on the next line (shape mismatch)
+                    out['status'] = 2
+                    out['f_o'] = np.full(len(rn), np.nan)
+                    return out
+            f[f < 0] = 1E-15
+            f[f > 1.0] = 1.0
+            out['n_relax'] = i + 1
+            if abs(np.sum(f - prev)) / np.sum(prev) < convergence:
+                break
+    out['f_o'] = f
+    return out
+
+
+# ----------------------------------------------------------------------------
 # The retrieval loop around the path (docs/source/advanced_tutorial.ipynb cells
 # 11, 13, 15): phase-averaged transmission spectrum, instrumental broadening,
 # log-likelihood.  Notebook code, restated; `astropy.convolution` is absent from

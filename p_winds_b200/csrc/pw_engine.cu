@@ -29,6 +29,7 @@
 #include "pw_lsoda.cuh"
 #include "pw_hydrogen.cuh"
 #include "pw_helium.cuh"
+#include "pw_oxygen.cuh"
 #include "pw_transit.cuh"
 #include "pw_draw.cuh"
 
@@ -83,7 +84,7 @@ struct pwb_ctx {
   cudaStream_t streams[kMaxChunks] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev_start = nullptr, ev_done[kMaxChunks] = {nullptr, nullptr, nullptr, nullptr};
   // scratch
-  DevBuf h_state, h_fields, he_order, he_work, rt_ncol, rt_sums, rt_partial, rt_tau, fw_f, fw_scal, fw_he, fw_n, fw_v, fw_T, misc;
+  DevBuf h_state, h_fields, he_order, he_work, o_work, rt_ncol, rt_sums, rt_partial, rt_tau, fw_f, fw_scal, fw_he, fw_n, fw_v, fw_T, misc;
 };
 
 static int fail(pwb_ctx* c, const char* fmt, const char* a = "") {
@@ -329,6 +330,41 @@ k_helium(int B, HeSched sched, const int* __restrict__ order, const double* __re
   HeOut out{f1 + (size_t)b * nr, f3 + (size_t)b * nr, scal + (size_t)b * 4,
             rates ? rates + (size_t)b * 11 * nr : nullptr, status + b};
   he_population_model<kRk45>(p, *tab, r, v + (size_t)b * nr, rho + (size_t)b * nr, f_h + (size_t)b * nr, nr, w, out);
+}
+
+// oxygen.ion_fraction: one thread per model (Radau / LSODA / RK45 replica), `lanes` models per warp
+__global__ void __launch_bounds__(32)
+k_oxygen(int B, int lanes, const double* __restrict__ T, const double* __restrict__ hfrac,
+         const double* __restrict__ vs, const double* __restrict__ rs, const double* __restrict__ rhos,
+         int sstride, const double* __restrict__ r, int nr, const double* __restrict__ v,
+         const double* __restrict__ rho, const double* __restrict__ f_h, const double* __restrict__ f_he,
+         pwb_o_opts o, const LsodaTables* __restrict__ tab, double* work, double* f_o, double* scal,
+         double* rates, int* status) {
+  if ((int)threadIdx.x >= lanes) return;
+  const int b = blockIdx.x * lanes + threadIdx.x;
+  if (b >= B) return;
+  if (status[b] != PW_OK && status[b] != PW_WARN_HE_RELAX) {  // upstream failure: propagate NaNs
+    const double nan_ = nan("");
+    for (int i = 0; i < nr; ++i) f_o[(size_t)b * nr + i] = nan_;
+    for (int k = 0; k < 4; ++k) scal[(size_t)b * 4 + k] = 0.0;
+    return;
+  }
+  OParams p;
+  p.T = T[b]; p.h_fraction = hfrac[b];
+  p.vs = vs[(size_t)b * sstride]; p.rs = rs[(size_t)b * sstride]; p.rhos = rhos[(size_t)b * sstride];
+  p.r_pl = o.planet_radius; p.o_fraction = o.o_fraction; p.y0 = o.initial_f_o_ion;
+  p.relax = o.relax_solution; p.max_n_relax = o.max_n_relax; p.convergence = o.convergence;
+  for (int k = 0; k < 4; ++k) p.rates[k] = o.rates[k];
+  p.method = o.method; p.rtol = o.rtol; p.atol = o.atol; p.first_step = o.first_step; p.max_step = o.max_step;
+  double* wb = work + (size_t)b * kOWorkPerRadius * nr;
+  OWork w{wb, wb + nr, wb + 2 * nr, wb + 3 * nr, wb + 4 * nr, wb + 5 * nr, wb + 6 * nr};
+  OOut out{f_o + (size_t)b * nr, scal + (size_t)b * 4, rates ? rates + (size_t)b * 5 * nr : nullptr, status + b};
+  int st = PW_OK;
+  OOut out2 = out;
+  out2.status = &st;
+  o_ion_fraction_model(p, *tab, r, v + (size_t)b * nr, rho + (size_t)b * nr, f_h + (size_t)b * nr,
+                       f_he + (size_t)b * nr, nr, w, out2);
+  if (st != PW_OK) status[b] = st;  // keeps an upstream PW_WARN_HE_RELAX otherwise
 }
 
 // n [m^-3] and v [m/s] for the RT stage (quickstart.ipynb cells 10-11; SURVEY 8(d) cfg 2)
@@ -788,7 +824,7 @@ int pwb_create(int device, pwb_ctx** out) {
 void pwb_destroy(pwb_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
-  DevBuf* bufs[] = {&c->sed_gw, &c->sed_sh, &c->sed_she, &c->sed_scal, &c->lsoda_tab, &c->geo_r, &c->h_state, &c->h_fields, &c->he_order, &c->he_work, &c->rt_ncol, &c->rt_sums,
+  DevBuf* bufs[] = {&c->sed_gw, &c->sed_sh, &c->sed_she, &c->sed_scal, &c->lsoda_tab, &c->geo_r, &c->h_state, &c->h_fields, &c->he_order, &c->he_work, &c->o_work, &c->rt_ncol, &c->rt_sums,
                     &c->rt_partial, &c->rt_tau, &c->fw_f, &c->fw_scal, &c->fw_he, &c->fw_n, &c->fw_v, &c->fw_T, &c->misc};
   for (DevBuf* b : bufs) b->release();
   for (auto& G : c->geo) {
@@ -991,6 +1027,25 @@ int pwb_he_population_batch(pwb_ctx* c, int B, const double* d_T, const double* 
   return launch_helium(c, (cudaStream_t)stream, B, d_T, d_hfrac, d_vs, d_rs, d_rhos, sstride, d_r, Nr, d_v, d_rho,
                        d_f_h, o, c->he_work.as<double>(), c->he_order.as<int>(), d_f1, d_f3, d_scal, d_rates,
                        d_status);
+}
+
+int pwb_o_ion_fraction_batch(pwb_ctx* c, int B, const double* d_T, const double* d_hfrac, const double* d_vs,
+                             const double* d_rs, const double* d_rhos, int sstride, const double* d_r, int Nr,
+                             const double* d_v, const double* d_rho, const double* d_f_h,
+                             const double* d_f_he_ion, const pwb_o_opts* o, double* d_f_o, double* d_scal,
+                             double* d_rates, int* d_status, void* stream) {
+  if (!c) return -1;
+  if (B <= 0) return 0;
+  if (Nr < 2) return fail(c, "pwb_o_ion_fraction_batch: radius profile needs >= 2 points");
+  if (o->method < 0 || o->method > 2) return fail(c, "pwb_o_ion_fraction_batch: unsupported method");
+  if (c->o_work.ensure(sizeof(double) * kOWorkPerRadius * (size_t)Nr * B)) return fail(c, "out of device memory");
+  int lanes = (int)std::min<long long>(32, std::max<long long>(1, ((long long)B + 4LL * c->sm_count - 1) / (4LL * c->sm_count)));
+  k_oxygen<<<(B + lanes - 1) / lanes, 32, 0, (cudaStream_t)stream>>>(
+      B, lanes, d_T, d_hfrac, d_vs, d_rs, d_rhos, sstride, d_r, Nr, d_v, d_rho, d_f_h, d_f_he_ion, *o,
+      c->lsoda_tab.as<LsodaTables>(), c->o_work.as<double>(), d_f_o, d_scal, d_rates, d_status);
+  c->launches++;
+  PWB_CUDA(c, cudaGetLastError());
+  return 0;
 }
 
 int pwb_set_geometry_phase(pwb_ctx* c, int slot, const double* d_i0, const double* d_r_map, int npix,

@@ -92,8 +92,25 @@ enum {
   PW_SC_H_PHI = 0, PW_SC_H_A0 = 1,
   PW_SC_HE_PHI1 = 2, PW_SC_HE_PHI3 = 3, PW_SC_HE_A1 = 4, PW_SC_HE_A3 = 5,
   PW_SC_HE_AH1 = 6, PW_SC_HE_AH3 = 7,
-  PW_SC_N_H = 8, PW_SC_I1 = 9, PW_SC_I0 = 10, PW_SC_COUNT = 16
+  PW_SC_N_H = 8, PW_SC_I1 = 9, PW_SC_I0 = 10,
+  PW_SC_O_PHI = 11, PW_SC_O_A = 12, PW_SC_O_AH = 13, PW_SC_O_AHE = 14,  // oxygen.radiative_processes
+  PW_SC_COUNT = 16
 };
+
+// microphysics.general_cross_section(wavelength, 'O I') (microphysics.py:224-281; Verner et al.
+// 1996 parameters of microphysics.py:307-308): E_thr, E_max, E_0, sigma_0, y_a, p, y_w, y_0, y_1
+PW_HD double sigma_verner_oi(double wl) {
+  const double e_thr = 1.362E1, e_0 = 1.240E0, sigma_0 = 1.745E3, y_a = 3.784E0, p = 1.764E1, y_w = 7.589E-2,
+               y_0 = 8.698E0, y_1 = 1.271E-1;
+  const double energy = ((6.62607015e-34 * 299792458.0) / wl) * ((1.0 / 1e-10) / 1.602176634e-19);
+  if (energy < e_thr) return 0.0;
+  const double x = energy / e_0 - y_0;
+  const double y = sqrt(x * x + y_1 * y_1);
+  const double term1 = (x - 1) * (x - 1) + y_w * y_w;
+  const double term2 = pow(y, 0.5 * p - 5.5);
+  const double term3 = pow(1 + sqrt(y / y_a), -p);
+  return sigma_0 * (term1 * term2 * term3) * 1E-18;
+}
 
 // Block-cooperative (one CTA) setup.  `gw/s_h/s_he` must hold n doubles each,
 // scalars PW_SC_COUNT doubles, `red` 33 doubles of shared scratch (device).
@@ -162,7 +179,37 @@ PW_HD void sed_setup(const double* __restrict__ wl, const double* __restrict__ f
   const double s_fa3 = block_sum(q_fa3, red), s_f3 = block_sum(q_f3, red),
                s_phi3 = block_sum(q_phi3, red);
 
+  // ---- oxygen.radiative_processes (oxygen.py:26-99): O I cut [:io1] at 12398.42 / 13.62 A,
+  //      He cut [:io0] at 504 A
+  const int io1 = nearest_index(wl, n, 12398.42 / 1.362E1);
+  const int io0 = i1;
+  double o_f = 0, o_fa = 0, o_fah = 0, o_phi = 0;
+  for (int j = PW_TID; j < io1; j += PW_NT) {
+    const double w = simpson_weight(io1, j, X);
+    const double a = sigma_verner_oi(wl[j]);
+    const double e_ev = (6.62607015e-34 * ((299792458.0 / wl[j]) / 1.0 * (1.0 / 1e-10 / 1.0))) *
+                        (1.0 / 1.602176634e-19);
+    const double e_erg = e_ev * (1.602176634e-19 / 1e-7);
+    o_f += w * flux[j];
+    o_fa += w * (flux[j] * a);
+    o_fah += w * (flux[j] * sigma_h(wl[j]));
+    o_phi += w * (flux[j] * a / e_erg);
+  }
+  const double so_f = block_sum(o_f, red), so_fa = block_sum(o_fa, red), so_fah = block_sum(o_fah, red),
+               so_phi = block_sum(o_phi, red);
+  double o_f0 = 0, o_fahe = 0;
+  for (int j = PW_TID; j < io0; j += PW_NT) {
+    const double w = simpson_weight(io0, j, X);
+    o_f0 += w * flux[j];
+    o_fahe += w * (flux[j] * sigma_he_total(wl[j]));
+  }
+  const double so_f0 = block_sum(o_f0, red), so_fahe = block_sum(o_fahe, red);
+
   if (PW_TID == 0) {
+    scalars[PW_SC_O_PHI] = fabs(so_phi);
+    scalars[PW_SC_O_A] = fabs(so_fa / so_f);
+    scalars[PW_SC_O_AH] = fabs(so_fah / so_f);
+    scalars[PW_SC_O_AHE] = fabs(so_fahe / so_f0);
     scalars[PW_SC_H_PHI] = fabs(s_fae);
     scalars[PW_SC_H_A0] = fabs(s_fa / s_f);
     scalars[PW_SC_HE_PHI1] = fabs(s_phi1);

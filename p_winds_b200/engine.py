@@ -14,6 +14,7 @@ STATUS_MESSAGES = {
     2: 'The solver ``odeint`` failed to obtain a solution.',      # helium.py:696
 }
 HE_METHODS = {'odeint': 0, 'LSODA': 1, 'RK45': 2}
+O_METHODS = {'Radau': 0, 'odeint': 1, 'RK45': 2}
 LD_LAWS = {None: 0, 'linear': 1, 'quadratic': 2, 'square-root': 3, 'log': 4, 'exp': 5,
            's3': 6, 'c4': 7}
 
@@ -91,7 +92,8 @@ class Engine:
         v = list(out)
         return {'h_phi': v[0], 'h_a0': v[1], 'he_phi_1': v[2], 'he_phi_3': v[3], 'he_a_1': v[4],
                 'he_a_3': v[5], 'he_a_h_1': v[6], 'he_a_h_3': v[7], 'n_cut_h': int(v[8]),
-                'i1': int(v[9]), 'i0': int(v[10])}
+                'i1': int(v[9]), 'i0': int(v[10]), 'o_phi': v[11], 'o_a': v[12], 'o_a_h': v[13],
+                'o_a_he': v[14]}
 
     # ------------------------------------------------------------------- parker
     def parker_structure(self, r):
@@ -165,6 +167,37 @@ class Engine:
             _ptr(rho), _ptr(f_h), C.byref(opts), _ptr(f1), _ptr(f3), _ptr(scal), _ptr(rates),
             _ptr(status), self._stream()))
         return {'f_1': f1, 'f_3': f3, 'scal': scal, 'rates': rates, 'status': status}
+
+    # ------------------------------------------------------------------- oxygen
+    @staticmethod
+    def o_opts(planet_radius, rates, o_fraction=10 ** (8.69 - 12.00), initial_f_o_ion=0.0,
+               relax_solution=False, convergence=0.01, max_n_relax=10, method='Radau', rtol=1e-3,
+               atol=1e-6, first_step=None, max_step=None):
+        if method not in O_METHODS:
+            raise ValueError("method %r is not available on the GPU path (supported: 'Radau', 'odeint', "
+                             "'RK45'); there is no CPU fallback" % (method,))
+        return _lib.OOpts(float(planet_radius), float(o_fraction), float(initial_f_o_ion),
+                          int(bool(relax_solution)), int(max_n_relax), float(convergence),
+                          (C.c_double * 4)(*[float(x) for x in rates]), O_METHODS[method], float(rtol),
+                          float(atol), float(first_step) if first_step else 0.0,
+                          float(max_step) if (max_step and np.isfinite(max_step)) else 0.0)
+
+    def o_ion_fraction_batch(self, T, h_fraction, vs, rs, rhos, r, v, rho, f_h, f_he_ion, opts,
+                             return_rates=False, status=None):
+        """oxygen.ion_fraction for B models (oxygen.py:186-491)."""
+        T, hf, vs, rs, rhos, r = (self.dev(x).reshape(-1) for x in (T, h_fraction, vs, rs, rhos, r))
+        B, nr = T.numel(), r.numel()
+        v, rho, f_h, f_he = (self.dev(x).reshape(B, nr) for x in (v, rho, f_h, f_he_ion))
+        f_o = torch.empty((B, nr), dtype=torch.float64, device=self.device)
+        scal = torch.empty((B, 4), dtype=torch.float64, device=self.device)
+        rates = torch.empty((B, 5, nr), dtype=torch.float64, device=self.device) if return_rates else None
+        if status is None:
+            status = torch.zeros(B, dtype=torch.int32, device=self.device)
+        self._check(self.lib.pwb_o_ion_fraction_batch(
+            self.ctx, B, _ptr(T), _ptr(hf), _ptr(vs), _ptr(rs), _ptr(rhos), 1, _ptr(r), nr, _ptr(v),
+            _ptr(rho), _ptr(f_h), _ptr(f_he), C.byref(opts), _ptr(f_o), _ptr(scal), _ptr(rates),
+            _ptr(status), self._stream()))
+        return {'f_o': f_o, 'scal': scal, 'rates': rates, 'status': status}
 
     # ------------------------------------------------------------------ transit
     def set_geometry(self, intensity_0, r_from_planet, radius_profile_si):

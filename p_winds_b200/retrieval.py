@@ -1,7 +1,7 @@
 """The retrieval loop of docs/source/advanced_tutorial.ipynb for a whole parameter grid.
 
 The notebook evaluates one `theta = (log_m_dot, log_T, v_wind)` per call of
-`cascading_model` / `log_likelihood` (cells 9-15) inside `scipy.optimize.minimize`; a
+`cascading_model` / `log_likelihood` (cells 9-15) inside a Nelder-Mead minimisation; a
 grid search or an MCMC ensemble evaluates thousands of them per step.  These functions
 keep the notebook's names and argument meaning and take arrays of models instead.
 Everything runs in the CUDA engine (no CPU fallback).

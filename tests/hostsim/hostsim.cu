@@ -179,6 +179,33 @@ int hs_rk45_vdp(double mu, const double* y0, const double* t, int n, double rtol
 }
 }
 
+#include "../../p_winds_b200/csrc/pw_oxygen.cuh"
+
+extern "C" {
+// model: [T, h_fraction, vs, rs, rhos]; opts: [r_pl, o_fraction, y0, relax, max_n_relax, convergence,
+//   method, rtol, atol, first_step, max_step]; rates[4]
+int hs_o_ion_fraction(const double* model, const double* opts, const double* rates, const double* r,
+                      const double* v, const double* rho, const double* f_h, const double* f_he, int nr,
+                      double* f_o, double* scal, double* rates_out) {
+  static LsodaTables tab;
+  static bool init = false;
+  if (!init) { lsoda_tables_init(&tab); init = true; }
+  OParams p;
+  p.T = model[0]; p.h_fraction = model[1]; p.vs = model[2]; p.rs = model[3]; p.rhos = model[4];
+  p.r_pl = opts[0]; p.o_fraction = opts[1]; p.y0 = opts[2]; p.relax = (int)opts[3];
+  p.max_n_relax = (int)opts[4]; p.convergence = opts[5]; p.method = (int)opts[6];
+  p.rtol = opts[7]; p.atol = opts[8]; p.first_step = opts[9]; p.max_step = opts[10];
+  for (int i = 0; i < 4; ++i) p.rates[i] = rates[i];
+  std::vector<double> buf(kOWorkPerRadius * nr);
+  double* b = buf.data();
+  OWork w{b, b + nr, b + 2 * nr, b + 3 * nr, b + 4 * nr, b + 5 * nr, b + 6 * nr};
+  int status = 0;
+  OOut o{f_o, scal, rates_out, &status};
+  o_ion_fraction_model(p, tab, r, v, rho, f_h, f_he, nr, w, o);
+  return status;
+}
+}
+
 #include "../../p_winds_b200/csrc/pw_transit.cuh"
 
 extern "C" {

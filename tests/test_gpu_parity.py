@@ -571,3 +571,54 @@ def test_config3_share_tidal_grid_properties(eng):
     assert np.array_equal(small['status'], st[pick])
     for k in ('f_r', 'f_1', 'f_3', 'spectrum'):
         assert np.array_equal(small[k], big[k][pick], equal_nan=True), k
+
+
+# --------------------------------------------------------------------------- SURVEY 8(f-3)
+def test_oxygen_reference_signature_and_batch(eng, oracle, sed):
+    """oxygen.ion_fraction on the GPU (k_oxygen: Radau / LSODA replicas) against the unmodified
+    reference (tests/golden/oxygen.npz): scalars of oxygen.radiative_processes to 1e-10, ion
+    fractions inside the reference's own 1-ulp noise envelope (fixture key `noise`; see
+    tests/test_hostsim_stages.py::_oxygen_tolerance), exceptions and return arity."""
+    from p_winds_b200 import oxygen
+    from p_winds_b200.engine import Engine
+    d = golden('oxygen')
+    g = golden('solar_sed')
+    sp = {'wavelength': g['wavelength'], 'flux_lambda': g['flux_lambda'], 'wavelength_unit': 'angstrom',
+          'flux_unit': 'erg / (s cm2 angstrom)'}
+    scal = np.array(oxygen.radiative_processes(sp))
+    assert np.max(_rel(scal, d['scalars'])) < 1e-10
+    for T in (7000., 9100., 12000.):
+        assert oxygen.electron_impact_ionization(T) == oracle.o_electron_impact_ionization(T)
+        assert oxygen.recombination(T) == oracle.o_recombination(T)
+        assert oxygen.charge_transfer(T) == oracle.o_charge_transfer(T)
+    for i in range(len(d['T0'])):
+        kw = dict(relax_solution=bool(d['relax'][i]))
+        if str(d['method'][i]) == 'odeint':
+            kw['method'] = 'odeint'
+        else:
+            kw.update(rtol=float(d['rtol'][i]), atol=float(d['atol'][i]))
+        f, rates = oxygen.ion_fraction(d['r'], d['v'][i], d['rho'][i], d['f_h'][i], d['f_he_ion'][i], 1.39,
+                                       float(d['T0'][i]), float(d['h_fraction'][i]), float(d['vs'][i]),
+                                       float(d['rs'][i]), float(d['rhos'][i]), sp, return_rates=True, **kw)
+        tol = 4.0 * float(d['noise'][i]) + 1e-6
+        err = np.max(_rel(f[1:], d['f_o'][i][1:]))
+        assert err < tol, (i, err, tol)
+        assert set(rates) == {'photoionization', 'recombination', 'e_impact_ionization', 'charge_exchange_HII',
+                              'charge_exchange_HI'}
+    # the whole fixture as one batch, plus a model that starts from a failed upstream stage
+    sel = [i for i in range(len(d['T0'])) if str(d['method'][i]) == 'Radau' and d['relax'][i] and d['rtol'][i] > 1e-6]
+    import torch
+    status = torch.zeros(len(sel), dtype=torch.int32, device='cuda')
+    status[1] = 1
+    opts = Engine.o_opts(1.39, scal, relax_solution=True)
+    o = eng.o_ion_fraction_batch(d['T0'][sel], d['h_fraction'][sel], d['vs'][sel], d['rs'][sel], d['rhos'][sel],
+                                 d['r'], d['v'][sel], d['rho'][sel], d['f_h'][sel], d['f_he_ion'][sel], opts,
+                                 status=status)
+    fo = o['f_o'].cpu().numpy()
+    assert np.isnan(fo[1]).all() and o['status'].cpu().numpy().tolist() == [0, 1, 0, 0]
+    for k, i in enumerate(sel):
+        if k != 1:
+            assert np.max(_rel(fo[k][1:], d['f_o'][i][1:])) < 4.0 * float(d['noise'][i]) + 1e-6
+    with pytest.raises(ValueError, match='not available on the GPU path'):
+        oxygen.ion_fraction(d['r'], d['v'][0], d['rho'][0], d['f_h'][0], d['f_he_ion'][0], 1.39, 9100., 0.9,
+                            float(d['vs'][0]), float(d['rs'][0]), float(d['rhos'][0]), sp, method='BDF')

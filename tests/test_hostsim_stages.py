@@ -251,3 +251,49 @@ def test_exp_neg(hostsim):
     assert np.max(np.abs(out[live] / ref[live] - 1)) < 3e-16
     assert np.all(out[~live] == 0.0)
     assert out[0 + 400000] == 1.0
+
+
+def _oxygen_tolerance(d, i):
+    """The reference's oxygen.ion_fraction is reproducible only to its round-off noise floor:
+    scipy's Radau builds its Jacobian by finite differences, which turns 1-ulp input noise into
+    another Newton / step sequence (fixture key `noise`: largest relative change of f_o over
+    six 1-ulp-perturbed runs of the unmodified reference, 2e-4 .. 3e-3 for Radau at any rtol,
+    <= 1e-5 for odeint).  Tolerance = 4 x that floor + 1e-6 (SURVEY.md 8(c) P3 protocol)."""
+    return 4.0 * float(d['noise'][i]) + 1e-6
+
+
+def test_oxygen_stage_against_reference(hostsim, oracle, sed):
+    """o_ion_fraction_model (Radau / odeint replicas) on the host build against the
+    unmodified reference's oxygen.ion_fraction (tests/golden/oxygen.npz) -- same relax-loop
+    outcome, right-hand-side count within the reference's own scatter, values inside its
+    noise envelope.  (Step-for-step identity of the Radau replica itself is shown on
+    pure-arithmetic problems in tests/test_hostsim_solvers.py.)"""
+    d = golden('oxygen')
+    rates = np.ascontiguousarray(d['scalars'])
+    meth = {'Radau': 0, 'odeint': 1}
+    for i in range(len(d['T0'])):
+        model = np.array([d['T0'][i], d['h_fraction'][i], d['vs'][i], d['rs'][i], d['rhos'][i]], dtype=float)
+        opts = np.array([1.39, 10 ** (8.69 - 12.00), 0.0, d['relax'][i], 10, 0.01, meth[str(d['method'][i])],
+                         d['rtol'][i], d['atol'][i], 0., 0.], dtype=float)
+        f, scal, rr = np.zeros(100), np.zeros(4), np.zeros((5, 100))
+        st = hostsim.hs_o_ion_fraction(P(model), P(opts), P(rates), P(np.ascontiguousarray(d['r'])),
+                                       P(np.ascontiguousarray(d['v'][i])), P(np.ascontiguousarray(d['rho'][i])),
+                                       P(np.ascontiguousarray(d['f_h'][i])), P(np.ascontiguousarray(d['f_he_ion'][i])),
+                                       100, P(f), P(scal), P(rr))
+        assert st == d['status'][i] == 0
+        tol = _oxygen_tolerance(d, i)
+        err = np.max(np.abs(f[1:] / d['f_o'][i][1:] - 1))
+        assert err < tol, (i, err, tol)
+        # the rates multiply (1 - f) or f: compare where neither factor is lost to cancellation
+        m = (d['f_o'][i] > 1e-3) & (d['f_o'][i] < 0.99)
+        m[0] = False
+        if m.any():
+            assert np.max(np.abs(rr[:, m] / d['rates'][i][:, m] - 1)) < 100 * tol
+        if str(d['method'][i]) == 'Radau':
+            kw = dict(rtol=float(d['rtol'][i]), atol=float(d['atol'][i]))
+            o = oracle.o_ion_fraction(d['r'], d['v'][i], d['rho'][i], d['f_h'][i], d['f_he_ion'][i], 1.39,
+                                      float(d['T0'][i]), float(d['h_fraction'][i]), float(d['vs'][i]),
+                                      float(d['rs'][i]), float(d['rhos'][i]), sed=sed,
+                                      relax_solution=bool(d['relax'][i]), **kw)
+            assert int(scal[0]) == o['n_relax']
+            assert abs(scal[1] / sum(o['nfev']) - 1) < 0.12     # the reference's own nfev scatters by +-5 %

@@ -153,3 +153,18 @@ def test_convolve_extend_definition(oracle):
     with pytest.raises(ValueError):
         oracle.convolve_extend(x, np.ones(4))
     assert abs(oracle.log_likelihood(x, x, np.full_like(x, 0.1)) + 0.5 * 169 * np.log(0.01)) < 1e-10
+
+
+def test_oxygen_oracle_matches_reference(oracle, sed):
+    """SURVEY 8(f-3), oxygen: scalars and ion fractions of the unmodified reference
+    (tests/golden/oxygen.npz, made by oracle/make_golden.py) -- bit for bit."""
+    d = golden('oxygen')
+    assert np.array_equal(np.array(oracle.o_radiative_processes(sed)), d['scalars'])
+    for i in range(len(d['T0'])):
+        kw = {} if d['method'][i] == 'odeint' else dict(rtol=float(d['rtol'][i]), atol=float(d['atol'][i]))
+        o = oracle.o_ion_fraction(d['r'], d['v'][i], d['rho'][i], d['f_h'][i], d['f_he_ion'][i], 1.39,
+                                  float(d['T0'][i]), float(d['h_fraction'][i]), float(d['vs'][i]), float(d['rs'][i]),
+                                  float(d['rhos'][i]), sed=sed, relax_solution=bool(d['relax'][i]),
+                                  method=str(d['method'][i]), **kw)
+        assert o['status'] == d['status'][i]
+        assert np.array_equal(o['f_o'], d['f_o'][i]), i
