@@ -81,6 +81,20 @@ typedef struct {
   double rtol, atol, first_step, max_step;
 } pwb_o_opts;
 
+/* Options of carbon.ion_fraction (carbon.py:256-262). */
+enum pwb_c_method { PWB_C_ODEINT = 0, PWB_C_RADAU = 1, PWB_C_RK45 = 2 };
+typedef struct {
+  double planet_radius;
+  double c_fraction;           /* 10 ** (8.43 - 12) = solar (carbon.py:21-22) */
+  double initial_f_c_ion[2];
+  int relax_solution;
+  int max_n_relax;
+  double convergence;
+  double rates[7];             /* phi_ci, phi_cii, a_ci, a_cii, a_h_ci, a_h_cii, a_he (carbon.py:131) */
+  int method;                  /* enum pwb_c_method; 'odeint' is the reference default */
+  double rtol, atol, first_step, max_step;
+} pwb_c_opts;
+
 /* Options of transit.radiative_transfer_2d (transit.py:120-126). */
 typedef struct {
   int n_lines;                       /* <= 8 */
@@ -113,8 +127,10 @@ int pwb_n_active_pixels(pwb_ctx* ctx);
  *      and helium.radiative_processes (helium.py:24-154).
  *      d_wavelength [angstrom], d_flux [erg s-1 cm-2 A-1], device pointers. */
 int pwb_set_sed(pwb_ctx* ctx, const double* d_wavelength, const double* d_flux, int n, void* stream);
-/* host out[16]: phi_H, a_0, phi_1, phi_3, a_1, a_3, a_h_1, a_h_3, n_cut_H, i1, i0 */
-int pwb_get_sed_scalars(pwb_ctx* ctx, double* out16);
+/* host out[32]: phi_H, a_0, phi_1, phi_3, a_1, a_3, a_h_1, a_h_3, n_cut_H, i1, i0,
+ *      [11..14] oxygen.radiative_processes (phi_oi, a_oi, a_h_oi, a_he; oxygen.py:99),
+ *      [16..22] carbon.radiative_processes (phi_ci, phi_cii, a_ci, a_cii, a_h_ci, a_h_cii, a_he; carbon.py:131) */
+int pwb_get_sed_scalars(pwb_ctx* ctx, double* out32);
 
 /* ---- parker.structure (parker.py:163-223) / structure_tidal (:271-358) --------- */
 int pwb_parker_structure(pwb_ctx* ctx, const double* d_r, int n, double* d_v, double* d_rho, void* stream);
@@ -158,6 +174,17 @@ int pwb_o_ion_fraction_batch(pwb_ctx* ctx, int B, const double* d_T, const doubl
                              const double* d_r, int Nr, const double* d_v, const double* d_rho,
                              const double* d_f_h, const double* d_f_he_ion, const pwb_o_opts* opts,
                              double* d_f_o, double* d_scal, double* d_rates, int* d_status, void* stream);
+
+/* ---- carbon.ion_fraction, batched (carbon.py:256-639) -------------
+ * outputs: d_f_cii, d_f_ciii [B][Nr]; d_scal [B][4] = n_relax, nfev, n_solves, -; d_rates (may be
+ *          NULL) [B][11][Nr] in the order of carbon.py:531-533; status 2 = the RuntimeError
+ *          of carbon.py:541-557 (the default 'odeint' gives up on dense winds). */
+int pwb_c_ion_fraction_batch(pwb_ctx* ctx, int B, const double* d_T, const double* d_hfrac,
+                             const double* d_vs, const double* d_rs, const double* d_rhos, int sstride,
+                             const double* d_r, int Nr, const double* d_v, const double* d_rho,
+                             const double* d_f_h, const double* d_f_he_ion, const pwb_c_opts* opts,
+                             double* d_f_cii, double* d_f_ciii, double* d_scal, double* d_rates,
+                             int* d_status, void* stream);
 
 /* ---- transit geometry (output of transit.draw_transit, transit.py:113-116) plus the
  *      radius grid of the RT call; builds the per-pixel interpolation table used by

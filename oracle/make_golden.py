@@ -284,9 +284,75 @@ def oxygen_fixture(sp):
     np.savez_compressed(os.path.join(OUT, 'oxygen.npz'), scalars=scal, r=R, **keep)
 
 
+def carbon_fixture(sp):
+    """tests/golden/carbon.npz: carbon.radiative_processes and carbon.ion_fraction of the
+    unmodified reference (default 'odeint' -- which gives up on some of these models, as SURVEY.md
+    8(f-3) notes -- and 'Radau', the method docs/source/exospheric_metals.ipynb uses)."""
+    from p_winds import carbon
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        scal = np.array(carbon.radiative_processes(sp))
+    cases, keep = [], {}
+    keys = ('ionization_CI', 'ionization_CII', 'recombination_CII', 'recombination_CIII', 'e_impact_ion_CI',
+            'e_impact_ion_CII', 'charge_exchange_CI_HII', 'charge_exchange_CI_HeII', 'charge_exchange_CII_HI',
+            'charge_exchange_CIII_HI', 'charge_exchange_CIII_HeI')
+    for (T0, md, h) in [(9100., 10 ** 10.27, 0.9), (9100., 1e11, 0.9), (11500., 10 ** 10.5, 0.85)]:
+        he_h = (1 - h) / h
+        mu_0 = (1 + 4 * he_h) / (1 + he_h)
+        f_r, mu = hydrogen.ion_fraction(R, R_PL, T0, h, md, M_PL, mu_0, spectrum_at_planet=sp,
+                                        initial_f_ion=0.0, relax_solution=True, exact_phi=True, return_mu=True)
+        vs = parker.sound_speed(T0, mu)
+        rs = parker.radius_sonic_point(M_PL, vs)
+        rhos = parker.density_sonic_point(md, rs, vs)
+        v, rho = parker.structure(R * R_PL / rs)
+        f1, f3 = helium.population_fraction(R, v, rho, f_r, R_PL, T0, h, vs, rs, rhos, spectrum_at_planet=sp,
+                                            initial_state=np.array([1.0, 0.0]), relax_solution=True)
+        f_he_ion = 1 - f1 - f3
+        for kw in (dict(), dict(relax_solution=True), dict(method='Radau'), dict(method='Radau', relax_solution=True),
+                   dict(method='Radau', relax_solution=True, rtol=1e-8, atol=1e-11)):
+            def run(rho_in):
+                with warnings.catch_warnings():
+                    warnings.simplefilter('ignore')
+                    return carbon.ion_fraction(R, v, rho_in, f_r, f_he_ion, R_PL, T0, h, vs, rs, rhos, sp,
+                                               return_rates=True, **kw)
+            try:
+                f2, f3c, rates = run(rho)
+                status = 0
+            except RuntimeError:
+                f2, f3c, rates, status = np.full(len(R), np.nan), np.full(len(R), np.nan), None, 2
+            # noise floor of the reference under 1-ulp input noise: C II everywhere; C III where it
+            # is within a factor 100 of its peak (below that it sits at the solver's atol)
+            noise, noise3 = 0.0, 0.0
+            if status == 0:
+                rng = np.random.default_rng(17)
+                for _ in range(6):
+                    try:
+                        g2, g3, _r = run(rho * (1 + 2.2e-16 * rng.standard_normal(len(rho))))
+                    except RuntimeError:
+                        noise = noise3 = np.inf
+                        continue
+                    big = f3c > 1e-2 * f3c.max()
+                    noise = max(noise, float(np.max(np.abs(g2[1:] / f2[1:] - 1))))
+                    noise3 = max(noise3, float(np.max(np.abs(g3[big] / f3c[big] - 1))))
+            cases.append(dict(T0=T0, mdot=md, h_fraction=h, vs=vs, rs=rs, rhos=rhos, v=v, rho=rho, f_h=f_r,
+                              f_he_ion=f_he_ion, relax=int(kw.get('relax_solution', False)),
+                              method=kw.get('method', 'odeint'), rtol=kw.get('rtol', 1e-3), atol=kw.get('atol', 1e-6),
+                              f_cii=f2, f_ciii=f3c, status=status, noise=noise, noise3=noise3,
+                              rates=np.array([rates[k] for k in keys]) if rates is not None
+                              else np.full((11, len(R)), np.nan)))
+            print('carbon', T0, '%.3e' % md, h, kw, 'status', status, 'f_cii[-1] %.6f' % f2[-1],
+                  'self-noise %.1e / %.1e' % (noise, noise3), 'max f_ciii %.2e' % np.nanmax(f3c), flush=True)
+    for k in cases[0]:
+        keep[k] = np.array([c[k] for c in cases])
+    np.savez_compressed(os.path.join(OUT, 'carbon.npz'), scalars=scal, r=R, **keep)
+
+
 if __name__ == '__main__':
-    if len(sys.argv) > 1 and sys.argv[1] == 'oxygen':
+    if len(sys.argv) > 1 and sys.argv[1] == 'carbon':
+        carbon_fixture(spectrum_dict())
+    elif len(sys.argv) > 1 and sys.argv[1] == 'oxygen':
         oxygen_fixture(spectrum_dict())
     else:
         main()
         oxygen_fixture(spectrum_dict())
+        carbon_fixture(spectrum_dict())

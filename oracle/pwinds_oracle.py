@@ -721,7 +721,9 @@ def radiative_transfer_2d(i0, r_map, r, n, v, w0, f, a_ij, wl, T, mass,
 # ----------------------------------------------------------------------------
 # microphysics.sigma_properties_v1996 (microphysics.py:300-318), Verner et al. 1996:
 # E_threshold, E_max, E_0, sigma_0, y_a, p, y_w, y_0, y_1
-_VERNER = {'O I': [1.362E1, 5.380E2, 1.240E0, 1.745E3, 3.784E0, 1.764E1, 7.589E-2, 8.698E0, 1.271E-1]}
+_VERNER = {'C I': [1.126E1, 2.910E2, 2.144E0, 5.027E2, 6.126E1, 5.101E0, 9.157E-2, 1.133E0, 1.607E0],
+           'C II': [2.438E1, 3.076E2, 4.058E-1, 8.709E0, 1.261E2, 8.578E0, 2.093E0, 4.929E1, 3.234E0],
+           'O I': [1.362E1, 5.380E2, 1.240E0, 1.745E3, 3.784E0, 1.764E1, 7.589E-2, 8.698E0, 1.271E-1]}
 SOLAR_OXYGEN_FRACTION = 10 ** (8.69 - 12.00)      # oxygen.py:21-22
 
 
@@ -875,6 +877,181 @@ def o_ion_fraction(r, v, rho, f_h, f_he_ion, r_pl, T, h_fraction, vs, rs, rhos, 
             if abs(np.sum(f - prev)) / np.sum(prev) < convergence:
                 break
     out['f_o'] = f
+    return out
+
+
+# ----------------------------------------------------------------------------
+# Carbon: carbon.py
+# ----------------------------------------------------------------------------
+SOLAR_CARBON_FRACTION = 10 ** (8.43 - 12.00)      # carbon.py:21-22
+
+
+def c_radiative_processes(sed):
+    """carbon.py:30-131 -> phi_ci, phi_cii, a_ci, a_cii, a_h_ci, a_h_cii, a_he."""
+    wl, flux = sed.wl, sed.flux
+    energy = (_H_SI * ((_C_SI / wl) / 1.0 * (1.0 / 1e-10 / 1.0))) * (1.0 / _EV_J)
+    energy_erg = energy * (_EV_J / 1e-7)
+    i0 = nearest_index(wl, 504)
+    i1 = nearest_index(wl, 12398.42 / _VERNER['C I'][0])
+    i2 = nearest_index(wl, 12398.42 / _VERNER['C II'][0])
+    w0, f0 = wl[:i0], flux[:i0]
+    w1, f1, e1 = wl[:i1], flux[:i1], energy_erg[:i1]
+    w2, f2, e2 = wl[:i2], flux[:i2], energy_erg[:i2]
+    a_l1 = general_cross_section(w1, 'C I')
+    a_l2 = general_cross_section(w2, 'C II')
+    a_ci = abs(simpson(f1 * a_l1, x=w1) / simpson(f1, x=w1))
+    a_cii = abs(simpson(f2 * a_l2, x=w2) / simpson(f2, x=w2))
+    a_h_ci = abs(simpson(f1 * sigma_h(w1), x=w1) / simpson(f1, x=w1))
+    a_h_cii = abs(simpson(f2 * sigma_h(w2), x=w2) / simpson(f2, x=w2))
+    a_he = abs(simpson(f0 * sigma_he_total(w0), x=w0) / simpson(f0, x=w0))
+    phi_ci = abs(simpson(f1 * a_l1 / e1, x=w1))
+    phi_cii = abs(simpson(f2 * a_l2 / e2, x=w2))
+    return phi_ci, phi_cii, a_ci, a_cii, a_h_ci, a_h_cii, a_he
+
+
+def c_electron_impact_ionization(T):
+    """carbon.py:135-165 (Voronov 1997)."""
+    e = 8.617333262145179e-05 * T
+    r1, r2 = 11.3 / e, 24.4 / e
+    return (6.85E-8 * (0.193 + r1) ** (-1) * r1 ** 0.25 * np.exp(-r1),
+            1.86E-8 * (0.286 + r2) ** (-1) * r2 ** 0.24 * np.exp(-r2))
+
+
+def c_recombination(T):
+    """carbon.py:169-194."""
+    return 4.67E-12 * (300 / T) ** 0.60, 2.3E-12 * (1000 / T) ** 0.645
+
+
+def c_charge_transfer(T):
+    """carbon.py:198-252 -> ct_ci_hp, ct_cii_h, ct_ci_hep, ct_cii_sii, ct_ciii_h, ct_ciii_he."""
+    ct_cii_h = 6.30E-17 * (300 / T) ** (-1.96) * np.exp(-1.7E5 / T)
+    ct_cii_sii = 2.1E-9
+    ct_ci_hp = 1.31E-15 * (300 / T) ** (-0.213)
+    ct_ci_hep = 2.5E-15 * (300 / T) ** (-1.597)
+    ct_ciii_h = 1.67E-4 * (T / 10000) ** 2.79 * (1 + 304.72 * np.exp(-4.07 * T / 10000))
+    ct_ciii_he = 1.23E-9
+    return ct_ci_hp, ct_cii_h, ct_ci_hep, ct_cii_sii, ct_ciii_h, ct_ciii_he
+
+
+def c_ion_fraction(r, v, rho, f_h, f_he_ion, r_pl, T, h_fraction, vs, rs, rhos, sed=None, rates=None,
+                   c_fraction=SOLAR_CARBON_FRACTION, initial_f_c_ion=np.array([0.0, 0.0]),
+                   relax_solution=False, convergence=0.01, max_n_relax=10, method='odeint', **options):
+    """carbon.py:256-639 -> dict(f_cii, f_ciii, status=0 ok / 2 solver failed, n_relax, nfev)."""
+    alpha_unit = ((rs * 7.1492E+09) ** 2 * vs * 1E5)
+    rec_ci, rec_cii = c_recombination(T)
+    rec_ci, rec_cii = rec_ci / alpha_unit, rec_cii / alpha_unit
+    m_h = 1.67262192E-24 / (rhos * (rs * 7.1492E+09) ** 3)
+    phi_unit = vs * 1E5 / rs / 7.1492E+09
+    phi_ci, phi_cii, a_ci, a_cii, a_h_ci, a_h_cii, a_he = rates if rates is not None else c_radiative_processes(sed)
+    phi_ci, phi_cii = phi_ci / phi_unit, phi_cii / phi_unit
+    a_ci = a_ci / (rs * 7.1492E+09) ** 2
+    a_h_ci = a_h_ci / (rs * 7.1492E+09) ** 2
+    a_cii = a_cii / (rs * 7.1492E+09) ** 2
+    a_h_cii = a_h_cii / (rs * 7.1492E+09) ** 2
+    a_he = a_he / (rs * 7.1492E+09) ** 2
+    ion_ci, ion_cii = c_electron_impact_ionization(T)
+    ion_ci, ion_cii = ion_ci / alpha_unit, ion_cii / alpha_unit
+    ct_ci_hp, ct_cii_h, ct_ci_hep, _, ct_ciii_h, ct_ciii_he = c_charge_transfer(T)
+    ct_cii_h, ct_ci_hp, ct_ci_hep = ct_cii_h / alpha_unit, ct_ci_hp / alpha_unit, ct_ci_hep / alpha_unit
+    ct_ciii_h, ct_ciii_he = ct_ciii_h / alpha_unit, ct_ciii_he / alpha_unit
+    rn = r * r_pl / rs
+    dr = np.diff(rn)
+    dr = np.concatenate((dr, np.array([dr[-1], ])))
+    col = np.flip(np.cumsum(np.flip(dr * rho)))
+    col_h0 = np.flip(np.cumsum(np.flip(dr * rho * (1 - f_h))))
+    he_fraction = 1 - h_fraction
+    col_he0 = np.flip(np.cumsum(np.flip(dr * rho * he_fraction * (1 - f_he_ion))))
+    den = h_fraction + 4 * he_fraction + 12 * c_fraction
+    k1, k2, k3 = h_fraction / den / m_h, he_fraction / den / m_h, c_fraction / den / m_h
+    tau_ci_h = k1 * a_h_ci * col_h0
+    tau_cii_h = k1 * a_h_cii * col_h0
+    tau_c_he = k2 * a_he * col_he0
+    y0 = np.asarray(initial_f_c_ion, dtype=float)
+    st = {'t1': (1 - y0[0] - y0[1]) * k3 * a_ci * col + tau_ci_h + tau_c_he,
+          't2': y0[0] * k3 * a_cii * col + tau_cii_h + tau_c_he}
+
+    def fun(x, y):
+        f2, f3 = y[0], y[1]
+        _v = np.interp(x, rn, v)
+        _rho = np.interp(x, rn, rho)
+        fh = np.interp(x, rn, f_h)
+        fhe = np.interp(x, rn, f_he_ion)
+        lt1 = np.log(k1) + np.log(_rho)
+        lt2 = np.log(k2) + np.log(_rho)
+        ion1 = np.exp(lt1 + np.log(ion_ci)) * fh + np.exp(lt2 + np.log(ion_ci)) * fhe
+        cthp = np.exp(lt1 + np.log(ct_ci_hp)) * fh
+        cthep = np.exp(lt2 + np.log(ct_ci_hep)) * fhe
+        rec1 = np.exp(lt1 + np.log(rec_ci)) * fh + np.exp(lt2 + np.log(rec_ci)) * fhe
+        ct2h = np.exp(lt1 + np.log(ct_cii_h)) * (1 - fh)
+        rec2 = np.exp(lt1 + np.log(rec_cii)) * fh + np.exp(lt2 + np.log(rec_cii)) * fhe
+        ct3h = np.exp(lt1 + np.log(ct_ciii_h)) * (1 - fh)
+        ct3he = np.exp(lt2 + np.log(ct_ciii_he)) * (1 - fhe)
+        ion2 = np.exp(lt1 + np.log(ion_cii)) * fh + np.exp(lt2 + np.log(ion_cii)) * fhe
+        t_ci = np.interp(x, rn, st['t1'])
+        t11 = (1 - f2 - f3) * phi_ci * np.exp(-t_ci)
+        t12 = (1 - f2 - f3) * ion1
+        t13 = (1 - f2 - f3) * cthp
+        t14 = (1 - f2 - f3) * cthep
+        t15 = f2 * rec1
+        t16 = f2 * ct2h
+        t17 = f3 * rec2
+        t18 = f3 * ct3h
+        t19 = f3 * ct3he
+        t_cii = np.interp(x, rn, st['t2'])
+        t21 = f2 * phi_cii * np.exp(-t_cii)
+        t22 = f2 * ion2
+        d2 = (t11 + t12 + t13 + t14 - t15 - t16 + t17 + t18 + t19 - t21 - t22) / _v
+        d3 = (t21 + t22 - t17 - t18 - t19) / _v
+        return np.array([d2, d3])
+
+    out = {'status': 0, 'n_relax': 0, 'nfev': []}
+    nan = np.full(len(rn), np.nan)
+
+    def solve(first):
+        if method == 'odeint':
+            with warnings.catch_warnings():
+                warnings.filterwarnings('error' if first else 'ignore')
+                try:
+                    sol = odeint(fun, y0=y0, t=rn, tfirst=True)
+                except Warning:
+                    return None
+            return np.copy(sol).T[0], np.copy(sol).T[1]
+        sol = solve_ivp(fun, (rn[0], rn[-1],), y0, t_eval=rn, method=method, **options)
+        out['nfev'].append(sol.nfev)
+        if len(sol['y'][0]) != len(rn):
+            return None
+        return sol['y'][0], sol['y'][1]
+
+    def clamp(a):
+        a[a < 0] = 1E-15
+        a[a > 1.0] = 1.0
+
+    res = solve(True)
+    if res is None:
+        out.update(status=2, f_cii=nan, f_ciii=nan.copy())
+        return out
+    f2, f3 = res
+    clamp(f2)
+    clamp(f3)
+    if relax_solution is True:
+        for i in range(max_n_relax):
+            p2, p3 = np.copy(f2), np.copy(f3)
+            st['t1'] = k3 * a_ci * np.flip(np.cumsum(np.flip(dr * rho * (1 - f2 - f3)))) + tau_ci_h + tau_c_he
+            st['t2'] = k3 * a_cii * np.flip(np.cumsum(np.flip(dr * rho * f2))) + tau_cii_h + tau_c_he
+            res = solve(False)
+            if res is None:          # the reference would crash on the next lines (shape mismatch)
+                out.update(status=2, f_cii=nan, f_ciii=nan.copy())
+                return out
+            f2, f3 = res
+            clamp(f2)
+            clamp(f3)
+            out['n_relax'] = i + 1
+            with np.errstate(all='ignore'):
+                d2 = abs(np.sum(f2 - p2)) / np.sum(p2)
+                d3 = abs(np.sum(f3 - p3)) / np.sum(p3)
+            if d2 < convergence and d3 < convergence:
+                break
+    out.update(f_cii=f2, f_ciii=f3)
     return out
 
 

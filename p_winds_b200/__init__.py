@@ -11,14 +11,14 @@ raises.
 """
 from . import lines, tools  # noqa: F401  (pure constants / host I/O helpers)
 
-__all__ = ['parker', 'hydrogen', 'helium', 'oxygen', 'transit', 'retrieval', 'lines', 'tools', 'engine']
+__all__ = ['parker', 'hydrogen', 'helium', 'oxygen', 'carbon', 'transit', 'retrieval', 'lines', 'tools', 'engine']
 __version__ = '0.1.0'
 
 
 def __getattr__(name):
     # the compute modules import the CUDA library lazily so that `import p_winds_b200`
     # (and the constants) work in a CPU-only build container
-    if name in ('parker', 'hydrogen', 'helium', 'oxygen', 'transit', 'retrieval', 'engine', '_lib'):
+    if name in ('parker', 'hydrogen', 'helium', 'oxygen', 'carbon', 'transit', 'retrieval', 'engine', '_lib'):
         import importlib
         return importlib.import_module('.' + name, __name__)
     raise AttributeError(name)

@@ -36,6 +36,13 @@ class OOpts(C.Structure):
                 ('first_step', C.c_double), ('max_step', C.c_double)]
 
 
+class COpts(C.Structure):
+    _fields_ = [('planet_radius', C.c_double), ('c_fraction', C.c_double), ('initial_f_c_ion', C.c_double * 2),
+                ('relax_solution', C.c_int), ('max_n_relax', C.c_int), ('convergence', C.c_double),
+                ('rates', C.c_double * 7), ('method', C.c_int), ('rtol', C.c_double), ('atol', C.c_double),
+                ('first_step', C.c_double), ('max_step', C.c_double)]
+
+
 class RtOpts(C.Structure):
     _fields_ = [('n_lines', C.c_int), ('central_wavelength', C.c_double * 8),
                 ('oscillator_strength', C.c_double * 8),
@@ -64,6 +71,8 @@ SYMBOLS = {
                                      C.POINTER(HeOpts), _VP, _VP, _VP, _VP, _VP, _VP]),
     'pwb_o_ion_fraction_batch': (_I, [_VP, _I, _VP, _VP, _VP, _VP, _VP, _I, _VP, _I, _VP, _VP, _VP, _VP,
                                       C.POINTER(OOpts), _VP, _VP, _VP, _VP, _VP]),
+    'pwb_c_ion_fraction_batch': (_I, [_VP, _I, _VP, _VP, _VP, _VP, _VP, _I, _VP, _I, _VP, _VP, _VP, _VP,
+                                      C.POINTER(COpts), _VP, _VP, _VP, _VP, _VP, _VP]),
     'pwb_set_geometry': (_I, [_VP, _VP, _VP, _I, _VP, _I, _VP]),
     'pwb_set_geometry_phase': (_I, [_VP, _I, _VP, _VP, _I, _VP, _I, _D, _VP]),
     'pwb_set_phase_count': (_I, [_VP, _I]),

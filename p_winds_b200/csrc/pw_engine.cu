@@ -30,6 +30,7 @@
 #include "pw_hydrogen.cuh"
 #include "pw_helium.cuh"
 #include "pw_oxygen.cuh"
+#include "pw_carbon.cuh"
 #include "pw_transit.cuh"
 #include "pw_draw.cuh"
 
@@ -365,6 +366,41 @@ k_oxygen(int B, int lanes, const double* __restrict__ T, const double* __restric
   o_ion_fraction_model(p, *tab, r, v + (size_t)b * nr, rho + (size_t)b * nr, f_h + (size_t)b * nr,
                        f_he + (size_t)b * nr, nr, w, out2);
   if (st != PW_OK) status[b] = st;  // keeps an upstream PW_WARN_HE_RELAX otherwise
+}
+
+// carbon.ion_fraction: one thread per model (LSODA / Radau / RK45 replica), `lanes` models per warp
+__global__ void __launch_bounds__(32)
+k_carbon(int B, int lanes, const double* __restrict__ T, const double* __restrict__ hfrac,
+         const double* __restrict__ vs, const double* __restrict__ rs, const double* __restrict__ rhos,
+         int sstride, const double* __restrict__ r, int nr, const double* __restrict__ v,
+         const double* __restrict__ rho, const double* __restrict__ f_h, const double* __restrict__ f_he,
+         pwb_c_opts o, const LsodaTables* __restrict__ tab, double* work, double* f_cii, double* f_ciii,
+         double* scal, double* rates, int* status) {
+  if ((int)threadIdx.x >= lanes) return;
+  const int b = blockIdx.x * lanes + threadIdx.x;
+  if (b >= B) return;
+  if (status[b] != PW_OK && status[b] != PW_WARN_HE_RELAX) {  // upstream failure: propagate NaNs
+    const double nan_ = nan("");
+    for (int i = 0; i < nr; ++i) { f_cii[(size_t)b * nr + i] = nan_; f_ciii[(size_t)b * nr + i] = nan_; }
+    for (int k = 0; k < 4; ++k) scal[(size_t)b * 4 + k] = 0.0;
+    return;
+  }
+  CParams p;
+  p.T = T[b]; p.h_fraction = hfrac[b];
+  p.vs = vs[(size_t)b * sstride]; p.rs = rs[(size_t)b * sstride]; p.rhos = rhos[(size_t)b * sstride];
+  p.r_pl = o.planet_radius; p.c_fraction = o.c_fraction; p.y0[0] = o.initial_f_c_ion[0]; p.y0[1] = o.initial_f_c_ion[1];
+  p.relax = o.relax_solution; p.max_n_relax = o.max_n_relax; p.convergence = o.convergence;
+  for (int k = 0; k < 7; ++k) p.rates[k] = o.rates[k];
+  p.method = o.method; p.rtol = o.rtol; p.atol = o.atol; p.first_step = o.first_step; p.max_step = o.max_step;
+  double* wb = work + (size_t)b * kCWorkPerRadius * nr;
+  CWork w{wb, wb + nr, wb + 2 * nr, wb + 3 * nr, wb + 4 * nr, wb + 5 * nr, wb + 6 * nr, wb + 7 * nr, wb + 8 * nr,
+          wb + 9 * nr};
+  int st = PW_OK;
+  COut out{f_cii + (size_t)b * nr, f_ciii + (size_t)b * nr, scal + (size_t)b * 4,
+           rates ? rates + (size_t)b * 11 * nr : nullptr, &st};
+  c_ion_fraction_model(p, *tab, r, v + (size_t)b * nr, rho + (size_t)b * nr, f_h + (size_t)b * nr,
+                       f_he + (size_t)b * nr, nr, w, out);
+  if (st != PW_OK) status[b] = st;
 }
 
 // n [m^-3] and v [m/s] for the RT stage (quickstart.ipynb cells 10-11; SURVEY 8(d) cfg 2)
@@ -863,9 +899,9 @@ int pwb_set_sed(pwb_ctx* c, const double* d_wl, const double* d_flux, int n, voi
   return 0;
 }
 
-int pwb_get_sed_scalars(pwb_ctx* c, double* out16) {
+int pwb_get_sed_scalars(pwb_ctx* c, double* out32) {
   if (!c || !c->sed_ready) return fail(c, "pwb_get_sed_scalars: no SED set");
-  memcpy(out16, c->sed_scal_host, sizeof(double) * PW_SC_COUNT);
+  memcpy(out32, c->sed_scal_host, sizeof(double) * PW_SC_COUNT);
   return 0;
 }
 
@@ -1043,6 +1079,25 @@ int pwb_o_ion_fraction_batch(pwb_ctx* c, int B, const double* d_T, const double*
   k_oxygen<<<(B + lanes - 1) / lanes, 32, 0, (cudaStream_t)stream>>>(
       B, lanes, d_T, d_hfrac, d_vs, d_rs, d_rhos, sstride, d_r, Nr, d_v, d_rho, d_f_h, d_f_he_ion, *o,
       c->lsoda_tab.as<LsodaTables>(), c->o_work.as<double>(), d_f_o, d_scal, d_rates, d_status);
+  c->launches++;
+  PWB_CUDA(c, cudaGetLastError());
+  return 0;
+}
+
+int pwb_c_ion_fraction_batch(pwb_ctx* c, int B, const double* d_T, const double* d_hfrac, const double* d_vs,
+                             const double* d_rs, const double* d_rhos, int sstride, const double* d_r, int Nr,
+                             const double* d_v, const double* d_rho, const double* d_f_h,
+                             const double* d_f_he_ion, const pwb_c_opts* o, double* d_f_cii, double* d_f_ciii,
+                             double* d_scal, double* d_rates, int* d_status, void* stream) {
+  if (!c) return -1;
+  if (B <= 0) return 0;
+  if (Nr < 2) return fail(c, "pwb_c_ion_fraction_batch: radius profile needs >= 2 points");
+  if (o->method < 0 || o->method > 2) return fail(c, "pwb_c_ion_fraction_batch: unsupported method");
+  if (c->o_work.ensure(sizeof(double) * kCWorkPerRadius * (size_t)Nr * B)) return fail(c, "out of device memory");
+  int lanes = (int)std::min<long long>(32, std::max<long long>(1, ((long long)B + 4LL * c->sm_count - 1) / (4LL * c->sm_count)));
+  k_carbon<<<(B + lanes - 1) / lanes, 32, 0, (cudaStream_t)stream>>>(
+      B, lanes, d_T, d_hfrac, d_vs, d_rs, d_rhos, sstride, d_r, Nr, d_v, d_rho, d_f_h, d_f_he_ion, *o,
+      c->lsoda_tab.as<LsodaTables>(), c->o_work.as<double>(), d_f_cii, d_f_ciii, d_scal, d_rates, d_status);
   c->launches++;
   PWB_CUDA(c, cudaGetLastError());
   return 0;

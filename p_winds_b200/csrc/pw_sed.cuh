@@ -94,8 +94,31 @@ enum {
   PW_SC_HE_AH1 = 6, PW_SC_HE_AH3 = 7,
   PW_SC_N_H = 8, PW_SC_I1 = 9, PW_SC_I0 = 10,
   PW_SC_O_PHI = 11, PW_SC_O_A = 12, PW_SC_O_AH = 13, PW_SC_O_AHE = 14,  // oxygen.radiative_processes
-  PW_SC_COUNT = 16
+  // carbon.radiative_processes: phi_ci, phi_cii, a_ci, a_cii, a_h_ci, a_h_cii, a_he
+  PW_SC_C_PHI1 = 16, PW_SC_C_PHI2 = 17, PW_SC_C_A1 = 18, PW_SC_C_A2 = 19, PW_SC_C_AH1 = 20, PW_SC_C_AH2 = 21,
+  PW_SC_C_AHE = 22,
+  PW_SC_COUNT = 32
 };
+
+// microphysics.general_cross_section (microphysics.py:224-281) for one parameter row of
+// sigma_properties_v1996: E_thr, E_max, E_0, sigma_0, y_a, p, y_w, y_0, y_1
+PW_HD double sigma_verner(double wl, double e_thr, double e_0, double sigma_0, double y_a, double p, double y_w,
+                          double y_0, double y_1) {
+  const double energy = ((6.62607015e-34 * 299792458.0) / wl) * ((1.0 / 1e-10) / 1.602176634e-19);
+  if (energy < e_thr) return 0.0;
+  const double x = energy / e_0 - y_0;
+  const double y = sqrt(x * x + y_1 * y_1);
+  const double term1 = (x - 1) * (x - 1) + y_w * y_w;
+  const double term2 = pow(y, 0.5 * p - 5.5);
+  const double term3 = pow(1 + sqrt(y / y_a), -p);
+  return sigma_0 * (term1 * term2 * term3) * 1E-18;
+}
+PW_HD double sigma_verner_ci(double wl) {   // 'C I'  (microphysics.py:300-301)
+  return sigma_verner(wl, 1.126E1, 2.144E0, 5.027E2, 6.126E1, 5.101E0, 9.157E-2, 1.133E0, 1.607E0);
+}
+PW_HD double sigma_verner_cii(double wl) {  // 'C II' (microphysics.py:302-303)
+  return sigma_verner(wl, 2.438E1, 4.058E-1, 8.709E0, 1.261E2, 8.578E0, 2.093E0, 4.929E1, 3.234E0);
+}
 
 // microphysics.general_cross_section(wavelength, 'O I') (microphysics.py:224-281; Verner et al.
 // 1996 parameters of microphysics.py:307-308): E_thr, E_max, E_0, sigma_0, y_a, p, y_w, y_0, y_1
@@ -205,7 +228,37 @@ PW_HD void sed_setup(const double* __restrict__ wl, const double* __restrict__ f
   }
   const double so_f0 = block_sum(o_f0, red), so_fahe = block_sum(o_fahe, red);
 
+  // ---- carbon.radiative_processes (carbon.py:30-131): C I cut [:ic1] at 12398.42 / 11.26 A,
+  //      C II cut [:ic2] at 12398.42 / 24.38 A, He cut [:io0]
+  const int ic1 = nearest_index(wl, n, 12398.42 / 1.126E1);
+  const int ic2 = nearest_index(wl, n, 12398.42 / 2.438E1);
+  double c_res[2][4];
+  for (int sp = 0; sp < 2; ++sp) {
+    const int icut = sp == 0 ? ic1 : ic2;
+    double q_f = 0, q_fa = 0, q_fah = 0, q_phi = 0;
+    for (int j = PW_TID; j < icut; j += PW_NT) {
+      const double w = simpson_weight(icut, j, X);
+      const double a = sp == 0 ? sigma_verner_ci(wl[j]) : sigma_verner_cii(wl[j]);
+      const double e_ev = (6.62607015e-34 * ((299792458.0 / wl[j]) / 1.0 * (1.0 / 1e-10 / 1.0))) *
+                          (1.0 / 1.602176634e-19);
+      const double e_erg = e_ev * (1.602176634e-19 / 1e-7);
+      q_f += w * flux[j];
+      q_fa += w * (flux[j] * a);
+      q_fah += w * (flux[j] * sigma_h(wl[j]));
+      q_phi += w * (flux[j] * a / e_erg);
+    }
+    c_res[sp][0] = block_sum(q_f, red); c_res[sp][1] = block_sum(q_fa, red);
+    c_res[sp][2] = block_sum(q_fah, red); c_res[sp][3] = block_sum(q_phi, red);
+  }
+
   if (PW_TID == 0) {
+    scalars[PW_SC_C_PHI1] = fabs(c_res[0][3]);
+    scalars[PW_SC_C_PHI2] = fabs(c_res[1][3]);
+    scalars[PW_SC_C_A1] = fabs(c_res[0][1] / c_res[0][0]);
+    scalars[PW_SC_C_A2] = fabs(c_res[1][1] / c_res[1][0]);
+    scalars[PW_SC_C_AH1] = fabs(c_res[0][2] / c_res[0][0]);
+    scalars[PW_SC_C_AH2] = fabs(c_res[1][2] / c_res[1][0]);
+    scalars[PW_SC_C_AHE] = fabs(so_fahe / so_f0);
     scalars[PW_SC_O_PHI] = fabs(so_phi);
     scalars[PW_SC_O_A] = fabs(so_fa / so_f);
     scalars[PW_SC_O_AH] = fabs(so_fah / so_f);

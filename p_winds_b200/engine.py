@@ -15,6 +15,7 @@ STATUS_MESSAGES = {
 }
 HE_METHODS = {'odeint': 0, 'LSODA': 1, 'RK45': 2}
 O_METHODS = {'Radau': 0, 'odeint': 1, 'RK45': 2}
+C_METHODS = {'odeint': 0, 'Radau': 1, 'RK45': 2}
 LD_LAWS = {None: 0, 'linear': 1, 'quadratic': 2, 'square-root': 3, 'log': 4, 'exp': 5,
            's3': 6, 'c4': 7}
 
@@ -87,13 +88,14 @@ class Engine:
             self._sed_key = key
 
     def sed_scalars(self):
-        out = (C.c_double * 16)()
+        out = (C.c_double * 32)()
         self._check(self.lib.pwb_get_sed_scalars(self.ctx, out))
         v = list(out)
         return {'h_phi': v[0], 'h_a0': v[1], 'he_phi_1': v[2], 'he_phi_3': v[3], 'he_a_1': v[4],
                 'he_a_3': v[5], 'he_a_h_1': v[6], 'he_a_h_3': v[7], 'n_cut_h': int(v[8]),
                 'i1': int(v[9]), 'i0': int(v[10]), 'o_phi': v[11], 'o_a': v[12], 'o_a_h': v[13],
-                'o_a_he': v[14]}
+                'o_a_he': v[14], 'c_phi_1': v[16], 'c_phi_2': v[17], 'c_a_1': v[18], 'c_a_2': v[19],
+                'c_a_h_1': v[20], 'c_a_h_2': v[21], 'c_a_he': v[22]}
 
     # ------------------------------------------------------------------- parker
     def parker_structure(self, r):
@@ -198,6 +200,38 @@ class Engine:
             _ptr(rho), _ptr(f_h), _ptr(f_he), C.byref(opts), _ptr(f_o), _ptr(scal), _ptr(rates),
             _ptr(status), self._stream()))
         return {'f_o': f_o, 'scal': scal, 'rates': rates, 'status': status}
+
+    # ------------------------------------------------------------------- carbon
+    @staticmethod
+    def c_opts(planet_radius, rates, c_fraction=10 ** (8.43 - 12.00), initial_f_c_ion=(0.0, 0.0),
+               relax_solution=False, convergence=0.01, max_n_relax=10, method='odeint', rtol=1e-3,
+               atol=1e-6, first_step=None, max_step=None):
+        if method not in C_METHODS:
+            raise ValueError("method %r is not available on the GPU path (supported: 'odeint', 'Radau', "
+                             "'RK45'); there is no CPU fallback" % (method,))
+        return _lib.COpts(float(planet_radius), float(c_fraction),
+                          (C.c_double * 2)(*[float(x) for x in initial_f_c_ion]), int(bool(relax_solution)),
+                          int(max_n_relax), float(convergence), (C.c_double * 7)(*[float(x) for x in rates]),
+                          C_METHODS[method], float(rtol), float(atol), float(first_step) if first_step else 0.0,
+                          float(max_step) if (max_step and np.isfinite(max_step)) else 0.0)
+
+    def c_ion_fraction_batch(self, T, h_fraction, vs, rs, rhos, r, v, rho, f_h, f_he_ion, opts,
+                             return_rates=False, status=None):
+        """carbon.ion_fraction for B models (carbon.py:256-639)."""
+        T, hf, vs, rs, rhos, r = (self.dev(x).reshape(-1) for x in (T, h_fraction, vs, rs, rhos, r))
+        B, nr = T.numel(), r.numel()
+        v, rho, f_h, f_he = (self.dev(x).reshape(B, nr) for x in (v, rho, f_h, f_he_ion))
+        f2 = torch.empty((B, nr), dtype=torch.float64, device=self.device)
+        f3 = torch.empty_like(f2)
+        scal = torch.empty((B, 4), dtype=torch.float64, device=self.device)
+        rates = torch.empty((B, 11, nr), dtype=torch.float64, device=self.device) if return_rates else None
+        if status is None:
+            status = torch.zeros(B, dtype=torch.int32, device=self.device)
+        self._check(self.lib.pwb_c_ion_fraction_batch(
+            self.ctx, B, _ptr(T), _ptr(hf), _ptr(vs), _ptr(rs), _ptr(rhos), 1, _ptr(r), nr, _ptr(v),
+            _ptr(rho), _ptr(f_h), _ptr(f_he), C.byref(opts), _ptr(f2), _ptr(f3), _ptr(scal), _ptr(rates),
+            _ptr(status), self._stream()))
+        return {'f_cii': f2, 'f_ciii': f3, 'scal': scal, 'rates': rates, 'status': status}
 
     # ------------------------------------------------------------------ transit
     def set_geometry(self, intensity_0, r_from_planet, radius_profile_si):

@@ -206,6 +206,33 @@ int hs_o_ion_fraction(const double* model, const double* opts, const double* rat
 }
 }
 
+#include "../../p_winds_b200/csrc/pw_carbon.cuh"
+
+extern "C" {
+// model: [T, h_fraction, vs, rs, rhos]; opts: [r_pl, c_fraction, y0_0, y0_1, relax, max_n_relax,
+//   convergence, method, rtol, atol, first_step, max_step]; rates[7]
+int hs_c_ion_fraction(const double* model, const double* opts, const double* rates, const double* r,
+                      const double* v, const double* rho, const double* f_h, const double* f_he, int nr,
+                      double* f2, double* f3, double* scal, double* rates_out) {
+  static LsodaTables tab;
+  static bool init = false;
+  if (!init) { lsoda_tables_init(&tab); init = true; }
+  CParams p;
+  p.T = model[0]; p.h_fraction = model[1]; p.vs = model[2]; p.rs = model[3]; p.rhos = model[4];
+  p.r_pl = opts[0]; p.c_fraction = opts[1]; p.y0[0] = opts[2]; p.y0[1] = opts[3]; p.relax = (int)opts[4];
+  p.max_n_relax = (int)opts[5]; p.convergence = opts[6]; p.method = (int)opts[7];
+  p.rtol = opts[8]; p.atol = opts[9]; p.first_step = opts[10]; p.max_step = opts[11];
+  for (int i = 0; i < 7; ++i) p.rates[i] = rates[i];
+  std::vector<double> buf(kCWorkPerRadius * nr);
+  double* b = buf.data();
+  CWork w{b, b + nr, b + 2 * nr, b + 3 * nr, b + 4 * nr, b + 5 * nr, b + 6 * nr, b + 7 * nr, b + 8 * nr, b + 9 * nr};
+  int status = 0;
+  COut o{f2, f3, scal, rates_out, &status};
+  c_ion_fraction_model(p, tab, r, v, rho, f_h, f_he, nr, w, o);
+  return status;
+}
+}
+
 #include "../../p_winds_b200/csrc/pw_transit.cuh"
 
 extern "C" {

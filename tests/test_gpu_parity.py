@@ -622,3 +622,48 @@ def test_oxygen_reference_signature_and_batch(eng, oracle, sed):
     with pytest.raises(ValueError, match='not available on the GPU path'):
         oxygen.ion_fraction(d['r'], d['v'][0], d['rho'][0], d['f_h'][0], d['f_he_ion'][0], 1.39, 9100., 0.9,
                             float(d['vs'][0]), float(d['rs'][0]), float(d['rhos'][0]), sp, method='BDF')
+
+
+def test_carbon_reference_signature(eng, oracle):
+    """carbon.ion_fraction on the GPU (k_carbon: LSODA / Radau replicas) against the unmodified
+    reference (tests/golden/carbon.npz): scalars to 1e-10, C II / C III fractions inside the
+    reference's own 1-ulp noise envelope, the RuntimeError of the default `odeint` on the dense
+    model, and the reference's rates dict (including its 'ionization_CII' = electron-impact slip)."""
+    from p_winds_b200 import carbon
+    d = golden('carbon')
+    g = golden('solar_sed')
+    sp = {'wavelength': g['wavelength'], 'flux_lambda': g['flux_lambda'], 'wavelength_unit': 'angstrom',
+          'flux_unit': 'erg / (s cm2 angstrom)'}
+    scal = np.array(carbon.radiative_processes(sp))
+    assert np.max(_rel(scal, d['scalars'])) < 1e-10
+    for T in (7000., 9100., 12000.):
+        assert carbon.electron_impact_ionization(T) == oracle.c_electron_impact_ionization(T)
+        assert carbon.recombination(T) == oracle.c_recombination(T)
+        assert carbon.charge_transfer(T) == oracle.c_charge_transfer(T)
+    keys = ('ionization_CI', 'ionization_CII', 'recombination_CII', 'recombination_CIII', 'e_impact_ion_CI',
+            'e_impact_ion_CII', 'charge_exchange_CI_HII', 'charge_exchange_CI_HeII', 'charge_exchange_CII_HI',
+            'charge_exchange_CIII_HI', 'charge_exchange_CIII_HeI')
+    n_fail = 0
+    for i in range(len(d['T0'])):
+        kw = dict(relax_solution=bool(d['relax'][i]))
+        if str(d['method'][i]) != 'odeint':
+            kw.update(method=str(d['method'][i]), rtol=float(d['rtol'][i]), atol=float(d['atol'][i]))
+        args = (d['r'], d['v'][i], d['rho'][i], d['f_h'][i], d['f_he_ion'][i], 1.39, float(d['T0'][i]),
+                float(d['h_fraction'][i]), float(d['vs'][i]), float(d['rs'][i]), float(d['rhos'][i]), sp)
+        if d['status'][i] == 2:
+            n_fail += 1
+            with pytest.raises(RuntimeError, match='odeint'):
+                carbon.ion_fraction(*args, **kw)
+            continue
+        f2, f3, rates = carbon.ion_fraction(*args, return_rates=True, **kw)
+        tol2, tol3 = 4.0 * float(d['noise'][i]) + 1e-5, 4.0 * float(d['noise3'][i]) + 1e-3
+        big = d['f_ciii'][i] > 1e-2 * d['f_ciii'][i].max()
+        e2, e3 = np.max(_rel(f2[1:], d['f_cii'][i][1:])), np.max(_rel(f3[big], d['f_ciii'][i][big]))
+        assert e2 < tol2 and e3 < tol3, (i, e2, tol2, e3, tol3)
+        assert tuple(rates) == keys
+        assert np.array_equal(rates['ionization_CII'], rates['e_impact_ion_CII'])
+        m = (d['f_cii'][i] > 1e-3) & (d['f_cii'][i] < 0.99)
+        m[0] = False
+        if m.any():
+            assert np.max(_rel(rates['recombination_CII'][m], d['rates'][i][2][m])) < 100 * tol2
+    assert n_fail == 2

@@ -14,7 +14,7 @@ R = np.logspace(0, np.log10(20), 100)
 @pytest.fixture(scope='module')
 def tables(hostsim, sed):
     n = len(sed.wl)
-    gw, sh, she, sc = np.zeros(n), np.zeros(n), np.zeros(n), np.zeros(16)
+    gw, sh, she, sc = np.zeros(n), np.zeros(n), np.zeros(n), np.zeros(32)
     hostsim.hs_sed_setup(P(sed.wl), P(sed.flux), n, P(gw), P(sh), P(she), P(sc))
     return gw, sh, she, sc
 
@@ -297,3 +297,40 @@ def test_oxygen_stage_against_reference(hostsim, oracle, sed):
                                       relax_solution=bool(d['relax'][i]), **kw)
             assert int(scal[0]) == o['n_relax']
             assert abs(scal[1] / sum(o['nfev']) - 1) < 0.12     # the reference's own nfev scatters by +-5 %
+
+
+def _carbon_tolerances(d, i):
+    """Same protocol as _oxygen_tolerance; C III is compared where it is within a factor 100 of
+    its peak (fixture keys `noise`, `noise3`).  The default odeint path is far less noise
+    sensitive than Radau's finite-difference Jacobian: floor 1e-5 / 1e-3."""
+    return 4.0 * float(d['noise'][i]) + 1e-5, 4.0 * float(d['noise3'][i]) + 1e-3
+
+
+def test_carbon_stage_against_reference(hostsim):
+    """c_ion_fraction_model (LSODA / Radau replicas) on the host build against the
+    unmodified reference's carbon.ion_fraction (tests/golden/carbon.npz), including the dense
+    model on which the default `odeint` gives up (status 2 = RuntimeError, carbon.py:541-546)."""
+    d = golden('carbon')
+    rates = np.ascontiguousarray(d['scalars'])
+    meth = {'odeint': 0, 'Radau': 1}
+    n_fail = 0
+    for i in range(len(d['T0'])):
+        model = np.array([d['T0'][i], d['h_fraction'][i], d['vs'][i], d['rs'][i], d['rhos'][i]], dtype=float)
+        opts = np.array([1.39, 10 ** (8.43 - 12.00), 0.0, 0.0, d['relax'][i], 10, 0.01, meth[str(d['method'][i])],
+                         d['rtol'][i], d['atol'][i], 0., 0.], dtype=float)
+        f2, f3, scal, rr = np.zeros(100), np.zeros(100), np.zeros(4), np.zeros((11, 100))
+        st = hostsim.hs_c_ion_fraction(P(model), P(opts), P(rates), P(np.ascontiguousarray(d['r'])),
+                                       P(np.ascontiguousarray(d['v'][i])), P(np.ascontiguousarray(d['rho'][i])),
+                                       P(np.ascontiguousarray(d['f_h'][i])), P(np.ascontiguousarray(d['f_he_ion'][i])),
+                                       100, P(f2), P(f3), P(scal), P(rr))
+        assert st == d['status'][i], i
+        if st != 0:
+            n_fail += 1
+            assert np.isnan(f2).all() and np.isnan(f3).all()
+            continue
+        tol2, tol3 = _carbon_tolerances(d, i)
+        e2 = np.max(np.abs(f2[1:] / d['f_cii'][i][1:] - 1))
+        big = d['f_ciii'][i] > 1e-2 * d['f_ciii'][i].max()
+        e3 = np.max(np.abs(f3[big] / d['f_ciii'][i][big] - 1))
+        assert e2 < tol2 and e3 < tol3, (i, e2, tol2, e3, tol3)
+    assert n_fail == 2

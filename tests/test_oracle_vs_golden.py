@@ -168,3 +168,21 @@ def test_oxygen_oracle_matches_reference(oracle, sed):
                                   method=str(d['method'][i]), **kw)
         assert o['status'] == d['status'][i]
         assert np.array_equal(o['f_o'], d['f_o'][i]), i
+
+
+def test_carbon_oracle_matches_reference(oracle, sed):
+    """SURVEY 8(f-3), carbon: scalars and ion fractions of the unmodified reference
+    (tests/golden/carbon.npz) -- bit for bit, including the models its default `odeint` gives up on."""
+    d = golden('carbon')
+    assert np.array_equal(np.array(oracle.c_radiative_processes(sed)), d['scalars'])
+    for T in (7000., 9100., 12000.):
+        assert all(np.isfinite(x) for x in oracle.c_charge_transfer(T))
+    for i in range(len(d['T0'])):
+        kw = {} if d['method'][i] == 'odeint' else dict(rtol=float(d['rtol'][i]), atol=float(d['atol'][i]))
+        o = oracle.c_ion_fraction(d['r'], d['v'][i], d['rho'][i], d['f_h'][i], d['f_he_ion'][i], 1.39,
+                                  float(d['T0'][i]), float(d['h_fraction'][i]), float(d['vs'][i]), float(d['rs'][i]),
+                                  float(d['rhos'][i]), sed=sed, relax_solution=bool(d['relax'][i]),
+                                  method=str(d['method'][i]), **kw)
+        assert o['status'] == d['status'][i], i
+        assert np.array_equal(o['f_cii'], d['f_cii'][i], equal_nan=True), i
+        assert np.array_equal(o['f_ciii'], d['f_ciii'][i], equal_nan=True), i
