@@ -81,6 +81,11 @@ typedef struct {
   double rtol, atol, first_step, max_step;
 } pwb_o_opts;
 
+/* Options of helium.ion_fraction (helium.py:789-793): the pwb_o_opts block with
+ * rates[0..2] = phi_he, a_he, a_h of helium.radiative_processes(combined_ionization=True),
+ * initial_f_o_ion = initial_f_he_ion; o_fraction is ignored. */
+typedef pwb_o_opts pwb_heion_opts;
+
 /* Options of carbon.ion_fraction (carbon.py:256-262). */
 enum pwb_c_method { PWB_C_ODEINT = 0, PWB_C_RADAU = 1, PWB_C_RK45 = 2 };
 typedef struct {
@@ -129,7 +134,8 @@ int pwb_n_active_pixels(pwb_ctx* ctx);
 int pwb_set_sed(pwb_ctx* ctx, const double* d_wavelength, const double* d_flux, int n, void* stream);
 /* host out[32]: phi_H, a_0, phi_1, phi_3, a_1, a_3, a_h_1, a_h_3, n_cut_H, i1, i0,
  *      [11..14] oxygen.radiative_processes (phi_oi, a_oi, a_h_oi, a_he; oxygen.py:99),
- *      [16..22] carbon.radiative_processes (phi_ci, phi_cii, a_ci, a_cii, a_h_ci, a_h_cii, a_he; carbon.py:131) */
+ *      [16..22] carbon.radiative_processes (phi_ci, phi_cii, a_ci, a_cii, a_h_ci, a_h_cii, a_he; carbon.py:131),
+ *      [24..25] helium.radiative_processes(combined_ionization=True): phi, a_he (a_h = out[6]) */
 int pwb_get_sed_scalars(pwb_ctx* ctx, double* out32);
 
 /* ---- parker.structure (parker.py:163-223) / structure_tidal (:271-358) --------- */
@@ -174,6 +180,14 @@ int pwb_o_ion_fraction_batch(pwb_ctx* ctx, int B, const double* d_T, const doubl
                              const double* d_r, int Nr, const double* d_v, const double* d_rho,
                              const double* d_f_h, const double* d_f_he_ion, const pwb_o_opts* opts,
                              double* d_f_o, double* d_scal, double* d_rates, int* d_status, void* stream);
+
+/* ---- helium.ion_fraction, batched (helium.py:789-1032) -------------
+ * outputs: d_f_he_ion [B][Nr]; d_scal [B][4] = n_relax, nfev, n_solves, - */
+int pwb_he_ion_fraction_batch(pwb_ctx* ctx, int B, const double* d_T, const double* d_hfrac,
+                              const double* d_vs, const double* d_rs, const double* d_rhos, int sstride,
+                              const double* d_r, int Nr, const double* d_v, const double* d_rho,
+                              const double* d_f_h, const pwb_heion_opts* opts, double* d_f_he_ion,
+                              double* d_scal, int* d_status, void* stream);
 
 /* ---- carbon.ion_fraction, batched (carbon.py:256-639) -------------
  * outputs: d_f_cii, d_f_ciii [B][Nr]; d_scal [B][4] = n_relax, nfev, n_solves, -; d_rates (may be

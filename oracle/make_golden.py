@@ -284,6 +284,50 @@ def oxygen_fixture(sp):
     np.savez_compressed(os.path.join(OUT, 'oxygen.npz'), scalars=scal, r=R, **keep)
 
 
+def heion_fixture(sp):
+    """tests/golden/helium_ion.npz: helium.radiative_processes(combined_ionization=True) and
+    helium.ion_fraction of the unmodified reference (default 'Radau', and 'odeint')."""
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        scal = np.array(helium.radiative_processes(sp, combined_ionization=True))
+    cases, keep = [], {}
+    for (T0, md, h) in [(9100., 10 ** 10.27, 0.9), (9100., 1e11, 0.9), (11500., 10 ** 10.5, 0.85),
+                        (13000., 10 ** 11.6, 0.9)]:
+        he_h = (1 - h) / h
+        mu_0 = (1 + 4 * he_h) / (1 + he_h)
+        f_r, mu = hydrogen.ion_fraction(R, R_PL, T0, h, md, M_PL, mu_0, spectrum_at_planet=sp,
+                                        initial_f_ion=0.0, relax_solution=True, exact_phi=True, return_mu=True)
+        vs = parker.sound_speed(T0, mu)
+        rs = parker.radius_sonic_point(M_PL, vs)
+        rhos = parker.density_sonic_point(md, rs, vs)
+        v, rho = parker.structure(R * R_PL / rs)
+        for kw in (dict(), dict(relax_solution=True), dict(relax_solution=True, rtol=1e-8, atol=1e-11),
+                   dict(relax_solution=True, method='odeint')):
+            def run(rho_in):
+                with warnings.catch_warnings():
+                    warnings.simplefilter('ignore')
+                    return helium.ion_fraction(R, v, rho_in, f_r, R_PL, T0, h, vs, rs, rhos, sp, **kw)
+            try:
+                f, status = run(rho), 0
+            except RuntimeError:
+                f, status = np.full(len(R), np.nan), 2
+            noise = 0.0
+            if status == 0:
+                rng = np.random.default_rng(17)
+                for _ in range(6):
+                    g = run(rho * (1 + 2.2e-16 * rng.standard_normal(len(rho))))
+                    noise = max(noise, float(np.max(np.abs(g[1:] / f[1:] - 1))))
+            cases.append(dict(T0=T0, mdot=md, h_fraction=h, vs=vs, rs=rs, rhos=rhos, v=v, rho=rho, f_h=f_r,
+                              relax=int(kw.get('relax_solution', False)), method=kw.get('method', 'Radau'),
+                              rtol=kw.get('rtol', 1e-3), atol=kw.get('atol', 1e-6), f_he_ion=f, status=status,
+                              noise=noise))
+            print('he ion', T0, '%.3e' % md, h, kw, 'status', status, 'f[-1] %.6f' % f[-1],
+                  'self-noise %.1e' % noise, flush=True)
+    for k in cases[0]:
+        keep[k] = np.array([c[k] for c in cases])
+    np.savez_compressed(os.path.join(OUT, 'helium_ion.npz'), scalars=scal, r=R, **keep)
+
+
 def carbon_fixture(sp):
     """tests/golden/carbon.npz: carbon.radiative_processes and carbon.ion_fraction of the
     unmodified reference (default 'odeint' -- which gives up on some of these models, as SURVEY.md
@@ -348,7 +392,9 @@ def carbon_fixture(sp):
 
 
 if __name__ == '__main__':
-    if len(sys.argv) > 1 and sys.argv[1] == 'carbon':
+    if len(sys.argv) > 1 and sys.argv[1] == 'heion':
+        heion_fixture(spectrum_dict())
+    elif len(sys.argv) > 1 and sys.argv[1] == 'carbon':
         carbon_fixture(spectrum_dict())
     elif len(sys.argv) > 1 and sys.argv[1] == 'oxygen':
         oxygen_fixture(spectrum_dict())
@@ -356,3 +402,4 @@ if __name__ == '__main__':
         main()
         oxygen_fixture(spectrum_dict())
         carbon_fixture(spectrum_dict())
+        heion_fixture(spectrum_dict())

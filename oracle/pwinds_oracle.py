@@ -717,6 +717,116 @@ def radiative_transfer_2d(i0, r_map, r, n, v, w0, f, a_ij, wl, T, mass,
 
 
 # ----------------------------------------------------------------------------
+# helium.ion_fraction: helium.py:789-1032
+# ----------------------------------------------------------------------------
+def he_radiative_processes_combined(sed):
+    """helium.radiative_processes(..., combined_ionization=True), helium.py:160-177 -> phi, a_he, a_h."""
+    wl, flux = sed.wl, sed.flux
+    energy = (_H_SI * ((_C_SI / wl) / 1.0 * (1.0 / 1e-10 / 1.0))) * (1.0 / _EV_J)
+    energy_erg = energy * (_EV_J / 1e-7)
+    i1 = nearest_index(wl, 504)
+    w1, f1, e1 = wl[:i1], flux[:i1], energy_erg[:i1]
+    a_l = sigma_he_total(w1)
+    a_he = abs(simpson(f1 * a_l, x=w1) / simpson(f1, x=w1))
+    a_h = abs(simpson(f1 * sigma_h(w1), x=w1) / simpson(f1, x=w1))
+    phi = abs(simpson(f1 * a_l / e1, x=w1))
+    return phi, a_he, a_h
+
+
+def he_recombination_all(T):
+    """helium.py:294-313."""
+    return 4.6E-12 * (T / 300) ** (-0.64)
+
+
+def he_charge_transfer(T):
+    """helium.py:384-409 -> (He + H+ -> He+, He+ + H -> He)."""
+    ct_hep_h = 1.25E-15 * (300 / T) ** (-0.25)
+    ct_he_hp = 1.75E-11 * (300 / T) ** 0.75 * np.exp(-128000 / T)
+    return ct_he_hp, ct_hep_h
+
+
+def he_ion_fraction(r, v, rho, f_h, r_pl, T, h_fraction, vs, rs, rhos, sed=None, rates=None,
+                    initial_f_he_ion=0.0, relax_solution=False, convergence=0.01, max_n_relax=10,
+                    method='Radau', **options):
+    """helium.py:789-1032 -> dict(f_he_ion, status, n_relax, nfev)."""
+    alpha_unit = ((rs * 7.1492E+09) ** 2 * vs * 1E5)
+    alpha_rec = he_recombination_all(T) / alpha_unit
+    m_h = 1.67262192E-24 / (rhos * (rs * 7.1492E+09) ** 3)
+    phi_unit = vs * 1E5 / rs / 7.1492E+09
+    phi_he, a_he, a_h = rates if rates is not None else he_radiative_processes_combined(sed)
+    phi_he = phi_he / phi_unit
+    a_he = a_he / (rs * 7.1492E+09) ** 2
+    a_h = a_h / (rs * 7.1492E+09) ** 2
+    ct_he_hp, ct_hep_h = he_charge_transfer(T)
+    ct_hep_h = ct_hep_h / alpha_unit
+    ct_he_hp = ct_he_hp / alpha_unit
+    rn = r * r_pl / rs
+    dr = np.diff(rn)
+    dr = np.concatenate((dr, np.array([dr[-1], ])))
+    col = np.flip(np.cumsum(np.flip(dr * rho)))
+    col_h0 = np.flip(np.cumsum(np.flip(dr * rho * (1 - f_h))))
+    he_fraction = 1 - h_fraction
+    k1 = h_fraction / (h_fraction + 4 * he_fraction) / m_h
+    k2 = he_fraction / (h_fraction + 4 * he_fraction) / m_h
+    tau_h = k1 * a_h * col_h0
+    st = {'tau': (initial_f_he_ion * k2 * a_he * col + tau_h)}
+
+    def fun(x, y):
+        f = y
+        _v = np.interp(x, rn, v)
+        _rho = np.interp(x, rn, rho)
+        fh = np.interp(x, rn, f_h)
+        lt1 = np.log(k1) + np.log(_rho)
+        lt2 = np.log(k2) + np.log(_rho)
+        ct1 = np.exp(lt1 + np.log(ct_he_hp)) * fh
+        rec = np.exp(lt1 + np.log(alpha_rec)) * fh + np.exp(lt2 + np.log(alpha_rec)) * f
+        ct2 = np.exp(lt1 + np.log(ct_hep_h)) * (1 - fh)
+        t_he = np.interp(x, rn, st['tau'])
+        term1 = (1 - f) * phi_he * np.exp(-t_he)
+        term2 = (1 - f) * ct1
+        term3 = f * rec
+        term4 = f * ct2
+        return (term1 + term2 - term3 - term4) / _v
+
+    out = {'status': 0, 'n_relax': 0, 'nfev': []}
+    nan = np.full(len(rn), np.nan)
+
+    def solve(first):
+        if method == 'odeint':
+            with warnings.catch_warnings():
+                warnings.filterwarnings('error' if first else 'ignore')
+                try:
+                    sol = odeint(fun, y0=initial_f_he_ion, t=rn, tfirst=True)
+                except Warning:
+                    return None
+            return np.copy(sol).T[0]
+        sol = solve_ivp(fun, (rn[0], rn[-1],), np.array([initial_f_he_ion, ]), t_eval=rn, method=method,
+                        **options)
+        out['nfev'].append(sol.nfev)
+        return sol['y'][0] if len(sol['y'][0]) == len(rn) else None
+
+    f = solve(True)
+    if f is None:
+        out.update(status=2, f_he_ion=nan)
+        return out
+    if relax_solution is True:     # (no clamp after the first solve, helium.py:985-997)
+        for i in range(max_n_relax):
+            prev = np.copy(f)
+            st['tau'] = k2 * a_he * np.flip(np.cumsum(np.flip(dr * rho * (1 - f)))) + tau_h
+            f = solve(False)
+            if f is None:
+                out.update(status=2, f_he_ion=nan)
+                return out
+            f[f < 0] = 1E-15
+            f[f > 1.0] = 1.0
+            out['n_relax'] = i + 1
+            if abs(np.sum(f - prev)) / np.sum(prev) < convergence:
+                break
+    out['f_he_ion'] = f
+    return out
+
+
+# ----------------------------------------------------------------------------
 # Oxygen (SURVEY.md 8(f-3)): oxygen.py, microphysics.general_cross_section
 # ----------------------------------------------------------------------------
 # microphysics.sigma_properties_v1996 (microphysics.py:300-318), Verner et al. 1996:

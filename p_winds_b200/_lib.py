@@ -71,6 +71,8 @@ SYMBOLS = {
                                      C.POINTER(HeOpts), _VP, _VP, _VP, _VP, _VP, _VP]),
     'pwb_o_ion_fraction_batch': (_I, [_VP, _I, _VP, _VP, _VP, _VP, _VP, _I, _VP, _I, _VP, _VP, _VP, _VP,
                                       C.POINTER(OOpts), _VP, _VP, _VP, _VP, _VP]),
+    'pwb_he_ion_fraction_batch': (_I, [_VP, _I, _VP, _VP, _VP, _VP, _VP, _I, _VP, _I, _VP, _VP, _VP,
+                                       C.POINTER(OOpts), _VP, _VP, _VP, _VP]),
     'pwb_c_ion_fraction_batch': (_I, [_VP, _I, _VP, _VP, _VP, _VP, _VP, _I, _VP, _I, _VP, _VP, _VP, _VP,
                                       C.POINTER(COpts), _VP, _VP, _VP, _VP, _VP, _VP]),
     'pwb_set_geometry': (_I, [_VP, _VP, _VP, _I, _VP, _I, _VP]),

@@ -31,6 +31,7 @@
 #include "pw_helium.cuh"
 #include "pw_oxygen.cuh"
 #include "pw_carbon.cuh"
+#include "pw_heion.cuh"
 #include "pw_transit.cuh"
 #include "pw_draw.cuh"
 
@@ -366,6 +367,37 @@ k_oxygen(int B, int lanes, const double* __restrict__ T, const double* __restric
   o_ion_fraction_model(p, *tab, r, v + (size_t)b * nr, rho + (size_t)b * nr, f_h + (size_t)b * nr,
                        f_he + (size_t)b * nr, nr, w, out2);
   if (st != PW_OK) status[b] = st;  // keeps an upstream PW_WARN_HE_RELAX otherwise
+}
+
+// helium.ion_fraction: one thread per model
+__global__ void __launch_bounds__(32)
+k_he_ion(int B, int lanes, const double* __restrict__ T, const double* __restrict__ hfrac,
+         const double* __restrict__ vs, const double* __restrict__ rs, const double* __restrict__ rhos,
+         int sstride, const double* __restrict__ r, int nr, const double* __restrict__ v,
+         const double* __restrict__ rho, const double* __restrict__ f_h, pwb_o_opts o,
+         const LsodaTables* __restrict__ tab, double* work, double* f_he, double* scal, int* status) {
+  if ((int)threadIdx.x >= lanes) return;
+  const int b = blockIdx.x * lanes + threadIdx.x;
+  if (b >= B) return;
+  if (status[b] != PW_OK) {
+    const double nan_ = nan("");
+    for (int i = 0; i < nr; ++i) f_he[(size_t)b * nr + i] = nan_;
+    for (int k = 0; k < 4; ++k) scal[(size_t)b * 4 + k] = 0.0;
+    return;
+  }
+  HeIonParams p;
+  p.T = T[b]; p.h_fraction = hfrac[b];
+  p.vs = vs[(size_t)b * sstride]; p.rs = rs[(size_t)b * sstride]; p.rhos = rhos[(size_t)b * sstride];
+  p.r_pl = o.planet_radius; p.y0 = o.initial_f_o_ion;
+  p.relax = o.relax_solution; p.max_n_relax = o.max_n_relax; p.convergence = o.convergence;
+  for (int k = 0; k < 3; ++k) p.rates[k] = o.rates[k];
+  p.method = o.method; p.rtol = o.rtol; p.atol = o.atol; p.first_step = o.first_step; p.max_step = o.max_step;
+  double* wb = work + (size_t)b * kOWorkPerRadius * nr;
+  OWork w{wb, wb + nr, wb + 2 * nr, wb + 3 * nr, wb + 4 * nr, wb + 5 * nr, wb + 6 * nr};
+  int st = PW_OK;
+  he_ion_fraction_model(p, *tab, r, v + (size_t)b * nr, rho + (size_t)b * nr, f_h + (size_t)b * nr, nr, w,
+                        f_he + (size_t)b * nr, scal + (size_t)b * 4, &st);
+  if (st != PW_OK) status[b] = st;
 }
 
 // carbon.ion_fraction: one thread per model (LSODA / Radau / RK45 replica), `lanes` models per warp
@@ -1079,6 +1111,25 @@ int pwb_o_ion_fraction_batch(pwb_ctx* c, int B, const double* d_T, const double*
   k_oxygen<<<(B + lanes - 1) / lanes, 32, 0, (cudaStream_t)stream>>>(
       B, lanes, d_T, d_hfrac, d_vs, d_rs, d_rhos, sstride, d_r, Nr, d_v, d_rho, d_f_h, d_f_he_ion, *o,
       c->lsoda_tab.as<LsodaTables>(), c->o_work.as<double>(), d_f_o, d_scal, d_rates, d_status);
+  c->launches++;
+  PWB_CUDA(c, cudaGetLastError());
+  return 0;
+}
+
+int pwb_he_ion_fraction_batch(pwb_ctx* c, int B, const double* d_T, const double* d_hfrac, const double* d_vs,
+                              const double* d_rs, const double* d_rhos, int sstride, const double* d_r, int Nr,
+                              const double* d_v, const double* d_rho, const double* d_f_h,
+                              const pwb_heion_opts* o, double* d_f_he_ion, double* d_scal, int* d_status,
+                              void* stream) {
+  if (!c) return -1;
+  if (B <= 0) return 0;
+  if (Nr < 2) return fail(c, "pwb_he_ion_fraction_batch: radius profile needs >= 2 points");
+  if (o->method < 0 || o->method > 2) return fail(c, "pwb_he_ion_fraction_batch: unsupported method");
+  if (c->o_work.ensure(sizeof(double) * kOWorkPerRadius * (size_t)Nr * B)) return fail(c, "out of device memory");
+  int lanes = (int)std::min<long long>(32, std::max<long long>(1, ((long long)B + 4LL * c->sm_count - 1) / (4LL * c->sm_count)));
+  k_he_ion<<<(B + lanes - 1) / lanes, 32, 0, (cudaStream_t)stream>>>(
+      B, lanes, d_T, d_hfrac, d_vs, d_rs, d_rhos, sstride, d_r, Nr, d_v, d_rho, d_f_h, *o,
+      c->lsoda_tab.as<LsodaTables>(), c->o_work.as<double>(), d_f_he_ion, d_scal, d_status);
   c->launches++;
   PWB_CUDA(c, cudaGetLastError());
   return 0;

@@ -97,6 +97,8 @@ enum {
   // carbon.radiative_processes: phi_ci, phi_cii, a_ci, a_cii, a_h_ci, a_h_cii, a_he
   PW_SC_C_PHI1 = 16, PW_SC_C_PHI2 = 17, PW_SC_C_A1 = 18, PW_SC_C_A2 = 19, PW_SC_C_AH1 = 20, PW_SC_C_AH2 = 21,
   PW_SC_C_AHE = 22,
+  // helium.radiative_processes(combined_ionization=True): phi, a_he (a_h is PW_SC_HE_AH1)
+  PW_SC_HEI_PHI = 24, PW_SC_HEI_A = 25,
   PW_SC_COUNT = 32
 };
 
@@ -165,7 +167,7 @@ PW_HD void sed_setup(const double* __restrict__ wl, const double* __restrict__ f
 
   // ---- helium.radiative_processes (helium.py:85-154)
   // singlet cut [:i1]
-  double q_fa1 = 0, q_f1 = 0, q_fah1 = 0, q_phi1 = 0;
+  double q_fa1 = 0, q_f1 = 0, q_fah1 = 0, q_phi1 = 0, q_fat = 0, q_phit = 0;
   for (int j = PW_TID; j < i1; j += PW_NT) {
     const double w = simpson_weight(i1, j, X);
     const double a1 = sigma_he_singlet(wl[j]);
@@ -177,7 +179,11 @@ PW_HD void sed_setup(const double* __restrict__ wl, const double* __restrict__ f
     q_f1 += w * flux[j];
     q_fah1 += w * (flux[j] * sigma_h(wl[j]));
     q_phi1 += w * (flux[j] * a1 / e_erg);
+    const double at = sigma_he_total(wl[j]);  // combined_ionization=True branch (helium.py:160-177)
+    q_fat += w * (flux[j] * at);
+    q_phit += w * (flux[j] * at / e_erg);
   }
+  const double s_fat = block_sum(q_fat, red), s_phit = block_sum(q_phit, red);
   const double s_fa1 = block_sum(q_fa1, red), s_f1 = block_sum(q_f1, red),
                s_fah1 = block_sum(q_fah1, red), s_phi1 = block_sum(q_phi1, red);
   // hydrogen cut [:i0] for a_h_3
@@ -252,6 +258,8 @@ PW_HD void sed_setup(const double* __restrict__ wl, const double* __restrict__ f
   }
 
   if (PW_TID == 0) {
+    scalars[PW_SC_HEI_PHI] = fabs(s_phit);
+    scalars[PW_SC_HEI_A] = fabs(s_fat / s_f1);
     scalars[PW_SC_C_PHI1] = fabs(c_res[0][3]);
     scalars[PW_SC_C_PHI2] = fabs(c_res[1][3]);
     scalars[PW_SC_C_A1] = fabs(c_res[0][1] / c_res[0][0]);

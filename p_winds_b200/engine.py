@@ -95,7 +95,8 @@ class Engine:
                 'he_a_3': v[5], 'he_a_h_1': v[6], 'he_a_h_3': v[7], 'n_cut_h': int(v[8]),
                 'i1': int(v[9]), 'i0': int(v[10]), 'o_phi': v[11], 'o_a': v[12], 'o_a_h': v[13],
                 'o_a_he': v[14], 'c_phi_1': v[16], 'c_phi_2': v[17], 'c_a_1': v[18], 'c_a_2': v[19],
-                'c_a_h_1': v[20], 'c_a_h_2': v[21], 'c_a_he': v[22]}
+                'c_a_h_1': v[20], 'c_a_h_2': v[21], 'c_a_he': v[22], 'hei_phi': v[24], 'hei_a_he': v[25],
+                'hei_a_h': v[6]}
 
     # ------------------------------------------------------------------- parker
     def parker_structure(self, r):
@@ -200,6 +201,21 @@ class Engine:
             _ptr(rho), _ptr(f_h), _ptr(f_he), C.byref(opts), _ptr(f_o), _ptr(scal), _ptr(rates),
             _ptr(status), self._stream()))
         return {'f_o': f_o, 'scal': scal, 'rates': rates, 'status': status}
+
+    def he_ion_fraction_batch(self, T, h_fraction, vs, rs, rhos, r, v, rho, f_h, opts, status=None):
+        """helium.ion_fraction for B models (helium.py:789-1032); `opts` = Engine.o_opts(planet_radius,
+        (phi_he, a_he, a_h, 0), initial_f_o_ion=initial_f_he_ion, ...)."""
+        T, hf, vs, rs, rhos, r = (self.dev(x).reshape(-1) for x in (T, h_fraction, vs, rs, rhos, r))
+        B, nr = T.numel(), r.numel()
+        v, rho, f_h = (self.dev(x).reshape(B, nr) for x in (v, rho, f_h))
+        f = torch.empty((B, nr), dtype=torch.float64, device=self.device)
+        scal = torch.empty((B, 4), dtype=torch.float64, device=self.device)
+        if status is None:
+            status = torch.zeros(B, dtype=torch.int32, device=self.device)
+        self._check(self.lib.pwb_he_ion_fraction_batch(
+            self.ctx, B, _ptr(T), _ptr(hf), _ptr(vs), _ptr(rs), _ptr(rhos), 1, _ptr(r), nr, _ptr(v),
+            _ptr(rho), _ptr(f_h), C.byref(opts), _ptr(f), _ptr(scal), _ptr(status), self._stream()))
+        return {'f_he_ion': f, 'scal': scal, 'status': status}
 
     # ------------------------------------------------------------------- carbon
     @staticmethod

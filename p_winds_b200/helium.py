@@ -5,8 +5,8 @@ import numpy as np
 from . import tools
 from .engine import default_engine, STATUS_MESSAGES, Engine
 
-__all__ = ['radiative_processes', 'radiative_processes_mono', 'recombination', 'collision',
-           'population_fraction']
+__all__ = ['radiative_processes', 'radiative_processes_mono', 'recombination', 'recombination_all',
+           'collision', 'charge_transfer', 'population_fraction', 'ion_fraction']
 
 _RATE_KEYS = ['ionization_1', 'ionization_3', 'recombination_1', 'recombination_3',
               'radiative_transition', 'transition_1_to_3', 'transition_3_to_21s',
@@ -37,13 +37,12 @@ def _sigma_h(wl):
 def radiative_processes(spectrum_at_planet, combined_ionization=False):
     """phi_1, phi_3, a_1, a_3, a_h_1, a_h_3 (helium.py:24-154), computed on the GPU
     when the SED is uploaded."""
-    if combined_ionization:
-        raise NotImplementedError('combined_ionization feeds helium.ion_fraction, which is '
-                                  'outside the He-triplet hot path')
     eng = default_engine()
     wl, fl = tools.spectrum_to_cgs(spectrum_at_planet)
     eng.set_sed_cached(wl, fl)
     s = eng.sed_scalars()
+    if combined_ionization:   # phi, a_he, a_h (helium.py:160-177)
+        return s['hei_phi'], s['hei_a_he'], s['hei_a_h']
     return (s['he_phi_1'], s['he_phi_3'], s['he_a_1'], s['he_a_3'], s['he_a_h_1'], s['he_a_h_3'])
 
 
@@ -118,3 +117,38 @@ def population_fraction(radius_profile, velocity, density, hydrogen_ion_fraction
         rr = o['rates'][0].cpu().numpy()
         return f1, f3, {k: rr[i] for i, k in enumerate(_RATE_KEYS)}
     return f1, f3
+
+
+def recombination_all(temperature):
+    """He II -> He I without singlet / triplet distinction, cm3/s (helium.py:294-313)."""
+    return 4.6E-12 * (temperature / 300) ** (-0.64)
+
+
+def charge_transfer(temperature):
+    """(He + H+ -> He+, He+ + H -> He) in cm3/s (helium.py:384-409)."""
+    ct_rate_hep_h = 1.25E-15 * (300 / temperature) ** (-0.25)
+    ct_rate_he_hp = 1.75E-11 * (300 / temperature) ** 0.75 * np.exp(-128000 / temperature)
+    return ct_rate_he_hp, ct_rate_hep_h
+
+
+def ion_fraction(radius_profile, velocity, density, hydrogen_ion_fraction, planet_radius, temperature,
+                 h_fraction, speed_sonic_point, radius_sonic_point, density_sonic_point,
+                 spectrum_at_planet, initial_f_he_ion=0.0, relax_solution=False, convergence=0.01,
+                 max_n_relax=10, method='Radau', **options_solve_ivp):
+    """Fraction of ionised helium versus radius (helium.py:789-1032), same arguments, units and
+    exceptions as the reference.  `method`: 'Radau' (default), 'odeint' or 'RK45'."""
+    phi, a_he, a_h = radiative_processes(spectrum_at_planet, combined_ionization=True)
+    opt = dict(options_solve_ivp)
+    extra = set(opt) - {'rtol', 'atol', 'first_step', 'max_step'}
+    if extra:
+        raise ValueError('unsupported solve_ivp options on the GPU path: %s' % sorted(extra))
+    eng = default_engine()
+    opts = Engine.o_opts(planet_radius, (phi, a_he, a_h, 0.0), 0.0, initial_f_he_ion, relax_solution is True,
+                         convergence, max_n_relax, method, opt.get('rtol', 1e-3), opt.get('atol', 1e-6),
+                         opt.get('first_step'), opt.get('max_step'))
+    r = np.ascontiguousarray(radius_profile, dtype=float)
+    o = eng.he_ion_fraction_batch([temperature], [h_fraction], [speed_sonic_point], [radius_sonic_point],
+                                  [density_sonic_point], r, velocity, density, hydrogen_ion_fraction, opts)
+    if int(o['status'].cpu()[0]) == 2:
+        raise RuntimeError(STATUS_MESSAGES[2] if method == 'odeint' else STATUS_MESSAGES[1])
+    return o['f_he_ion'][0].cpu().numpy()

@@ -206,6 +206,30 @@ int hs_o_ion_fraction(const double* model, const double* opts, const double* rat
 }
 }
 
+#include "../../p_winds_b200/csrc/pw_heion.cuh"
+
+extern "C" {
+// model: [T, h_fraction, vs, rs, rhos]; opts: [r_pl, y0, relax, max_n_relax, convergence, method, rtol, atol,
+//   first_step, max_step]; rates[3]
+int hs_he_ion_fraction(const double* model, const double* opts, const double* rates, const double* r,
+                       const double* v, const double* rho, const double* f_h, int nr, double* f, double* scal) {
+  static LsodaTables tab;
+  static bool init = false;
+  if (!init) { lsoda_tables_init(&tab); init = true; }
+  HeIonParams p;
+  p.T = model[0]; p.h_fraction = model[1]; p.vs = model[2]; p.rs = model[3]; p.rhos = model[4];
+  p.r_pl = opts[0]; p.y0 = opts[1]; p.relax = (int)opts[2]; p.max_n_relax = (int)opts[3]; p.convergence = opts[4];
+  p.method = (int)opts[5]; p.rtol = opts[6]; p.atol = opts[7]; p.first_step = opts[8]; p.max_step = opts[9];
+  for (int i = 0; i < 3; ++i) p.rates[i] = rates[i];
+  std::vector<double> buf(kOWorkPerRadius * nr);
+  double* b = buf.data();
+  OWork w{b, b + nr, b + 2 * nr, b + 3 * nr, b + 4 * nr, b + 5 * nr, b + 6 * nr};
+  int status = 0;
+  he_ion_fraction_model(p, tab, r, v, rho, f_h, nr, w, f, scal, &status);
+  return status;
+}
+}
+
 #include "../../p_winds_b200/csrc/pw_carbon.cuh"
 
 extern "C" {

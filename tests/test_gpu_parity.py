@@ -667,3 +667,28 @@ def test_carbon_reference_signature(eng, oracle):
         if m.any():
             assert np.max(_rel(rates['recombination_CII'][m], d['rates'][i][2][m])) < 100 * tol2
     assert n_fail == 2
+
+
+def test_helium_ion_fraction_reference_signature(eng):
+    """helium.ion_fraction on the GPU (k_he_ion) against the unmodified reference
+    (tests/golden/helium_ion.npz): scalars of radiative_processes(combined_ionization=True) to
+    1e-10, fractions inside the reference's noise envelope + solver tolerance."""
+    from p_winds_b200 import helium
+    d = golden('helium_ion')
+    g = golden('solar_sed')
+    sp = {'wavelength': g['wavelength'], 'flux_lambda': g['flux_lambda'], 'wavelength_unit': 'angstrom',
+          'flux_unit': 'erg / (s cm2 angstrom)'}
+    scal = np.array(helium.radiative_processes(sp, combined_ionization=True))
+    assert np.max(_rel(scal, d['scalars'])) < 1e-10
+    for i in range(len(d['T0'])):
+        kw = dict(relax_solution=bool(d['relax'][i]))
+        if str(d['method'][i]) == 'odeint':
+            kw['method'] = 'odeint'
+        else:
+            kw.update(rtol=float(d['rtol'][i]), atol=float(d['atol'][i]))
+        f = helium.ion_fraction(d['r'], d['v'][i], d['rho'][i], d['f_h'][i], 1.39, float(d['T0'][i]),
+                                float(d['h_fraction'][i]), float(d['vs'][i]), float(d['rs'][i]),
+                                float(d['rhos'][i]), sp, **kw)
+        floor = 1e-5 if str(d['method'][i]) == 'odeint' else max(1e-6, float(d['rtol'][i]))
+        err = np.max(_rel(f[1:], d['f_he_ion'][i][1:]))
+        assert err < 4.0 * float(d['noise'][i]) + floor, (i, err)

@@ -334,3 +334,35 @@ def test_carbon_stage_against_reference(hostsim):
         e3 = np.max(np.abs(f3[big] / d['f_ciii'][i][big] - 1))
         assert e2 < tol2 and e3 < tol3, (i, e2, tol2, e3, tol3)
     assert n_fail == 2
+
+
+def _heion_tolerance(d, i):
+    """4 x the reference's own 1-ulp noise (fixture key `noise`) + the solver's relative tolerance
+    (Radau: the step sequence either survives last-bit differences, ~1e-9, or it does not, ~rtol)."""
+    floor = 1e-5 if str(d['method'][i]) == 'odeint' else max(1e-6, float(d['rtol'][i]))
+    return 4.0 * float(d['noise'][i]) + floor
+
+
+def test_helium_ion_fraction_stage_against_reference(hostsim):
+    """he_ion_fraction_model on the host build against the unmodified reference's
+    helium.ion_fraction (tests/golden/helium_ion.npz)."""
+    d = golden('helium_ion')
+    rates = np.ascontiguousarray(d['scalars'])
+    meth = {'Radau': 0, 'odeint': 1}
+    errs = []
+    for i in range(len(d['T0'])):
+        model = np.array([d['T0'][i], d['h_fraction'][i], d['vs'][i], d['rs'][i], d['rhos'][i]], dtype=float)
+        opts = np.array([1.39, 0.0, d['relax'][i], 10, 0.01, meth[str(d['method'][i])], d['rtol'][i], d['atol'][i],
+                         0., 0.], dtype=float)
+        f, scal = np.zeros(100), np.zeros(4)
+        st = hostsim.hs_he_ion_fraction(P(model), P(opts), P(rates), P(np.ascontiguousarray(d['r'])),
+                                        P(np.ascontiguousarray(d['v'][i])), P(np.ascontiguousarray(d['rho'][i])),
+                                        P(np.ascontiguousarray(d['f_h'][i])), 100, P(f), P(scal))
+        assert st == 0
+        err = np.max(np.abs(f[1:] / d['f_he_ion'][i][1:] - 1))
+        errs.append(err)
+        assert err < _heion_tolerance(d, i), (i, err, _heion_tolerance(d, i))
+    # where the reference's step sequence is stable under 1-ulp noise the replica reproduces it
+    # to rounding -- the realistic-RHS counterpart of the trace tests in test_hostsim_solvers.py
+    stable = [e for e, nz, m in zip(errs, d['noise'], d['method']) if nz < 1e-8 and str(m) == 'Radau']
+    assert len(stable) >= 2 and min(stable) < 1e-7

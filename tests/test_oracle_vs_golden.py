@@ -186,3 +186,17 @@ def test_carbon_oracle_matches_reference(oracle, sed):
         assert o['status'] == d['status'][i], i
         assert np.array_equal(o['f_cii'], d['f_cii'][i], equal_nan=True), i
         assert np.array_equal(o['f_ciii'], d['f_ciii'][i], equal_nan=True), i
+
+
+def test_helium_ion_fraction_oracle_matches_reference(oracle, sed):
+    """SURVEY 8(f-3), helium.ion_fraction (helium.py:789-1032): bit for bit."""
+    d = golden('helium_ion')
+    assert np.array_equal(np.array(oracle.he_radiative_processes_combined(sed)), d['scalars'])
+    for i in range(len(d['T0'])):
+        kw = {} if d['method'][i] == 'odeint' else dict(rtol=float(d['rtol'][i]), atol=float(d['atol'][i]))
+        o = oracle.he_ion_fraction(d['r'], d['v'][i], d['rho'][i], d['f_h'][i], 1.39, float(d['T0'][i]),
+                                   float(d['h_fraction'][i]), float(d['vs'][i]), float(d['rs'][i]),
+                                   float(d['rhos'][i]), sed=sed, relax_solution=bool(d['relax'][i]),
+                                   method=str(d['method'][i]), **kw)
+        assert o['status'] == d['status'][i] == 0
+        assert np.array_equal(o['f_he_ion'], d['f_he_ion'][i]), i
