@@ -692,3 +692,70 @@ def test_helium_ion_fraction_reference_signature(eng):
         floor = 1e-5 if str(d['method'][i]) == 'odeint' else max(1e-6, float(d['rtol'][i]))
         err = np.max(_rel(f[1:], d['f_he_ion'][i][1:]))
         assert err < 4.0 * float(d['noise'][i]) + floor, (i, err)
+
+
+def test_metals_chain_config5_lines_on_gpu(eng, oracle, sed):
+    """BASELINE configs[4] names C II and O I lines next to He 10830.  Here their number
+    densities come from the GPU as well: H -> Parker -> He populations -> O II and C II / C III
+    fractions (Radau) -> n(O I), n(C II) -> radiative transfer at the O I and C II lines, for a
+    small batch, against the oracle running the same chain.  Tight solver tolerances on both
+    sides, so that the comparison is meaningful per model (tier P2): spectra <= 1e-5 relative."""
+    from p_winds_b200.engine import Engine
+    from p_winds_b200 import lines
+    T = np.array([9100., 11000.])
+    md = np.array([10 ** 10.27, 10 ** 10.8])
+    hf = np.array([0.9, 0.9])
+    ho, heo, _ = _opts(eng, True, False)
+    mu0 = (1 + 4 * (1 - hf) / hf) / (1 + (1 - hf) / hf)
+    h = eng.h_ion_fraction_batch(T, md, hf, mu0, R, ho)
+    vs, rs, rhos = (h['scal'][:, k].contiguous() for k in (1, 2, 3))
+    he = eng.he_population_batch(T, hf, vs, rs, rhos, R, h['v'], h['rho'], h['f_r'], heo, status=h['status'].clone())
+    f_he_ion = 1 - he['f_1'] - he['f_3']
+    sc = eng.sed_scalars()
+    tight = dict(relax_solution=True, method='Radau', rtol=1e-10, atol=1e-13)
+    oo = Engine.o_opts(1.39, [sc[k] for k in ('o_phi', 'o_a', 'o_a_h', 'o_a_he')], **tight)
+    co = Engine.c_opts(1.39, [sc[k] for k in ('c_phi_1', 'c_phi_2', 'c_a_1', 'c_a_2', 'c_a_h_1', 'c_a_h_2', 'c_a_he')],
+                       **tight)
+    ox = eng.o_ion_fraction_batch(T, hf, vs, rs, rhos, R, h['v'], h['rho'], h['f_r'], f_he_ion, oo,
+                                  status=he['status'].clone())
+    ca = eng.c_ion_fraction_batch(T, hf, vs, rs, rhos, R, h['v'], h['rho'], h['f_r'], f_he_ion, co,
+                                  status=he['status'].clone())
+    assert (ox['status'].cpu().numpy() == 0).all() and (ca['status'].cpu().numpy() == 0).all()
+    o_frac, c_frac = 10 ** (8.69 - 12.00), 10 ** (8.43 - 12.00)
+    m_p = 1.67262192369e-27
+    r_si = R * 1.39 * 71492000
+    o1, c2 = lines.o_i_properties(), lines.c_ii_properties()
+    wl_o = np.linspace(1300.9, 1307.1, 120) * 1e-10
+    wl_c = np.linspace(1332.9, 1337.1, 120) * 1e-10
+    geo = golden('geometry')
+    hfd, rho_d, rhos_d = eng.dev(hf)[:, None], h['rho'], rhos[:, None]
+    v_si = h['v'] * vs[:, None] * 1000
+    n_o = rho_d * rhos_d * o_frac / (hfd + 4 * (1 - hfd) + 16 * o_frac) / 1.67262192369e-24 * (1 - ox['f_o']) * 1e6
+    n_c = rho_d * rhos_d * c_frac / (hfd + 4 * (1 - hfd) + 12 * c_frac) / 1.67262192369e-24 * ca['f_cii'] * 1e6
+    s_o = eng.rt2d_batch(n_o, v_si, T, wl_o, Engine.rt_opts(o1[:3], o1[3:6], o1[6:9], 16 * m_p)).cpu().numpy()
+    s_c = eng.rt2d_batch(n_c, v_si, T, wl_c, Engine.rt_opts(c2[:3], c2[3:6], c2[6:9], 12 * m_p)).cpu().numpy()
+    he_rates = oracle.he_radiative_processes(sed)
+    for b in range(2):
+        oh = oracle.h_ion_fraction(R, 1.39, T[b], hf[b], md[b], 0.73, mu0[b], sed=sed, exact_phi=True,
+                                   relax_solution=True, rtol=1e-10, atol=1e-13)
+        ovs = oracle.sound_speed(T[b], oh['mu_bar'])
+        ors = oracle.radius_sonic_point(0.73, ovs)
+        orhos = oracle.density_sonic_point(md[b], ors, ovs)
+        ov, orho = oracle.structure(R * 1.39 / ors)
+        ohe = oracle.he_population(R, ov, orho, oh['f_r'], 1.39, T[b], hf[b], ovs, ors, orhos, rates=he_rates,
+                                   initial_state=np.array([1., 0.]), relax_solution=True, method='LSODA',
+                                   rtol=1e-10, atol=1e-16)
+        fhe = 1 - ohe['f_1'] - ohe['f_3']
+        kw = dict(relax_solution=True, method='Radau', rtol=1e-10, atol=1e-13)
+        oo_ = oracle.o_ion_fraction(R, ov, orho, oh['f_r'], fhe, 1.39, T[b], hf[b], ovs, ors, orhos, sed=sed, **kw)
+        oc_ = oracle.c_ion_fraction(R, ov, orho, oh['f_r'], fhe, 1.39, T[b], hf[b], ovs, ors, orhos, sed=sed, **kw)
+        assert np.max(_rel(ox['f_o'][b].cpu().numpy()[1:], oo_['f_o'][1:])) < 1e-6
+        assert np.max(_rel(ca['f_cii'][b].cpu().numpy()[1:], oc_['f_cii'][1:])) < 1e-6
+        on_o = orho * orhos * o_frac / (hf[b] + 4 * (1 - hf[b]) + 16 * o_frac) / 1.67262192369e-24 * (1 - oo_['f_o']) * 1e6
+        on_c = orho * orhos * c_frac / (hf[b] + 4 * (1 - hf[b]) + 12 * c_frac) / 1.67262192369e-24 * oc_['f_cii'] * 1e6
+        ref_o = oracle.radiative_transfer_2d(geo['i0'], geo['r_map'], r_si, on_o, ov * ovs * 1000, np.array(o1[:3]),
+                                             np.array(o1[3:6]), np.array(o1[6:9]), wl_o, T[b], 16 * m_p)
+        ref_c = oracle.radiative_transfer_2d(geo['i0'], geo['r_map'], r_si, on_c, ov * ovs * 1000, np.array(c2[:3]),
+                                             np.array(c2[3:6]), np.array(c2[6:9]), wl_c, T[b], 12 * m_p)
+        assert np.max(_rel(s_o[b], ref_o)) < 1e-5 and np.max(_rel(s_c[b], ref_c)) < 1e-5, b
+        assert ref_c.min() < 0.999 * ref_c.max()      # the C II lines are actually there
