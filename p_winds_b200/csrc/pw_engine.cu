@@ -82,9 +82,6 @@ struct pwb_ctx {
   int geo_nr = 0;
   DevBuf geo_r;
   // internal streams for the chunked forward pipeline
-  static const int kMaxChunks = 4;
-  cudaStream_t streams[kMaxChunks] = {nullptr, nullptr, nullptr, nullptr};
-  cudaEvent_t ev_start = nullptr, ev_done[kMaxChunks] = {nullptr, nullptr, nullptr, nullptr};
   // scratch
   DevBuf h_state, h_fields, he_order, he_key, he_work, o_work, rt_ncol, rt_sums, rt_partial, rt_tau, fw_f, fw_scal, fw_he, fw_n, fw_v, fw_T, misc;
 };
@@ -905,11 +902,6 @@ int pwb_create(int device, pwb_ctx** out) {
   k_lsoda_tables<<<1, 32>>>(c->lsoda_tab.as<LsodaTables>());
   c->launches++;
   if (cudaDeviceSynchronize() != cudaSuccess) { delete c; return -6; }
-  for (int i = 0; i < pwb_ctx::kMaxChunks; ++i) {
-    cudaStreamCreateWithFlags(&c->streams[i], cudaStreamNonBlocking);
-    cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming);
-  }
-  cudaEventCreateWithFlags(&c->ev_start, cudaEventDisableTiming);
   cudaFuncSetAttribute(k_h_fields, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   cudaFuncSetAttribute(k_rt_los, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
   cudaFuncSetAttribute(k_rt_formal_tau, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
@@ -926,11 +918,6 @@ void pwb_destroy(pwb_ctx* c) {
   for (auto& G : c->geo) {
     G.px_lo.release(); G.px_whi.release(); G.px_wlo.release(); G.px_i0.release(); G.px_meta.release();
   }
-  for (int i = 0; i < pwb_ctx::kMaxChunks; ++i) {
-    if (c->streams[i]) cudaStreamDestroy(c->streams[i]);
-    if (c->ev_done[i]) cudaEventDestroy(c->ev_done[i]);
-  }
-  if (c->ev_start) cudaEventDestroy(c->ev_start);
   delete c;
 }
 

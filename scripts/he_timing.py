@@ -1,9 +1,15 @@
+"""Developer script: per-model start / end times of k_helium by schedule segment.
+
+Needs the timing build of the library:
+    PW_DEFS="-DPW_HE_TIMING" PW_OUT=build/lib_timing.so ./build.sh
+(the per-model slots n_relax and the spare one then carry globaltimer values)."""
 import os, sys
 import numpy as np, torch
-sys.path.insert(0, '/root/repo')
-os.environ['PWB_LIB_PATH'] = '/root/repo/build/lib_timing.so'
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+os.environ['PWB_LIB_PATH'] = os.path.join(ROOT, 'build', 'lib_timing.so')
 from p_winds_b200.engine import Engine
-g = np.load('/root/repo/tests/golden/solar_sed.npz')
+g = np.load(os.path.join(ROOT, 'tests/golden/solar_sed.npz'))
 r = np.logspace(0, np.log10(20), 100)
 eng = Engine(0); eng.set_sed(g['wavelength'], g['flux_lambda']); sc = eng.sed_scalars()
 rates = [sc[k] for k in ('he_phi_1', 'he_phi_3', 'he_a_1', 'he_a_3', 'he_a_h_1', 'he_a_h_3')]
@@ -21,7 +27,8 @@ for rep in range(2):
 sc4 = he['scal'].cpu().numpy()
 t0, t1, nfe = sc4[:, 0], sc4[:, 3], sc4[:, 1]
 base = t0.min()
-key = (h['scal'][:, 3] * h['scal'][:, 2]).cpu().numpy()
+dr = np.diff(r); dr = np.concatenate((dr, dr[-1:]))
+key = (h['scal'][:, 3] * (h['rho'] * eng.dev(dr)[None, :]).sum(1)).cpu().numpy()   # column-density proxy of k_he_key
 order = np.argsort(-key, kind='stable')
 B = T.size
 frac = [0.05, 0.25, 0.40, 0.30]; lanes = [1, 2, 4, 8]
