@@ -320,9 +320,28 @@ def run_ours(args):
                                                    'uses a 12-instruction exp' % (px, eng.n_active_pixels())},
     }
     dom = max(kernels, key=lambda k: kernels[k]['ms'])
+    # DRAM bytes of the dominant kernel per launch, from the committed `ncu --set full` capture
+    # (profiles/r1_ncu_full_summary.csv: dram__bytes_read.sum + dram__bytes_write.sum); null if absent
+    traffic = None
+    try:
+        import csv
+        with open(os.path.join(ROOT, 'profiles', 'r1_ncu_full_summary.csv')) as fh:
+            rows = list(csv.reader(fh))
+        hdr = rows[0]
+        for row in rows[1:]:
+            if 'k_helium' in row[0]:
+                def _bytes(cell):
+                    val, unit = cell.split()[:2]
+                    return float(val) * {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}[unit]
+                traffic = _bytes(row[hdr.index('dram__bytes_read.sum')]) + _bytes(row[hdr.index('dram__bytes_write.sum')])
+                break
+    except Exception:
+        traffic = None
     roofline = {'bound': 'fp64', 'kernel': dom, 'achieved': kernels[dom]['achieved_tflops'],
                 'peak': fp64_peak, 'unit': 'TFLOP/s', 'frac': kernels[dom]['achieved_tflops'] / fp64_peak,
-                'traffic': None,
+                'traffic': traffic,
+                'traffic_source': 'profiles/r1_ncu_full_summary.csv (ncu --set full capture of k_helium, bytes per launch); '
+                                  'not an HBM-bound kernel' if traffic is not None else None,
                 'peak_source': 'FP64 DFMA microbenchmark run in this process (pwb_fp64_peak); '
                                'MEASURED_PEAKS.json has no FP64 figure; no tensor cores on this path',
                 'whole_step': {'flop': w_h + w_he + w_rt,

@@ -155,6 +155,13 @@ int pwb_h_ion_fraction_batch(pwb_ctx* ctx, int B, const double* d_T, const doubl
                              const pwb_h_opts* opts, double* d_f_r, double* d_v, double* d_rho,
                              double* d_scal, int* d_status, void* stream);
 
+/* ---- hydrogen.ion_fraction(return_rates=True) (hydrogen.py:538-561): call right after
+ *      pwb_h_ion_fraction_batch with the same batch and options (exact_phi required, as in the
+ *      reference).  d_rates [B][2][Nr] = photoionization, recombination (1/s); NaN for failed models. */
+int pwb_h_rates_batch(pwb_ctx* ctx, int B, const double* d_T, const double* d_mdot, const double* d_hfrac,
+                      const double* d_mu0, const double* d_r, int Nr, const pwb_h_opts* opts, double* d_rates,
+                      void* stream);
+
 /* ---- helium.population_fraction, batched (helium.py:413-785) --------------------
  * inputs : d_T, d_hfrac, d_vs, d_rs, d_rhos [B] (d_vs.. may alias columns of d_scal
  *          with stride `scal_stride` doubles; pass 1 for dense arrays);

@@ -284,6 +284,22 @@ def oxygen_fixture(sp):
     np.savez_compressed(os.path.join(OUT, 'oxygen.npz'), scalars=scal, r=R, **keep)
 
 
+def hydrogen_rates_fixture(sp):
+    """tests/golden/hydrogen_rates.npz: hydrogen.ion_fraction(..., return_rates=True)."""
+    cases = []
+    for (T0, md, relax, tidal) in [(9100., 10 ** 10.27, True, False), (9100., 1e11, False, False),
+                                   (11500., 10 ** 10.8, True, True)]:
+        kw = dict(star_mass=M_STAR, semimajor_axis=A_AU) if tidal else {}
+        f_r, mu, rates = hydrogen.ion_fraction(R, R_PL, T0, 0.9, md, M_PL, 1.2, spectrum_at_planet=sp,
+                                               initial_f_ion=0.0, relax_solution=relax, exact_phi=True,
+                                               return_mu=True, return_rates=True, **kw)
+        cases.append(dict(T0=T0, mdot=md, relax=int(relax), tidal=int(tidal), f_r=f_r, mu_bar=mu,
+                          photoionization=rates['photoionization'], recombination=rates['recombination']))
+        print('hydrogen rates', T0, '%.3e' % md, relax, tidal, flush=True)
+    np.savez_compressed(os.path.join(OUT, 'hydrogen_rates.npz'), r=R,
+                        **{k: np.array([c[k] for c in cases]) for k in cases[0]})
+
+
 def heion_fixture(sp):
     """tests/golden/helium_ion.npz: helium.radiative_processes(combined_ionization=True) and
     helium.ion_fraction of the unmodified reference (default 'Radau', and 'odeint')."""
@@ -392,7 +408,9 @@ def carbon_fixture(sp):
 
 
 if __name__ == '__main__':
-    if len(sys.argv) > 1 and sys.argv[1] == 'heion':
+    if len(sys.argv) > 1 and sys.argv[1] == 'hrates':
+        hydrogen_rates_fixture(spectrum_dict())
+    elif len(sys.argv) > 1 and sys.argv[1] == 'heion':
         heion_fixture(spectrum_dict())
     elif len(sys.argv) > 1 and sys.argv[1] == 'carbon':
         carbon_fixture(spectrum_dict())
@@ -403,3 +421,4 @@ if __name__ == '__main__':
         oxygen_fixture(spectrum_dict())
         carbon_fixture(spectrum_dict())
         heion_fixture(spectrum_dict())
+        hydrogen_rates_fixture(spectrum_dict())

@@ -360,6 +360,15 @@ def h_ion_fraction(r, r_pl, T, h_fraction, mdot, m_pl, mu_0=1.0, m_star=1.0,
                 break
     out['f_r'] = f_r
     out['mu_bar'] = mu_bar
+    if exact_phi and sed is not None:
+        # return_rates=True (hydrogen.py:538-561): photoionisation with the structure of the last
+        # normalisation, recombination with the final structure
+        fin_phi = phi_exact(sed, r_cm, rho_n * rhos, f_r, h_fraction) * (1 - f_r)
+        fvs = sound_speed(T, mu_bar)
+        frs = radius_sonic_point_tidal(m_pl, fvs, m_star, a)
+        frhos = density_sonic_point(mdot, frs, fvs)
+        _, frho_n = structure_tidal(r * r_pl / frs, fvs, frs, m_pl, m_star, a)
+        out['rates'] = {'photoionization': fin_phi, 'recombination': k2_abs * (frho_n * frhos) * f_r ** 2}
     return out
 
 

@@ -67,6 +67,7 @@ SYMBOLS = {
     'pwb_parker_structure_tidal': (_I, [_VP, _VP, _I, _D, _D, _D, _D, _D, _VP, _VP, _VP]),
     'pwb_h_ion_fraction_batch': (_I, [_VP, _I, _VP, _VP, _VP, _VP, _VP, _I, C.POINTER(HOpts),
                                       _VP, _VP, _VP, _VP, _VP, _VP]),
+    'pwb_h_rates_batch': (_I, [_VP, _I, _VP, _VP, _VP, _VP, _VP, _I, C.POINTER(HOpts), _VP, _VP]),
     'pwb_he_population_batch': (_I, [_VP, _I, _VP, _VP, _VP, _VP, _VP, _I, _VP, _I, _VP, _VP, _VP,
                                      C.POINTER(HeOpts), _VP, _VP, _VP, _VP, _VP, _VP]),
     'pwb_o_ion_fraction_batch': (_I, [_VP, _I, _VP, _VP, _VP, _VP, _VP, _I, _VP, _I, _VP, _VP, _VP, _VP,

@@ -190,6 +190,36 @@ k_h_fields(int B, int pass, const double* __restrict__ T, const double* __restri
   }
 }
 
+// hydrogen.ion_fraction(return_rates=True): one CTA per model, after the relax loop
+__global__ void __launch_bounds__(128)
+k_h_rates(int B, const double* __restrict__ T, const double* __restrict__ mdot, const double* __restrict__ hfrac,
+          const double* __restrict__ mu0, const double* __restrict__ r, int nr, pwb_h_opts o,
+          const double* __restrict__ gw, const double* __restrict__ s_h, const double* __restrict__ s_he, int n_h,
+          const HState* __restrict__ state, const double* __restrict__ fields, double* __restrict__ rates) {
+  extern __shared__ double smem[];
+  __shared__ double s_e2[32];
+  const int b = blockIdx.x;
+  if (b >= B) return;
+  if (threadIdx.x < 32) s_e2[threadIdx.x] = kExp2TabDev[threadIdx.x];
+  const HParams p = h_params(o, T[b], mdot[b], hfrac[b], mu0[b]);
+  double* out = rates + (size_t)b * 2 * nr;
+  if (state[b].status != PW_OK) {
+    for (int i = threadIdx.x; i < 2 * nr; i += blockDim.x) out[i] = nan("");
+    return;
+  }
+  SedTables t;
+  t.n_h = n_h; t.i1 = 0; t.i0 = 0; t.gw = gw; t.s_h = s_h; t.s_he = s_he;
+  double* base = smem;
+  HWork w;
+  w.rn = base; w.v = base + nr; w.rho = base + 2 * nr; w.phi = base + 3 * nr; w.tau = base + 4 * nr;
+  w.f = base + 5 * nr; w.fprev = base + 6 * nr; w.colh = base + 7 * nr; w.colhe = base + 8 * nr;
+  w.rcm = base + 9 * nr; w.red = base + 10 * nr;
+  const double* g = fields + (size_t)b * kHFieldsPerRadius * nr;
+  for (int i = threadIdx.x; i < nr; i += blockDim.x) { w.rho[i] = g[2 * nr + i]; w.f[i] = g[5 * nr + i]; }
+  __syncthreads();
+  h_rates(p, t, r, nr, w, state[b], out, (unsigned)__cvta_generic_to_shared(s_e2));
+}
+
 __global__ void __launch_bounds__(32)
 k_h_solve(int B, int lanes, int pass, const double* __restrict__ T, const double* __restrict__ mdot,
           const double* __restrict__ hfrac, const double* __restrict__ mu0, const double* __restrict__ r,
@@ -998,6 +1028,25 @@ static int launch_hydrogen(pwb_ctx* c, cudaStream_t s, int B, const double* d_T,
   }
   k_h_finish<<<B, 128, 0, s>>>(B, d_T, d_mdot, d_hfrac, d_mu0, d_r, Nr, *o, st, fields, d_f_r, d_v, d_rho, d_scal,
                                d_status);
+  c->launches++;
+  PWB_CUDA(c, cudaGetLastError());
+  return 0;
+}
+
+int pwb_h_rates_batch(pwb_ctx* c, int B, const double* d_T, const double* d_mdot, const double* d_hfrac,
+                      const double* d_mu0, const double* d_r, int Nr, const pwb_h_opts* o, double* d_rates,
+                      void* stream) {
+  if (!c) return -1;
+  if (B <= 0) return 0;
+  if (!o->exact_phi || !c->sed_ready) return fail(c, "pwb_h_rates_batch: needs exact_phi and a SED (hydrogen.py:540-543)");
+  if (c->h_state.cap < sizeof(HState) * (size_t)B || c->h_fields.cap < sizeof(double) * kHFieldsPerRadius * (size_t)Nr * B)
+    return fail(c, "pwb_h_rates_batch: call pwb_h_ion_fraction_batch with the same batch first");
+  const size_t smem = sizeof(double) * (10 * (size_t)Nr + 40);
+  if (smem > 200 * 1024) return fail(c, "pwb_h_rates_batch: radius profile too long for shared memory");
+  if (smem > 48 * 1024) PWB_CUDA(c, cudaFuncSetAttribute(k_h_rates, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_h_rates<<<B, 128, smem, (cudaStream_t)stream>>>(B, d_T, d_mdot, d_hfrac, d_mu0, d_r, Nr, *o, c->sed_gw.as<double>(),
+                                                     c->sed_sh.as<double>(), c->sed_she.as<double>(), c->sed_nh,
+                                                     c->h_state.as<HState>(), c->h_fields.as<double>(), d_rates);
   c->launches++;
   PWB_CUDA(c, cudaGetLastError());
   return 0;

@@ -141,6 +141,7 @@ struct HRhs {
 // ---------------------------------------------------------------------------------------
 struct HState {
   double mu;       // mean molecular weight the next pass normalises with
+  double mu_pass;  // ... and the one the last executed pass was normalised with (return_rates)
   double mu_bar;   // of the last solution
   double vs_amw;   // `vs` average_molecular_weight is called with (hydrogen.py:351, rebound at :480 if exact)
   int n_relax, nfev_total, n_solves, status;
@@ -153,6 +154,7 @@ struct HPassScal {
 
 PW_HD void h_state_init(const HParams& p, HState* s) {
   s->mu = p.mu0;
+  s->mu_pass = p.mu0;
   s->mu_bar = 0.0;
   s->vs_amw = sound_speed(p.T, p.mu0);
   s->n_relax = 0; s->nfev_total = 0; s->n_solves = 0; s->status = PW_OK; s->done = 0;
@@ -214,6 +216,7 @@ PW_HD void h_pass_fields(const HParams& p, const SedTables& sed, const double* _
 PW_HD void h_pass_solve(const HParams& p, const double* __restrict__ r, int nr, const HWork& w, int pass,
                         HState* s) {
   const HPassScal q = h_pass_scalars(p, s->mu);
+  s->mu_pass = s->mu;
   if (p.exact_phi) s->vs_amw = q.vs;
   const double he_h = (1 - p.h_fraction) / p.h_fraction;
   for (int i = 0; i < nr; ++i) w.fprev[i] = w.f[i];
@@ -271,6 +274,33 @@ PW_HD void h_finish(const HParams& p, const double* __restrict__ r, int nr, cons
     out.scal[4] = (double)s.n_relax; out.scal[5] = (double)s.nfev_total; out.scal[6] = (double)s.n_solves;
     out.scal[7] = 0.0;
     *out.status = status;
+  }
+}
+
+// return_rates=True of hydrogen.ion_fraction (hydrogen.py:538-561), all threads of the CTA:
+//   photoionization = radiative_processes_exact(r, rho_norm * rhos, f_r) * (1 - f_r) with the
+//                     density structure of the last normalisation (w.rho + s.mu_pass),
+//   recombination   = k2_abs * final_rho * f_r^2 with the structure of the final mu_bar.
+// w.rho must hold the last pass's rho_norm and w.f the final f_r; rates = [2][Nr].
+PW_HD void h_rates(const HParams& p, const SedTables& sed, const double* __restrict__ r, int nr, const HWork& w,
+                   const HState& s, double* rates, unsigned e2tab = 0) {
+  for (int i = PW_TID; i < nr; i += PW_NT) w.rcm[i] = r[i] * p.r_pl * (7.1492e7 / 1e-2);
+  const HPassScal q = h_pass_scalars(p, s.mu_pass);
+  PW_SYNC();
+  phi_exact(sed, w, nr, w.rho, q.rhos, w.f, p.h_fraction, e2tab);
+  const double alpha_rec = 2.59E-13 * pw_pow(p.T / 1E4, -0.7);
+  const double he_fraction = 1 - p.h_fraction;
+  const double k2_abs = p.h_fraction / (p.h_fraction + 4 * he_fraction) * alpha_rec / kMH;
+  const double vs_f = sound_speed(p.T, s.mu_bar);
+  const double rs_f = radius_sonic_point_tidal(p.m_pl, vs_f, p.m_star, p.a_au);
+  const double rhos_f = density_sonic_point(p.mdot, rs_f, vs_f);
+  const TidalCoef tcf = tidal_coef(vs_f, rs_f, p.m_pl, p.m_star, p.a_au);
+  for (int i = PW_TID; i < nr; i += PW_NT) {
+    double vv, rr;
+    parker_point_tidal(tcf, r[i] * p.r_pl / rs_f, &vv, &rr);
+    const double f = w.f[i];
+    rates[i] = w.phi[i] * (1 - f);
+    rates[nr + i] = k2_abs * (rr * rhos_f) * (f * f);
   }
 }
 

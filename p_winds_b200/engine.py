@@ -128,7 +128,7 @@ class Engine:
                           float(max_step) if (max_step and np.isfinite(max_step)) else 0.0,
                           int(bool(structure_tidal)))
 
-    def h_ion_fraction_batch(self, T, mdot, h_fraction, mu0, r, opts):
+    def h_ion_fraction_batch(self, T, mdot, h_fraction, mu0, r, opts, return_rates=False):
         T, mdot, hf, mu0, r = (self.dev(x).reshape(-1) for x in (T, mdot, h_fraction, mu0, r))
         B, nr = T.numel(), r.numel()
         f_r = torch.empty((B, nr), dtype=torch.float64, device=self.device)
@@ -138,7 +138,13 @@ class Engine:
         self._check(self.lib.pwb_h_ion_fraction_batch(
             self.ctx, B, _ptr(T), _ptr(mdot), _ptr(hf), _ptr(mu0), _ptr(r), nr, C.byref(opts),
             _ptr(f_r), _ptr(v), _ptr(rho), _ptr(scal), _ptr(status), self._stream()))
-        return {'f_r': f_r, 'v': v, 'rho': rho, 'scal': scal, 'status': status}
+        out = {'f_r': f_r, 'v': v, 'rho': rho, 'scal': scal, 'status': status}
+        if return_rates:
+            rates = torch.empty((B, 2, nr), dtype=torch.float64, device=self.device)
+            self._check(self.lib.pwb_h_rates_batch(self.ctx, B, _ptr(T), _ptr(mdot), _ptr(hf), _ptr(mu0), _ptr(r),
+                                                   nr, C.byref(opts), _ptr(rates), self._stream()))
+            out['rates'] = rates
+        return out
 
     # ------------------------------------------------------------------- helium
     @staticmethod

@@ -64,20 +64,25 @@ def ion_fraction(radius_profile, planet_radius, temperature, h_fraction, mass_lo
         phi_abs, a_0 = radiative_processes_mono(flux_euv)
     else:
         raise ValueError('Either `spectrum_at_planet` or `flux_euv` must be provided.')
-    if return_rates:
-        raise NotImplementedError('return_rates is not available on the GPU path yet')
+    if return_rates is True and not exact:
+        # the reference reads variables that only the exact_phi branch defines (hydrogen.py:540-543)
+        raise ValueError('`return_rates` needs `exact_phi=True` and a `spectrum_at_planet`.')
     opts = Engine.h_opts(planet_radius, planet_mass, star_mass, semimajor_axis, initial_f_ion,
                          relax_solution is True, convergence, max_n_relax, exact, phi_abs, a_0,
                          ivp.get('rtol', 1e-3), ivp.get('atol', 1e-6), ivp.get('first_step'),
                          ivp.get('max_step'))
     r = np.ascontiguousarray(radius_profile, dtype=float)
     o = eng.h_ion_fraction_batch([temperature], [mass_loss_rate], [h_fraction],
-                                 [mean_molecular_weight_0], r, opts)
+                                 [mean_molecular_weight_0], r, opts, return_rates=return_rates is True)
     status = int(o['status'].cpu()[0])
     if status != 0:
         raise RuntimeError(STATUS_MESSAGES.get(status, 'The solver failed (status %d).' % status))
     f_r = o['f_r'][0].cpu().numpy()
     mu_bar = float(o['scal'][0, 0].cpu())
+    if return_rates is True:
+        rr = o['rates'][0].cpu().numpy()
+        rates = {'photoionization': rr[0], 'recombination': rr[1]}
+        return (f_r, mu_bar, rates) if return_mu is True else (f_r, rates)
     if return_mu is True:
         return f_r, mu_bar
     return f_r

@@ -184,6 +184,32 @@ def test_hydrogen_reference_signature(eng):
         hydrogen.ion_fraction(R, 1.39, 9100., 0.9, 1e10, 0.73, flux_euv=1e3, method='Radau')
 
 
+def test_hydrogen_return_rates(eng):
+    """hydrogen.ion_fraction(..., return_rates=True) (hydrogen.py:538-573): both rate profiles and
+    every return arity, against the unmodified reference (tests/golden/hydrogen_rates.npz)."""
+    from p_winds_b200 import hydrogen
+    d = golden('hydrogen_rates')
+    g = golden('solar_sed')
+    sp = {'wavelength': g['wavelength'], 'flux_lambda': g['flux_lambda'], 'wavelength_unit': 'angstrom',
+          'flux_unit': 'erg / (s cm2 angstrom)'}
+    for i in range(len(d['T0'])):
+        kw = dict(star_mass=1.07, semimajor_axis=0.04634) if d['tidal'][i] else {}
+        f_r, mu, rates = hydrogen.ion_fraction(d['r'], 1.39, float(d['T0'][i]), 0.9, float(d['mdot'][i]), 0.73, 1.2,
+                                               spectrum_at_planet=sp, relax_solution=bool(d['relax'][i]),
+                                               exact_phi=True, return_mu=True, return_rates=True, **kw)
+        # reference tolerances (RK45 1e-3): same step sequence as the reference -> ~1e-9
+        assert np.max(_rel(f_r[1:], d['f_r'][i][1:])) < 1e-6 and abs(mu / d['mu_bar'][i] - 1) < 1e-8
+        assert np.max(_rel(rates['recombination'][1:], d['recombination'][i][1:])) < 1e-6
+        m = d['f_r'][i] < 0.999
+        assert np.max(_rel(rates['photoionization'][m], d['photoionization'][i][m])) < 1e-5
+    f2, r2 = hydrogen.ion_fraction(d['r'], 1.39, 9100., 0.9, 10 ** 10.27, 0.73, 1.2, spectrum_at_planet=sp,
+                                   relax_solution=True, exact_phi=True, return_rates=True)
+    assert np.array_equal(f2, f_r) is False and set(r2) == {'photoionization', 'recombination'}
+    with pytest.raises(ValueError, match='exact_phi'):
+        hydrogen.ion_fraction(d['r'], 1.39, 9100., 0.9, 10 ** 10.27, 0.73, 1.2, spectrum_at_planet=sp,
+                              return_rates=True)
+
+
 def test_helium_reference_signature(eng, oracle, sed):
     """reference tests/test_helium.py:28-79 (range checks) + oracle comparison at tight
     tolerance + return_rates + the monochromatic channel."""

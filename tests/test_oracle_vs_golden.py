@@ -200,3 +200,15 @@ def test_helium_ion_fraction_oracle_matches_reference(oracle, sed):
                                    method=str(d['method'][i]), **kw)
         assert o['status'] == d['status'][i] == 0
         assert np.array_equal(o['f_he_ion'], d['f_he_ion'][i]), i
+
+
+def test_hydrogen_rates_oracle_matches_reference(oracle, sed):
+    """hydrogen.ion_fraction(return_rates=True) (hydrogen.py:538-561): bit for bit."""
+    d = golden('hydrogen_rates')
+    for i in range(len(d['T0'])):
+        star = (1.07, 0.04634) if d['tidal'][i] else (1.0, 1.0)
+        o = oracle.h_ion_fraction(d['r'], 1.39, float(d['T0'][i]), 0.9, float(d['mdot'][i]), 0.73, 1.2, *star,
+                                  sed=sed, exact_phi=True, relax_solution=bool(d['relax'][i]))
+        assert np.array_equal(o['f_r'], d['f_r'][i]) and o['mu_bar'] == d['mu_bar'][i]
+        assert np.array_equal(o['rates']['photoionization'], d['photoionization'][i])
+        assert np.array_equal(o['rates']['recombination'], d['recombination'][i])
