@@ -1093,7 +1093,9 @@ static HeSched he_schedule(pwb_ctx* c, int B, bool* sorted) {
     const int v = atoi(e);
     if (v >= 1 && v <= 32) { nseg = 1; frac[0] = 1.0; lanes[0] = v; *sorted = false; }
   } else if (!getenv("PWB_HE_SCHED")) {
-    const double capacity = 8.0 * c->sm_count;
+    double per_sm = 8.0;
+    if (const char* e2 = getenv("PWB_HE_CAP")) { const double v = atof(e2); if (v >= 1. && v <= 32.) per_sm = v; }
+    const double capacity = per_sm * c->sm_count;
     double warps = 0;
     for (int s = 0; s < nseg; ++s) warps += frac[s] * B / lanes[s];
     if (warps > capacity) {

@@ -176,9 +176,9 @@ struct Lsoda {
       : f(f_), tab(t_), o(o_), yhs_(hi_rows), started(false) {}
 
   PW_HD double vmnorm(const double* v) const {
-    double vm = 0.0;
+    double vm = pw_pos_or_zero(fabs(v[0]) * ewt[0]);
 #pragma unroll
-    for (int i = 0; i < N; ++i) {
+    for (int i = 1; i < N; ++i) {
       const double a = fabs(v[i]) * ewt[i];
       vm = (a > vm) ? a : vm;  // == fmax(vm, a) for vm >= 0
     }
@@ -248,11 +248,11 @@ struct Lsoda {
     rtc = PW_DIV(1., tq2 * conit);
   }
   PW_HD void scaleh(double* rh, double* pdh) {  // stoda labels 175-180
-    *rh = fmin(*rh, rmax);
-    *rh = PW_DIV(*rh, fmax(1., fabs(h) * hmxi * (*rh)));
+    *rh = pw_min(*rh, rmax);
+    *rh = PW_DIV(*rh, pw_max(1., fabs(h) * hmxi * (*rh)));
     if (meth == 1) {
       irflag = 0;
-      *pdh = fmax(fabs(h) * pdlast, 0.000001);
+      *pdh = pw_max(fabs(h) * pdlast, 0.000001);
       if ((*rh * *pdh * 1.00001) >= sm1(nq)) {
         *rh = PW_DIV(sm1(nq), *pdh);
         irflag = 1;
@@ -281,38 +281,40 @@ struct Lsoda {
   // above kF the run-time rows are advanced out of line first (lsoda_pascal_hi); what the
   // register rows need from them -- row kF+2 as it stands before each of the last kF+1
   // passes -- comes back in `hand`.
-  // order known at compile time: straight-line code, no guards
-  template <int kSign, int Q>
-  PW_HD void pascal_q() {
+  // order known at compile time: straight-line code, no guards.  The sign is a run-time
+  // +-1.0 so that prediction and retraction share ONE copy of the code (a +- b == fma(+-1, b, a)
+  // bit for bit); retraction only runs after a failed step, but its own copy of the five
+  // orders would sit in the middle of the step loop's instruction-cache footprint.
+  template <int Q>
+  PW_HD void pascal_q(double sgn) {
 #pragma unroll
     for (int j = Q; j >= 1; --j)
 #pragma unroll
       for (int i1 = j; i1 <= Q; ++i1)
 #pragma unroll
-        for (int i = 0; i < N; ++i) yh[i1][i] += kSign * yh[i1 + 1][i];
+        for (int i = 0; i < N; ++i) yh[i1][i] = pw_fma(sgn, yh[i1 + 1][i], yh[i1][i]);
   }
-  template <int kSign>
-  PW_HD void pascal() {
+  PW_HD void pascal(double sgn) {
     static_assert(kF == 5, "one case per register-resident order");
     switch (nq) {  // the register-resident orders, one unguarded body each
-      case 1: pascal_q<kSign, 1>(); return;
-      case 2: pascal_q<kSign, 2>(); return;
-      case 3: pascal_q<kSign, 3>(); return;
-      case 4: pascal_q<kSign, 4>(); return;
-      case 5: pascal_q<kSign, 5>(); return;
+      case 1: pascal_q<1>(sgn); return;
+      case 2: pascal_q<2>(sgn); return;
+      case 3: pascal_q<3>(sgn); return;
+      case 4: pascal_q<4>(sgn); return;
+      case 5: pascal_q<5>(sgn); return;
       default: break;
     }
     double hand[(kF + 1) * N];
-    lsoda_pascal_hi<N>(yhs_, nq, kF, (double)kSign, hand);
+    lsoda_pascal_hi<N>(yhs_, nq, kF, sgn, hand);
 #pragma unroll
     for (int j = kF + 1; j >= 1; --j) {
 #pragma unroll
       for (int i1 = j; i1 <= kF; ++i1) {
 #pragma unroll
-        for (int i = 0; i < N; ++i) yh[i1][i] += kSign * yh[i1 + 1][i];
+        for (int i = 0; i < N; ++i) yh[i1][i] = pw_fma(sgn, yh[i1 + 1][i], yh[i1][i]);
       }
 #pragma unroll
-      for (int i = 0; i < N; ++i) yh[kF + 1][i] += kSign * hand[(kF + 1 - j) * N + i];
+      for (int i = 0; i < N; ++i) yh[kF + 1][i] = pw_fma(sgn, hand[(kF + 1 - j) * N + i], yh[kF + 1][i]);
     }
   }
   template <int Q>
@@ -324,8 +326,6 @@ struct Lsoda {
       for (int i = 0; i < N; ++i) yh[j][i] += r * acor[i];
     }
   }
-  PW_HD void predict() { pascal<1>(); }
-  PW_HD void retract() { pascal<-1>(); }
 
   // prja, miter = 2: finite-difference Jacobian, P = I - h*el0*J, LU (dgefa)
   PW_HD void prja() {
@@ -348,7 +348,7 @@ struct Lsoda {
         ej = (i == j) ? ewt[i] : ej;
         eij = (i == j) ? ewi[i] : eij;
       }
-      const double r = fmax(srur * fabs(yj), PW_RDIV(r0, ej, eij));
+      const double r = pw_max(srur * fabs(yj), PW_RDIV(r0, ej, eij));
       double yp[N], ftem[N];
 #pragma unroll
       for (int i = 0; i < N; ++i) yp[i] = (i == j) ? yj + r : y[i];
@@ -369,7 +369,7 @@ struct Lsoda {
       double sum = 0.;
 #pragma unroll
       for (int j = 0; j < N; ++j) sum += PW_RDIV(fabs(wm[i][j]), ewt[j], ewi[j]);
-      an = fmax(an, sum * ewt[i]);
+      an = pw_max(an, sum * ewt[i]);
     }
     pdnorm = PW_DIV(an, fabs(hl0));
 #pragma unroll
@@ -533,7 +533,7 @@ struct Lsoda {
         double rh1it = 2. * rh1;
         *pdh = pdlast * fabs(h);
         if ((*pdh * rh1) > 0.00001) rh1it = PW_DIV(sm1(nq), *pdh);
-        rh1 = fmin(rh1, rh1it);
+        rh1 = pw_min(rh1, rh1it);
         // (ODEPACK's branch for nq > mxords cannot be taken: nq <= 5 = mxords here)
         const double dm2 = dsm * PW_DIV(tab.cm1[nq], tab.cm2[nq]);
         rh2 = PW_DIV(1., 1.2 * pw_root(dm2, l) + 0.0000012);
@@ -564,10 +564,10 @@ struct Lsoda {
     double rh1it = 2. * rh1;
     *pdh = pdnorm * fabs(h);
     if ((*pdh * rh1) > 0.00001) rh1it = PW_DIV(sm1(nqm1), *pdh);
-    rh1 = fmin(rh1, rh1it);
+    rh1 = pw_min(rh1, rh1it);
     const double rh2 = PW_DIV(1., 1.2 * pw_root(dsm, l) + 0.0000012);
     if ((rh1 * ratio) < (5. * rh2)) return;
-    const double alpha = fmax(0.001, rh1);
+    const double alpha = pw_max(0.001, rh1);
     dm1 *= pw_root(alpha, lm1);
     if (dm1 <= 1000. * kEps * pnorm) return;
     *rh = rh1;
@@ -591,10 +591,10 @@ struct Lsoda {
       rhdn = PW_DIV(1., 1.3 * pw_root(ddn, nq) + 0.0000013);
     }
     if (meth == 1) {
-      *pdh = fmax(fabs(h) * pdlast, 0.000001);
-      if (l < lmax) rhup = fmin(rhup, PW_DIV(sm1(l), *pdh));
-      rhsm = fmin(rhsm, PW_DIV(sm1(nq), *pdh));
-      if (nq > 1) rhdn = fmin(rhdn, PW_DIV(sm1(nq - 1), *pdh));
+      *pdh = pw_max(fabs(h) * pdlast, 0.000001);
+      if (l < lmax) rhup = pw_min(rhup, PW_DIV(sm1(l), *pdh));
+      rhsm = pw_min(rhsm, PW_DIV(sm1(nq), *pdh));
+      if (nq > 1) rhdn = pw_min(rhdn, PW_DIV(sm1(nq - 1), *pdh));
       pdest = 0.;
     }
     int newq;
@@ -635,7 +635,7 @@ struct Lsoda {
     } else {
       if (kflag == 0 && *rh < 1.1) { ialth = 3; return; }
     }
-    if (kflag <= -2) *rh = fmin(*rh, 0.2);
+    if (kflag <= -2) *rh = pw_min(*rh, 0.2);
     if (newq == nq) { *orderflag = 1; return; }
     nq = newq;
     l = nq + 1;
@@ -704,19 +704,25 @@ struct Lsoda {
       if (fabs(rc - 1.) > 0.3 /*ccmax*/) ipup = miter;
       if (nst >= nslp + 20 /*msbp*/) ipup = miter;
       tn += h;
-      predict();
-      const double pnorm = vmnorm(yh[1]);
-      const bool cfail = correction(pnorm, &del, &m);
-      bool efail = false;
-      if (!cfail) {
-        jcur = 0;
-        dsm = PW_RDIV((m == 0) ? del : vmnorm(acor), tq2, rtq2);
-        efail = !(dsm <= 1.);
-      }
-      if (cfail || efail) {  // labels 430 / 500 start the same way
+      // predict (yh <- yh * Pascal), correct, test; after a failure the same call site -- one
+      // copy of the code -- takes the prediction back (labels 430 / 500 start the same way)
+      double pnorm = 0., sgn = 1.;
+      bool cfail = false, efail = false;
+#pragma unroll 1
+      for (int undo = 0; undo < 2; ++undo) {
+        pascal(sgn);
+        if (undo) break;
+        pnorm = vmnorm(yh[1]);
+        cfail = correction(pnorm, &del, &m);
+        if (!cfail) {
+          jcur = 0;
+          dsm = PW_RDIV((m == 0) ? del : vmnorm(acor), tq2, rtq2);
+          efail = !(dsm <= 1.);
+        }
+        if (!(cfail || efail)) break;
         tn = told;
-        retract();
         rmax = 2.;
+        sgn = -1.;
       }
       if (cfail) {
         ++ncf;
@@ -889,20 +895,20 @@ struct Lsoda {
     double h0 = o.h0;
     if (!(h0 > 0.)) {
       const double tdist = fabs(tout - t0);
-      const double w0 = fmax(fabs(t0), fabs(tout));
+      const double w0 = pw_max(fabs(t0), fabs(tout));
       if (tdist < 2. * kEps * w0) return -3;
       double tol = o.rtol;
       if (tol <= 0.)
         for (int i = 0; i < N; ++i) {
           const double ayi = fabs(y[i]);
-          if (ayi != 0.) tol = fmax(tol, o.atol / ayi);
+          if (ayi != 0.) tol = pw_max(tol, o.atol / ayi);
         }
-      tol = fmax(tol, 100. * kEps);
-      tol = fmin(tol, 0.001);
+      tol = pw_max(tol, 100. * kEps);
+      tol = pw_min(tol, 0.001);
       double sum = vmnorm(yh[2]);
       sum = 1. / (tol * w0 * w0) + tol * sum * sum;
       h0 = 1. / sqrt(sum);
-      h0 = fmin(h0, tdist);
+      h0 = pw_min(h0, tdist);
       h0 = copysign(h0, tout - t0);
     }
     const double rh = fabs(h0) * hmxi;
