@@ -31,6 +31,8 @@ struct LsodaTables {
   double tesco[2][13][4];
   double rtesco2[2][13];  // 1 / tesco[meth][nq][2] (label 700 scales acor by it)
   double rtesco1[2][13], rtesco3[2][13];  // 1 / tesco[meth][nq][1], [3] (PW_RDIV)
+  double conit[13];     // 0.5 / (nq + 2): stoda label 150
+  double rtcon[2][13];  // 1 / (tesco[meth][nq][2] * conit[nq]) (PW_RDIV in the corrector's convergence test)
   double cm1[13], cm2[6];
   double sm1[13];  // Adams stability-region bounds used by the switching logic
 };
@@ -97,6 +99,8 @@ PW_HD void lsoda_tables_init(LsodaTables* t) {
       t->rtesco2[m][a] = (t->tesco[m][a][2] != 0.) ? 1. / t->tesco[m][a][2] : 0.;
       t->rtesco1[m][a] = (t->tesco[m][a][1] != 0.) ? 1. / t->tesco[m][a][1] : 0.;
       t->rtesco3[m][a] = (t->tesco[m][a][3] != 0.) ? 1. / t->tesco[m][a][3] : 0.;
+      t->conit[a] = 0.5 / (double)(a + 2);
+      t->rtcon[m][a] = (t->tesco[m][a][2] != 0.) ? 1. / (t->tesco[m][a][2] * t->conit[a]) : 0.;
     }
   for (int i = 1; i <= 5; ++i) t->cm2[i] = t->tesco[1][i][2] * t->elco[1][i][i + 1];
   for (int i = 1; i <= 12; ++i) t->cm1[i] = t->tesco[0][i][2] * t->elco[0][i][i + 1];
@@ -244,8 +248,8 @@ struct Lsoda {
     const double el1 = elp[1];
     rc = PW_DIV(rc * el1, el0);
     el0 = el1;
-    conit = PW_DIV(0.5, (double)(nq + 2));
-    rtc = PW_DIV(1., tq2 * conit);
+    conit = tab.conit[nq];
+    rtc = tab.rtcon[meth_tab - 1][nq];
   }
   PW_HD void scaleh(double* rh, double* pdh) {  // stoda labels 175-180
     *rh = pw_min(*rh, rmax);
@@ -276,33 +280,28 @@ struct Lsoda {
     rc *= *rh;
     ialth = l;
   }
-  // yh <- yh * Pascal triangle (sign = +1, prediction) or its inverse (sign = -1).  Each
-  // pass j = nq..1 adds row i1+1 to row i1 for i1 = j..nq in ascending order.  For orders
+  // yh <- yh * Pascal triangle (sgn = +1, prediction) or its inverse (sgn = -1, retraction after
+  // a failed step).  Each pass j = nq..1 adds row i1+1 to row i1 for i1 = j..nq in ascending
+  // order.  The sign is a run-time +-1.0 and stoda() has a single call site, so that prediction
+  // and retraction share ONE copy of the code (a +- b == fma(+-1, b, a) bit for bit): a second
+  // copy would sit in the middle of the step loop's instruction-cache footprint.  For orders
   // above kF the run-time rows are advanced out of line first (lsoda_pascal_hi); what the
   // register rows need from them -- row kF+2 as it stands before each of the last kF+1
   // passes -- comes back in `hand`.
-  // order known at compile time: straight-line code, no guards.  The sign is a run-time
-  // +-1.0 so that prediction and retraction share ONE copy of the code (a +- b == fma(+-1, b, a)
-  // bit for bit); retraction only runs after a failed step, but its own copy of the five
-  // orders would sit in the middle of the step loop's instruction-cache footprint.
-  template <int Q>
-  PW_HD void pascal_q(double sgn) {
-#pragma unroll
-    for (int j = Q; j >= 1; --j)
-#pragma unroll
-      for (int i1 = j; i1 <= Q; ++i1)
-#pragma unroll
-        for (int i = 0; i < N; ++i) yh[i1][i] = pw_fma(sgn, yh[i1 + 1][i], yh[i1][i]);
-  }
   PW_HD void pascal(double sgn) {
-    static_assert(kF == 5, "one case per register-resident order");
-    switch (nq) {  // the register-resident orders, one unguarded body each
-      case 1: pascal_q<1>(sgn); return;
-      case 2: pascal_q<2>(sgn); return;
-      case 3: pascal_q<3>(sgn); return;
-      case 4: pascal_q<4>(sgn); return;
-      case 5: pascal_q<5>(sgn); return;
-      default: break;
+    // one copy for all register-resident orders: the row operations of order kF, each under
+    // the guard `row <= nq` (a guarded-off operation costs its issue slot)
+    if (nq <= kF) {
+#pragma unroll
+      for (int j = kF; j >= 1; --j)
+#pragma unroll
+        for (int i1 = j; i1 <= kF; ++i1) {
+          const bool on = (i1 <= nq);
+#pragma unroll
+          for (int i = 0; i < N; ++i)
+            if (on) yh[i1][i] = pw_fma(sgn, yh[i1 + 1][i], yh[i1][i]);
+        }
+      return;
     }
     double hand[(kF + 1) * N];
     lsoda_pascal_hi<N>(yhs_, nq, kF, sgn, hand);
@@ -317,16 +316,6 @@ struct Lsoda {
       for (int i = 0; i < N; ++i) yh[kF + 1][i] = pw_fma(sgn, hand[(kF + 1 - j) * N + i], yh[kF + 1][i]);
     }
   }
-  template <int Q>
-  PW_HD void correct_q() {
-#pragma unroll
-    for (int j = 1; j <= Q + 1; ++j) {
-      const double r = elp[j];
-#pragma unroll
-      for (int i = 0; i < N; ++i) yh[j][i] += r * acor[i];
-    }
-  }
-
   // prja, miter = 2: finite-difference Jacobian, P = I - h*el0*J, LU (dgefa)
   PW_HD void prja() {
     ++nje;
@@ -529,14 +518,14 @@ struct Lsoda {
         rh2 = 2.;
         nqm2 = nq < mxords ? nq : mxords;
       } else {
-        double rh1 = PW_DIV(1., 1.2 * pw_root(dsm, l) + 0.0000012);
+        double rh1 = pw_step_ratio(dsm, l, 1.2, 0.0000012);
         double rh1it = 2. * rh1;
         *pdh = pdlast * fabs(h);
         if ((*pdh * rh1) > 0.00001) rh1it = PW_DIV(sm1(nq), *pdh);
         rh1 = pw_min(rh1, rh1it);
         // (ODEPACK's branch for nq > mxords cannot be taken: nq <= 5 = mxords here)
         const double dm2 = dsm * PW_DIV(tab.cm1[nq], tab.cm2[nq]);
-        rh2 = PW_DIV(1., 1.2 * pw_root(dm2, l) + 0.0000012);
+        rh2 = pw_step_ratio(dm2, l, 1.2, 0.0000012);
         nqm2 = nq;
         if (rh2 < ratio * rh1) return;
       }
@@ -559,13 +548,13 @@ struct Lsoda {
     if (ratio == 5. && *pdh >= 1.) return;
     // (ODEPACK's branch for mxordn < nq cannot be taken: nq <= 5 < 12 = mxordn here)
     double dm1 = dsm * PW_DIV(tab.cm2[nq], tab.cm1[nq]);
-    double rh1 = PW_DIV(1., 1.2 * pw_root(dm1, l) + 0.0000012);
+    double rh1 = pw_step_ratio(dm1, l, 1.2, 0.0000012);
     const int nqm1 = nq, lm1 = l;
     double rh1it = 2. * rh1;
     *pdh = pdnorm * fabs(h);
     if ((*pdh * rh1) > 0.00001) rh1it = PW_DIV(sm1(nqm1), *pdh);
     rh1 = pw_min(rh1, rh1it);
-    const double rh2 = PW_DIV(1., 1.2 * pw_root(dsm, l) + 0.0000012);
+    const double rh2 = pw_step_ratio(dsm, l, 1.2, 0.0000012);
     if ((rh1 * ratio) < (5. * rh2)) return;
     const double alpha = pw_max(0.001, rh1);
     dm1 *= pw_root(alpha, lm1);
@@ -582,13 +571,13 @@ struct Lsoda {
   // labels 540-630.  orderflag: 0 no change, 1 h changes, 2 h and nq change
   PW_HD void orderswitch(double rhup, double dsm, double* pdh, double* rh, int* orderflag) {
     *orderflag = 0;
-    double rhsm = PW_DIV(1., 1.2 * pw_root(dsm, l) + 0.0000012);
+    double rhsm = pw_step_ratio(dsm, l, 1.2, 0.0000012);
     double rhdn = 0.;
     if (nq != 1) {
       double top[N];
       row_get(l, top);
       const double ddn = PW_RDIV(vmnorm(top), tq1, rtq1);
-      rhdn = PW_DIV(1., 1.3 * pw_root(ddn, nq) + 0.0000013);
+      rhdn = pw_step_ratio(ddn, nq, 1.3, 0.0000013);
     }
     if (meth == 1) {
       *pdh = pw_max(fabs(h) * pdlast, 0.000001);
@@ -749,19 +738,22 @@ struct Lsoda {
         nqu = nq;
         rtq2u = rtq2;
         mused = meth;
-        switch (nq) {  // yh(., j) += el(j) * acor for j = 1..l, unguarded per order
-          case 1: correct_q<1>(); break;
-          case 2: correct_q<2>(); break;
-          case 3: correct_q<3>(); break;
-          case 4: correct_q<4>(); break;
-          case 5: correct_q<5>(); break;
-          default:
-            correct_q<kF>();
+        // yh(., j) += el(j) * acor for j = 1..l: one guarded copy (el(j) = 0 in the table for j > l
+        // would do as well, but rows above l must keep their bits)
+#pragma unroll
+        for (int j = 1; j <= kF + 1; ++j) {
+          const bool on = (j <= l);
+          const double r = elp[j];
+#pragma unroll
+          for (int i = 0; i < N; ++i)
+            if (on) yh[j][i] += r * acor[i];
+        }
+        if (PW_UNLIKELY(nq > kF)) {
 #pragma unroll 1
-            for (int j = kF + 2; j <= l; ++j) {
-              const double r = elp[j];
-              for (int i = 0; i < N; ++i) yhs_[(j) * N + i] += r * acor[i];
-            }
+          for (int j = kF + 2; j <= l; ++j) {
+            const double r = elp[j];
+            for (int i = 0; i < N; ++i) yhs_[(j) * N + i] += r * acor[i];
+          }
         }
         --icount;
         if (icount < 0) {
@@ -784,7 +776,7 @@ struct Lsoda {
 #pragma unroll
           for (int i = 0; i < N; ++i) savf[i] = acor[i] - top[i];
           const double dup = PW_RDIV(vmnorm(savf), tq3, rtq3);
-          rhup = PW_DIV(1., 1.4 * pw_root(dup, l + 1) + 0.0000014);
+          rhup = pw_step_ratio(dup, l + 1, 1.4, 0.0000014);
         }
       } else {
         // error test failed (label 500)
@@ -851,13 +843,15 @@ struct Lsoda {
       for (int j = l - 1; j >= kF + 2; --j)
         for (int i = 0; i < N; ++i) dky[i] = yhs_[(j) * N + i] + s * dky[i];
     }
+    // Horner from row l down; rows above l are skipped, and row l itself enters as
+    // yh[l] + s * 0 (dky is still zero there) -- one predicated fma per row and component
 #pragma unroll
     for (int j = kF + 1; j >= 1; --j) {
+      const bool on = (j <= l);
 #pragma unroll
       for (int i = 0; i < N; ++i) {
-        const double v = yh[j][i];  // unconditional read, value select (see row_get)
-        const double hn = v + s * dky[i];
-        dky[i] = (j == l) ? v : ((j < l) ? hn : dky[i]);
+        const double hn = pw_fma(s, dky[i], yh[j][i]);
+        dky[i] = on ? hn : dky[i];
       }
     }
     return 0;
