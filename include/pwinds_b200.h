@@ -279,6 +279,13 @@ int pwb_draw_transit(pwb_ctx* ctx, double planet_to_star_ratio, double planet_ph
  *      has no FP64 figure): runs a dependent-chain DFMA kernel and returns TFLOP/s. */
 int pwb_fp64_peak(pwb_ctx* ctx, double* tflops, void* stream);
 
+/* ---- Self-test of the step arithmetic (test hook, no reference counterpart): quot[i] =
+ *      a[i] / b[i] and root[i] = a[i] ** (1 / k[i]) through the routines the device build of the
+ *      LSODA replica uses in place of IEEE division and pow (csrc/pw_common.cuh: PW_DIV,
+ *      pw_root), so that the GPU tests can compare them with numpy. */
+int pwb_selftest_arith(pwb_ctx* ctx, int n, const double* d_a, const double* d_b, const int* d_k,
+                       double* d_quot, double* d_root, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

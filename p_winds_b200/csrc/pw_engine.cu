@@ -901,6 +901,17 @@ __global__ void k_fp64_peak(double* out, int iters) {
   out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
 }
 
+// The two arithmetic primitives the device build of the LSODA step swaps in for a / b and
+// pow(a, 1 / k), exposed so that the GPU tests can hold them to IEEE division / libm over the
+// operand ranges of the step (tests/test_gpu_parity.py::test_step_arithmetic_on_gpu).
+__global__ void k_selftest_arith(int n, const double* __restrict__ a, const double* __restrict__ b,
+                                 const int* __restrict__ k, double* __restrict__ quot, double* __restrict__ root) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  quot[i] = PW_DIV(a[i], b[i]);
+  root[i] = pw_root(a[i], k[i]);
+}
+
 // mu_0 = (1 + 4 he/h) / (1 + he/h + mean_f_ion), mean_f_ion = 0 (quickstart.ipynb cell 2)
 __global__ void k_mu0(int B, const double* __restrict__ hfrac, double* mu0) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1420,9 +1431,13 @@ int pwb_forward_batch(pwb_ctx* c, int B, const double* d_T, const double* d_mdot
   double* mu0 = base + 5 * bn;  // [B]
   double* hscal = d_hscal ? d_hscal : c->fw_scal.as<double>();
   double* hescal = d_hescal ? d_hescal : c->fw_he.as<double>();
-  // hydrogen -> helium -> line-of-sight + pixel sum, all on the caller's stream.  (Cutting the
-  // batch into chunks on separate streams to overlap the stages was measured slower on B200:
-  // another chunk's hydrogen stage steals issue slots from the latency-critical helium warps.)
+  // hydrogen -> helium -> line-of-sight + pixel sum, all on the caller's stream.  (Overlapping
+  // the stages of different models was measured twice and dropped: equal chunks on separate
+  // streams were slower, and a cost-ordered two-chunk pipeline -- costly 30 % first on a
+  // high-priority stream, the cheap chunk's hydrogen stage and pixel sum under the head and
+  // tail of the first helium kernel -- gave 54.4 against 56.5 ms on the 64 x 64 grid and
+  // 134 against 123 ms on 24 576 models: the FP64-bound kernels of one chunk slow the
+  // latency-critical helium warps of the other by about what the overlap saves.)
   k_mu0<<<(B + 255) / 256, 256, 0, s>>>(B, d_hfrac, mu0);   // quickstart.ipynb cell 2
   c->launches++;
   if (launch_hydrogen(c, s, B, d_T, d_mdot, d_hfrac, mu0, d_r, Nr, hopts, f_r, v, rho, hscal, d_status)) return -1;
@@ -1471,6 +1486,16 @@ int pwb_loglike_batch(pwb_ctx* c, int B, const double* d_model, int Nw, const do
   if (!c) return -1;
   if (B <= 0) return 0;
   k_loglike<<<B, 128, 0, (cudaStream_t)stream>>>(B, Nw, d_model, d_y, d_yerr, d_status, d_out);
+  c->launches++;
+  PWB_CUDA(c, cudaGetLastError());
+  return 0;
+}
+
+int pwb_selftest_arith(pwb_ctx* c, int n, const double* d_a, const double* d_b, const int* d_k, double* d_quot,
+                        double* d_root, void* stream) {
+  if (!c) return -1;
+  if (n <= 0) return 0;
+  k_selftest_arith<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(n, d_a, d_b, d_k, d_quot, d_root);
   c->launches++;
   PWB_CUDA(c, cudaGetLastError());
   return 0;

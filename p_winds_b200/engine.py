@@ -403,6 +403,15 @@ class Engine:
             self._stream()))
         return i0, depth.value, rm
 
+    def selftest_arith(self, a, b, k):
+        """(a / b, a ** (1 / k)) through the device routines of the LSODA step (test hook)."""
+        a = self.dev(a); b = self.dev(b)
+        kk = torch.as_tensor(np.ascontiguousarray(k, dtype=np.int32), device=self.device)
+        q = torch.empty_like(a); r = torch.empty_like(a)
+        self._check(self.lib.pwb_selftest_arith(self.ctx, a.numel(), _ptr(a), _ptr(b), _ptr(kk), _ptr(q), _ptr(r),
+                                                self._stream()))
+        return q, r
+
     def fp64_peak_tflops(self):
         t = C.c_double()
         self._check(self.lib.pwb_fp64_peak(self.ctx, C.byref(t), self._stream()))

@@ -785,3 +785,31 @@ def test_metals_chain_config5_lines_on_gpu(eng, oracle, sed):
                                              np.array(c2[3:6]), np.array(c2[6:9]), wl_c, T[b], 12 * m_p)
         assert np.max(_rel(s_o[b], ref_o)) < 1e-5 and np.max(_rel(s_c[b], ref_c)) < 1e-5, b
         assert ref_c.min() < 0.999 * ref_c.max()      # the C II lines are actually there
+
+
+def test_step_arithmetic_on_gpu(eng):
+    """The device build of the LSODA step replaces `a / b` by the fast path of the IEEE division
+    algorithm (csrc/pw_common.cuh PW_DIV) and pow(a, 1/k) by a Newton root (pw_root).  Over the
+    operand ranges of the step the quotient must be the correctly rounded one, bit for bit, the
+    special cases (0, inf, nan, denormal divisors) must keep their IEEE results, and the root
+    must sit within 2e-15 of the true one."""
+    rng = np.random.default_rng(11)
+    n = 200000
+    a = np.concatenate([rng.standard_normal(n) * 10.0 ** rng.uniform(-40, 40, n),
+                        rng.uniform(-2, 2, n), [0.0, 1.0, -1.0, np.inf, np.nan, 1e300, 1.0, 1.0, 5e-324, 1.0]])
+    b = np.concatenate([rng.standard_normal(n) * 10.0 ** rng.uniform(-40, 40, n),
+                        1.49012e-8 * (1 + rng.uniform(0, 1, n)), [1.0, 0.0, np.inf, 2.0, 1.0, 1e-300, 5e-324, np.nan, 3.0, -0.0]])
+    k = np.concatenate([rng.integers(1, 14, 2 * n), np.arange(1, 11)]).astype(np.int32)
+    q, r = eng.selftest_arith(a, b, k)
+    q = q.cpu().numpy(); r = r.cpu().numpy()
+    with np.errstate(all='ignore'):
+        want = a / b
+    assert np.array_equal(q, want, equal_nan=True)
+    # roots: a > 0 in the range the step-size selection produces (error ratios)
+    ar = np.abs(a[:2 * n]) + 1e-300
+    _, r2 = eng.selftest_arith(ar, np.ones_like(ar), k[:2 * n])
+    r2 = r2.cpu().numpy()
+    ref = ar ** (1.0 / k[:2 * n])
+    m = (ar > 1e-30) & (ar < 1e30)
+    assert np.max(np.abs(r2[m] / ref[m] - 1)) < 2e-15
+    assert np.max(np.abs(r2[~m] / ref[~m] - 1)) < 1e-13
