@@ -647,8 +647,8 @@ k_rt_sum(int B, int nw, int nr, pwb_rt_opts o, const double* __restrict__ wl, co
          double* tau_out /*[B][nr][nw] or null*/, const double* __restrict__ tau_tab /*'formal': [B][nr][nw]*/) {
   __shared__ double s_ncol[1024];
   __shared__ double s_np[PW_RT_CHUNK], s_i0[PW_RT_CHUNK];
-  __shared__ double s_e2[32];
-  if (threadIdx.x < 32) s_e2[threadIdx.x] = kExp2TabDev[threadIdx.x];
+  __shared__ double s_e2[64];
+  if (threadIdx.x < 64) s_e2[threadIdx.x] = kExp2Tab64Dev[threadIdx.x];
   const unsigned e2 = (unsigned)__cvta_generic_to_shared(s_e2);
   const int b = blockIdx.x, split = blockIdx.y;
   const int k = blockIdx.z * blockDim.x + threadIdx.x;  // wavelength index
@@ -670,7 +670,7 @@ k_rt_sum(int B, int nw, int nr, pwb_rt_opts o, const double* __restrict__ wl, co
       for (int q = p0; q < p1; ++q) {
         const int lo = px_lo[q];
         const double t = px_whi[q] * tb[(size_t)(lo + 1) * nw] + px_wlo[q] * tb[(size_t)lo * nw];
-        acc = pw_fma(px_i0[q], pw_exp_neg_sh(-t, e2), acc);
+        acc = pw_fma(px_i0[q], pw_exp_neg_sum_sh(-t, e2), acc);
       }
       if (split == 0) acc += meta[1];
       out[((size_t)b * nsplit + split) * nw + k] = acc;
@@ -715,7 +715,7 @@ k_rt_sum(int B, int nw, int nr, pwb_rt_opts o, const double* __restrict__ wl, co
     const int cnt = min(PW_RT_CHUNK, p1 - start);
     if (k < nw) {  // (the warps past the last wavelength only help staging)
 #pragma unroll 4
-      for (int j = 0; j < cnt; ++j) acc = pw_fma(s_i0[j], pw_exp_neg_sh(-(s_np[j] * phi), e2), acc);
+      for (int j = 0; j < cnt; ++j) acc = pw_fma(s_i0[j], pw_exp_neg_sum_sh(-(s_np[j] * phi), e2), acc);
     }
   }
   if (k < nw) {

@@ -299,6 +299,9 @@ void hs_tau_average(const double* r, const double* n, const double* v, const dou
 extern "C" void hs_exp_neg(const double* x, int n, double* out) {
   for (int i = 0; i < n; ++i) out[i] = pw::pw_exp_neg(x[i], pw::kExp2Tab);
 }
+extern "C" void hs_exp_neg_sum(const double* x, int n, double* out) {
+  for (int i = 0; i < n; ++i) out[i] = pw::pw_exp_neg_sum(x[i], pw::kExp2Tab64);
+}
 
 extern "C" void hs_root_newton(const double* a, const int* k, int n, double* out) {
   for (int i = 0; i < n; ++i) out[i] = pw::pw_root_newton(a[i], k[i]);

@@ -253,6 +253,26 @@ def test_exp_neg(hostsim):
     assert out[0 + 400000] == 1.0
 
 
+def test_exp_neg_sum(hostsim):
+    """pw_exp_neg_sum (64-entry table, degree-5 series, one-constant reduction: the e^{-tau} of the
+    pixel sum): absolute error below half an ulp of the O(1) sum everywhere, relative error at
+    rounding level where the term matters."""
+    rng = np.random.default_rng(6)
+    x = -np.concatenate([10 ** rng.uniform(-12, 2.85, 200000), rng.uniform(0, 40, 200000),
+                         [0.0, 1e-300, 707.9, 708.0, 708.5, 745.0, 800.0, np.inf]])
+    out = np.zeros_like(x)
+    hostsim.hs_exp_neg_sum.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    hostsim.hs_exp_neg_sum(P(x), x.size, P(out))
+    ref = np.exp(x)
+    live = x > -708.0
+    assert np.max(np.abs(out[live] - ref[live])) < 1.2e-16          # one ulp below 1
+    near = x > -2.0
+    assert np.max(np.abs(out[near] / ref[near] - 1)) < 3e-16
+    assert np.max(np.abs(out[live] / ref[live] - 1) / np.maximum(1.0, -x[live])) < 3e-16
+    assert np.all(out[~live] == 0.0)
+    assert out[0 + 400000] == 1.0
+
+
 def _oxygen_tolerance(d, i):
     """The reference's oxygen.ion_fraction is reproducible only to its round-off noise floor:
     scipy's Radau builds its Jacobian by finite differences, which turns 1-ulp input noise into
