@@ -47,17 +47,31 @@ def grid(n_gpus):
     return TT.ravel(), MM.ravel(), HH.ravel()
 
 
-def grid_cfg3_share():
-    """One GPU's share (1/8, interleaved) of BASELINE configs[3]: 256 x 256 (T0, Mdot) x 3 h_fractions,
-    tidal Parker profile (M* = 1.07, a = 0.04634 au)."""
+def grid_cfg3():
+    """BASELINE configs[3]: 256 x 256 (T0, Mdot) x 3 h_fractions, tidal Parker profile
+    (M* = 1.07, a = 0.04634 au); 196 608 models."""
     T0 = np.linspace(9000, 13000, 256)
     md = np.logspace(9.5, 12, 256)
     hf = np.array([0.85, 0.90, 0.95])
     HH, TT, MM = np.meshgrid(hf, T0, md, indexing='ij')
-    return TT.ravel()[0::8].copy(), MM.ravel()[0::8].copy(), HH.ravel()[0::8].copy()
+    return TT.ravel(), MM.ravel(), HH.ravel()
 
 
-def config(n_gpus):
+def grid_cfg3_share():
+    """One GPU's share (1/8, interleaved) of the configs[3] grid."""
+    T, md, hf = grid_cfg3()
+    return T[0::8].copy(), md[0::8].copy(), hf[0::8].copy()
+
+
+def config(n_gpus, workload='grid64'):
+    if workload == 'cfg3':
+        n = 256 * 256 * 3
+        return {'workload': 'He-triplet retrieval grid 256x256 (T0, Mdot) x 3 h_fractions, tidal Parker profile '
+                            '(BASELINE configs[3], the north-star target); HD 209458 b, solar SED, Nr=100, G=100 '
+                            '(ss=10), Nw=200, 3 lines, exact_phi, relax_solution, reference solver tolerances',
+                'models_per_gpu': -(-n // n_gpus), 'global_models': n,
+                'sharding': 'interleaved over ranks, final all_gather of chi2+status' if n_gpus > 1 else 'single GPU',
+                'l2_policy': 'L2 flushed (512 MiB write) before every timed step'}
     return {'workload': 'He-triplet retrieval grid 64x64 (T0, Mdot) per GPU (BASELINE configs[2]); '
                         'HD 209458 b, solar SED, Nr=100, G=100 (ss=10), Nw=200, 3 lines, exact_phi, '
                         'relax_solution, reference solver tolerances',
@@ -186,13 +200,20 @@ def run_ours(args):
     eng.set_geometry(geo['i0'], geo['r_map'], r * (R_PL * 71492000))
     sc = eng.sed_scalars()
     rates = [sc[k] for k in ('he_phi_1', 'he_phi_3', 'he_a_1', 'he_a_3', 'he_a_h_1', 'he_a_h_3')]
-    ho = Engine.h_opts(R_PL, M_PL, relax_solution=True, exact_phi=True)
+    cfg3 = (args.workload == 'cfg3')
+    if cfg3:   # the whole 256 x 256 x 3 tidal grid, cut over the ranks (total work fixed: strong scaling)
+        ho = Engine.h_opts(R_PL, M_PL, star_mass=1.07, semimajor_axis=0.04634, relax_solution=True,
+                           exact_phi=True, structure_tidal=True)
+        args.no_large_batch = True
+        args.no_cpu_baseline = True
+    else:
+        ho = Engine.h_opts(R_PL, M_PL, relax_solution=True, exact_phi=True)
     heo = Engine.he_opts(R_PL, rates, (1.0, 0.0), True)
     w = lines.he_3_properties()
     rto = Engine.rt_opts(w[:3], w[3:6], [w[6]] * 3, M_HE)
     fp64_peak = eng.fp64_peak_tflops()
 
-    T, md, hf = grid(world)
+    T, md, hf = grid_cfg3() if cfg3 else grid(world)
     n_global = len(T)
     idx = pgrid.shard_indices(n_global, rank, world)
     B = len(idx)
@@ -396,9 +417,9 @@ def run_ours(args):
     if rank == 0:
         line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
                 'warmup': max(args.warmup, 3), 'ms_per_step': ms_dev / args.steps, 'higher_is_better': True,
-                'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
+                'scaling': 'strong' if cfg3 else 'weak', 'vs_baseline': None, 'dtype': 'f64',
                 'data': 'synthetic (T0, Mdot, h) grid; reference solar SED and HD 209458 b geometry',
-                'config': config(world),
+                'config': config(world, args.workload),
                 'e2e': {'value': e2e, 'unit': UNIT, 'ms_per_step': ms_e2e / args.steps,
                         'h2d_bytes_per_step': int(h_in.numel() * 8),
                         'd2h_bytes_per_step': int(h_spec.numel() * 8 + h_chi2.numel() * 8 + h_status.numel() * 4),
@@ -489,6 +510,9 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-large-batch', action='store_true')
+    ap.add_argument('--workload', default='grid64', choices=['grid64', 'cfg3'],
+                    help="grid64: 64x64 grid per GPU (default, the headline line); cfg3: the whole 256x256x3 tidal "
+                         "grid of BASELINE configs[3] cut over the ranks (ours only)")
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)
