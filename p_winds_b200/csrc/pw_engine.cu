@@ -565,7 +565,7 @@ __global__ void __launch_bounds__(256)
 k_rt_los(int B, const double* __restrict__ r, const double* __restrict__ n, const double* __restrict__ v,
          const double* __restrict__ Tprof, int t_is_profile, int nr, int nz, const int* __restrict__ status,
          double* ncol, double* sums) {
-  extern __shared__ double sm[];  // r, n, v, (T) staged: 4*nr + 40
+  extern __shared__ double sm[];  // r, n, v, (T) staged: 4*nr + 40; one row of nz cells per warp
   const int b = blockIdx.x;
   if (b >= B) return;
   if (status && status[b] != PW_OK && status[b] != PW_WARN_HE_RELAX) return;
@@ -576,7 +576,8 @@ k_rt_los(int B, const double* __restrict__ r, const double* __restrict__ n, cons
     st[i] = t_is_profile ? Tprof[(size_t)b * nr + i] : 0.0;
   }
   __syncthreads();
-  rt_los_average(sr, sn, sv, t_is_profile ? st : nullptr, nr, nz, ncol + (size_t)b * nr, sums + (size_t)b * 4, red);
+  rt_los_average(sr, sn, sv, t_is_profile ? st : nullptr, nr, nz, ncol + (size_t)b * nr, sums + (size_t)b * 4, red,
+                 sm + 4 * nr + 40);
 }
 
 
@@ -1351,7 +1352,9 @@ static int launch_rt(pwb_ctx* c, cudaStream_t s, int B, const double* d_n, const
     c->launches++;
     PWB_CUDA(c, cudaGetLastError());
   } else {
-    k_rt_los<<<B, 256, sizeof(double) * (4 * (size_t)Nr + 40), s>>>(
+    const size_t smem_los = sizeof(double) * (4 * (size_t)Nr + 40 + 8 * (size_t)o->z_grid_size);
+    if (smem_los > 100 * 1024) return fail(c, "pwb_rt2d_batch: z_grid_size too large for the line-of-sight kernel");
+    k_rt_los<<<B, 256, smem_los, s>>>(
         B, c->geo_r.as<double>(), d_n, d_v, d_T, o->temperature_is_profile, Nr, o->z_grid_size, d_status, ncol, sums);
     c->launches++;
     PWB_CUDA(c, cudaGetLastError());

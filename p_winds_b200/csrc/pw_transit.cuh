@@ -200,7 +200,8 @@ PW_HD double los_z(double r_top, int nz, int j) {
 // (Nz, Nr) LOS grid (transit.py:482-488, :517-519).
 PW_HD void rt_los_average(const double* __restrict__ r, const double* __restrict__ n,
                           const double* __restrict__ v, const double* __restrict__ tprof, int nr, int nz,
-                          double* __restrict__ ncol, double* sums, double* red) {
+                          double* __restrict__ ncol, double* sums, double* red, double* rows) {
+  // `rows`: nz doubles of scratch per warp (device: shared memory; host: one row)
   const double r_top = r[nr - 1];
   double s_n = 0.0, s_v2n = 0.0, s_tn = 0.0;
 #if defined(__CUDA_ARCH__)
@@ -208,26 +209,34 @@ PW_HD void rt_los_average(const double* __restrict__ r, const double* __restrict
 #else
   const int lane = 0, warp = 0, nwarp = 1, nlane = 1;
 #endif
+  double* row = rows + (size_t)warp * nz;
   for (int i = warp; i < nr; i += nwarp) {
     const double b = r[i];
-    double acc = 0.0;
-    // each lane owns z-intervals j -> (z_j, z_{j+1}); trapezoid d * (y1 + y0) / 2
+    // every cell of the line of sight once: the lane that owns z_j keeps n(z_j) in the warp's
+    // row for its neighbour's trapezoid and adds the cell to the moments
     for (int j = lane; j < nz; j += nlane) {
       const double z0 = los_z(r_top, nz, j);
       double n0, vl0, t0;
       los_cell(r, n, v, tprof, nr, b, z0, &n0, &vl0, tprof ? &t0 : nullptr);
+      row[j] = n0;
       s_n += n0;
       s_v2n += (vl0 * vl0) * n0;
       if (tprof) s_tn += t0 * n0;
-      if (j + 1 < nz) {
-        const double z1 = los_z(r_top, nz, j + 1);
-        double n1, vl1;
-        los_cell(r, n, v, nullptr, nr, b, z1, &n1, &vl1, nullptr);
-        acc += (z1 - z0) * (n1 + n0) / 2.0;
-      }
+    }
+#if defined(__CUDA_ARCH__)
+    __syncwarp();
+#endif
+    double acc = 0.0;
+    // each lane owns z-intervals j -> (z_j, z_{j+1}); trapezoid d * (y1 + y0) / 2
+    for (int j = lane; j + 1 < nz; j += nlane) {
+      const double z0 = los_z(r_top, nz, j), z1 = los_z(r_top, nz, j + 1);
+      acc += (z1 - z0) * (row[j + 1] + row[j]) / 2.0;
     }
     acc = warp_sum(acc);
     if (lane == 0) ncol[i] = acc;
+#if defined(__CUDA_ARCH__)
+    __syncwarp();   // the row is reused for the next impact parameter
+#endif
   }
   const double t_n = block_sum(s_n, red);
   const double t_v2n = block_sum(s_v2n, red);

@@ -277,7 +277,8 @@ void hs_tau_average(const double* r, const double* n, const double* v, const dou
                     double* tau, double* sums_out) {
   std::vector<double> ncol(nr);
   double sums[4], red[40];
-  rt_los_average(r, n, v, tprof, nr, nz, ncol.data(), sums, red);
+  std::vector<double> row(nz);
+  rt_los_average(r, n, v, tprof, nr, nz, ncol.data(), sums, red, row.data());
   RtParams p;
   p.n_lines = nlines;
   for (int k = 0; k < nlines; ++k) { p.w0[k] = w0[k]; p.fosc[k] = fosc[k]; p.aij[k] = aij[k]; }
