@@ -195,7 +195,7 @@ struct Lsoda {
       const double e = o.rtol * fabs(yc[i]) + o.atol;
       if (!(e > 0.0)) ok = false;
       ewi[i] = e;
-      ewt[i] = PW_DIV(1.0, e);
+      ewt[i] = PW_DIV_INL(1.0, e);  // inline: the N reciprocals overlap
     }
     return ok;
   }
@@ -253,7 +253,7 @@ struct Lsoda {
   }
   PW_HD void scaleh(double* rh, double* pdh) {  // stoda labels 175-180
     *rh = pw_min(*rh, rmax);
-    *rh = PW_DIV(*rh, pw_max(1., fabs(h) * hmxi * (*rh)));
+    if (hmxi != 0.) *rh = PW_DIV(*rh, pw_max(1., fabs(h) * hmxi * (*rh)));  // (hmxi = 0: rh / 1)
     if (meth == 1) {
       irflag = 0;
       *pdh = pw_max(fabs(h) * pdlast, 0.000001);
@@ -485,8 +485,10 @@ struct Lsoda {
         const double c15 = 1.5 * crate;
         const double dcon = PW_RDIV(del * ((c15 < 1.) ? c15 : 1.), tq2 * conit, rtc);
         if (dcon <= 1.) {
-          const double pd = PW_DIV(rate, fabs(h * el0));
-          pdest = (pd > pdest) ? pd : pdest;
+          if (rate != 0.) {  // (rate = 0: pd = 0, or NaN for h = 0, neither of which changes pdest >= 0)
+            const double pd = PW_DIV(rate, fabs(h * el0));
+            pdest = (pd > pdest) ? pd : pdest;
+          }
           if (pdest != 0.) pdlast = pdest;
           break;
         }
