@@ -195,7 +195,7 @@ struct Lsoda {
       const double e = o.rtol * fabs(yc[i]) + o.atol;
       if (!(e > 0.0)) ok = false;
       ewi[i] = e;
-      ewt[i] = PW_DIV_INL(1.0, e);  // inline: the N reciprocals overlap
+      ewt[i] = PW_DIV(1.0, e);
     }
     return ok;
   }
