@@ -924,8 +924,12 @@ struct Lsoda {
       if ((nst - nslast) >= o.mxstep) return -1;
       if (!ewset(yh[1])) return -6;
     }
-    const double tolsf = kEps * vmnorm(yh[1]);
-    if (tolsf > 1.) return (nst == 0) ? -3 : -2;
+    // "too much accuracy requested" (tolsf = eps * ||y / (rtol |y| + atol)||_max > 1) needs
+    // rtol < eps: with atol >= 0 every weighted component is below 1 / rtol.  Not evaluated otherwise.
+    if (!(o.rtol >= kEps && o.atol >= 0.)) {
+      const double tolsf = kEps * vmnorm(yh[1]);
+      if (tolsf > 1.) return (nst == 0) ? -3 : -2;
+    }
     if ((tn + h) == tn) ++nhnil;
     stoda();
     if (kflag == 0) {
