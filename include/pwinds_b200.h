@@ -33,7 +33,12 @@ enum pwb_status {
   PWB_FAIL_H_SOLVER = 1,   /* hydrogen.py:458-460, :511-513 RuntimeError */
   PWB_FAIL_HE_SOLVER = 2,  /* helium.py:693-697, :708-710 RuntimeError */
   PWB_WARN_HE_RELAX = 3,   /* helium.py:736 odeint warning inside the relax loop */
-  PWB_FAIL_NAN = 4
+  PWB_FAIL_NAN = 4,
+  /* The hydrogen RK45 solve was given up after pwb_h_opts.max_nfev right-hand-side evaluations.
+   * No reference equivalent: scipy's RK45 has no step limit; on a stiff start (cold, dense winds,
+   * e.g. T0 = 5000 K, Mdot = 7e9 g/s, h = 0.85, tidal) the reference crawls for 1.9e8
+   * evaluations -- hours -- before it raises its RuntimeError. */
+  PWB_FAIL_WORK_LIMIT = 5
 };
 
 enum pwb_he_method { PWB_HE_ODEINT = 0, PWB_HE_LSODA = 1, PWB_HE_RK45 = 2 };
@@ -53,6 +58,9 @@ typedef struct {
   double rtol, atol;           /* solve_ivp RK45 options (1e-3, 1e-6 = scipy defaults) */
   double first_step, max_step; /* <= 0: scipy default */
   int structure_tidal;         /* Parker structure written for the He stage: 0 plain, 1 tidal */
+  long long max_nfev;          /* RK45 right-hand-side evaluations per solve before the model is given
+                                * up with PWB_FAIL_WORK_LIMIT; 0 = the default (2 000 000, ~1000x a
+                                * typical solve); < 0 = no limit, like scipy */
 } pwb_h_opts;
 
 /* Options of helium.population_fraction (helium.py:413-421). */
@@ -119,7 +127,11 @@ typedef struct {
 int pwb_create(int device, pwb_ctx** out);
 void pwb_destroy(pwb_ctx* ctx);
 const char* pwb_last_error(pwb_ctx* ctx);
+/* "p_winds_b200 <version> (sm_100a) src:<sha256[:16] of csrc/ and this header>" */
 const char* pwb_version(void);
+/* sizeof the option blocks as compiled (0 pwb_h_opts, 1 pwb_he_opts, 2 pwb_o_opts, 3 pwb_c_opts,
+ * 4 pwb_rt_opts): lets a binding check its struct layout against the library without a GPU */
+int pwb_sizeof_opts(int which);
 /* number of kernels this context has launched so far (bench.py `gpu_launches`) */
 long long pwb_launch_count(pwb_ctx* ctx);
 /* terms of the pixel sum of the current geometry (lit, in-range pixels after equal-radius
@@ -248,6 +260,14 @@ int pwb_forward_batch(pwb_ctx* ctx, int B, const double* d_T, const double* d_md
                       const double* d_wl, int Nw, double* d_spectrum, double* d_f_r, double* d_f1,
                       double* d_f3, double* d_v, double* d_rho, double* d_hscal, double* d_hescal,
                       int* d_status, void* stream);
+
+/* ---- how chi^2 / log-likelihood score a model of status 3 (an `odeint` of the helium relax
+ *      loop warned, helium.py:736).  The reference does not check that call and carries on
+ *      with rows scipy left uninitialised, so its own result for such a model is not
+ *      reproducible; the engine stops at the warning and returns the last completed pass.
+ *      accept = 0 (default): status 3 is a failed model (+inf / -inf);
+ *      accept = 1: the spectrum of the last completed pass is scored like any other. */
+int pwb_set_relax_warning_policy(pwb_ctx* ctx, int accept);
 
 /* ---- chi^2 of each model spectrum against data (advanced_tutorial.ipynb:432-438):
  *      chi2[b] = sum_k ((data_k - model_bk / norm) / sigma_k)^2 ; failed models -> +inf */

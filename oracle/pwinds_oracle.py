@@ -422,8 +422,16 @@ def he_population(r, v, rho, f_h, r_pl, T, h_fraction, vs, rs, rhos, sed=None,
     """helium.py:413-785.  `rates` optionally carries the 6 SED scalars of
     `he_radiative_processes` (they are model independent).  Returns dict: f_1, f_3,
     status (0 ok, 2 = first-solve failure -> RuntimeError at :696/:709,
-    3 = a relax-loop odeint warned, which the reference does not turn into an
-    error, :736), n_relax, nfe (list)."""
+    3 = a relax-loop odeint warned, :736), n_relax, nfe (list).
+
+    Status 3.  The reference does not check the relax loop's ``odeint`` (:736) and
+    carries on with the result array, whose rows after the failing output point
+    scipy leaves UNINITIALISED -- the unmodified reference differs from itself run
+    to run on such models (tests/golden/he_failure_classes.npz, key
+    ``f_1_run_spread``).  Only the class is defined: everything up to the first
+    warning is deterministic.  This restatement (and the engine) stop there:
+    status 3, ``n_relax`` = the pass that warned, profiles = those of the last
+    pass that completed."""
     y0 = np.array(initial_state, dtype=float)
     rs_cm = rs * 7.1492E+09
     alpha_unit = (rs_cm ** 2 * vs * 1E5)
@@ -501,9 +509,7 @@ def he_population(r, v, rho, f_h, r_pl, T, h_fraction, vs, rs, rhos, sed=None,
             out['nst'].append(int(info['nst'][-1]))
             out['nje'].append(int(info['nje'][-1]))
             if len(w) > 0:
-                if first:
-                    return None
-                out['status'] = 3
+                return None if first else 'warned'
             return np.copy(sol).T[0], np.copy(sol).T[1]
         with warnings.catch_warnings():
             warnings.simplefilter('ignore')
@@ -533,6 +539,10 @@ def he_population(r, v, rho, f_h, r_pl, T, h_fraction, vs, rs, rhos, sed=None,
             if s is None:
                 out['status'] = 2
                 return out
+            if isinstance(s, str):  # odeint warned inside the relax loop: see the docstring
+                out['status'] = 3
+                f1, f3 = p1, p3
+                break
             f1, f3 = clamp(s[0]), clamp(s[1])
             d1 = abs(np.sum(f1 - p1)) / np.sum(p1)
             d3 = abs(np.sum(f3 - p3)) / np.sum(p3)

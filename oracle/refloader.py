@@ -1,17 +1,31 @@
-"""Import the UNMODIFIED reference (``/root/reference/p_winds``) with the two
-stand-in packages on ``sys.path``.  TEST INFRASTRUCTURE ONLY: used by
-``oracle/make_golden.py`` and by CPU tests that are skipped when the reference
-tree is absent (it does not exist on the GPU box)."""
+"""Import the UNMODIFIED reference with the two stand-in packages on ``sys.path``.
+TEST / BENCH INFRASTRUCTURE ONLY: used by ``oracle/make_golden.py``,
+``oracle/make_anchors.py``, by CPU tests that are skipped when no reference tree is
+present, and by the reference arm / ``cpu_baseline`` leg of ``bench.py``.
+
+Where the reference is looked for, in this order: ``$PWINDS_REFERENCE_ROOT``,
+``/root/reference`` (the build container), ``oracle/_ref`` (the byte-for-byte copy that
+``oracle/build_ref.py`` makes so that the reference travels to the GPU box)."""
 import os
 import sys
 import warnings
 
-REFERENCE_ROOT = os.environ.get('PWINDS_REFERENCE_ROOT', '/root/reference')
-_STANDINS = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'standins')
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_STANDINS = os.path.join(_HERE, 'standins')
+
+
+def _find():
+    for p in (os.environ.get('PWINDS_REFERENCE_ROOT'), '/root/reference', os.path.join(_HERE, '_ref')):
+        if p and os.path.isfile(os.path.join(p, 'p_winds', 'helium.py')):
+            return p
+    return os.environ.get('PWINDS_REFERENCE_ROOT', '/root/reference')
+
+
+REFERENCE_ROOT = _find()
 
 
 def available():
-    return os.path.isdir(os.path.join(REFERENCE_ROOT, 'p_winds'))
+    return os.path.isfile(os.path.join(REFERENCE_ROOT, 'p_winds', 'helium.py'))
 
 
 def load():

@@ -18,7 +18,7 @@ class HOpts(C.Structure):
                 ('max_n_relax', C.c_int), ('relax_solution', C.c_int),
                 ('exact_phi', C.c_int), ('phi_abs', C.c_double), ('a_0', C.c_double),
                 ('rtol', C.c_double), ('atol', C.c_double), ('first_step', C.c_double),
-                ('max_step', C.c_double), ('structure_tidal', C.c_int)]
+                ('max_step', C.c_double), ('structure_tidal', C.c_int), ('max_nfev', C.c_longlong)]
 
 
 class HeOpts(C.Structure):
@@ -59,6 +59,7 @@ SYMBOLS = {
     'pwb_destroy': (None, [_VP]),
     'pwb_last_error': (C.c_char_p, [_VP]),
     'pwb_version': (C.c_char_p, []),
+    'pwb_sizeof_opts': (_I, [_I]),
     'pwb_launch_count': (C.c_longlong, [_VP]),
     'pwb_n_active_pixels': (_I, [_VP]),
     'pwb_set_sed': (_I, [_VP, _VP, _VP, _I, _VP]),
@@ -85,6 +86,7 @@ SYMBOLS = {
     'pwb_forward_batch': (_I, [_VP, _I, _VP, _VP, _VP, _VP, _I, C.POINTER(HOpts), C.POINTER(HeOpts),
                                C.POINTER(RtOpts), _I, _VP, _I, _VP, _VP, _VP, _VP, _VP, _VP, _VP,
                                _VP, _VP, _VP]),
+    'pwb_set_relax_warning_policy': (_I, [_VP, _I]),
     'pwb_chi2_batch': (_I, [_VP, _I, _VP, _I, _VP, _VP, _D, _VP, _VP, _VP]),
     'pwb_draw_transit': (_I, [_VP, _D, _D, _D, _D, _I, _I, _I, c_double_p, _VP, _VP, c_double_p, _VP]),
     'pwb_fp64_peak': (_I, [_VP, c_double_p, _VP]),

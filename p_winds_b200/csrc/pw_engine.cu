@@ -78,6 +78,10 @@ struct pwb_ctx {
     double depth = 0.0;  // geometric transit depth added to the spectrum of this phase
     bool ready = false;
   } geo[kMaxGeo];
+  // chi^2 / log-likelihood of a model whose relax loop met an odeint warning (status 3): 0 =
+  // failed model (+inf / -inf, the default: the reference's own result is undefined there),
+  // 1 = score the spectrum of the last completed pass
+  int accept_relax_warning = 0;
   int n_geo = 1;         // phases the pixel sum averages over
   int geo_nr = 0;
   DevBuf geo_r;
@@ -142,6 +146,7 @@ __device__ __forceinline__ HParams h_params(const pwb_h_opts& o, double T, doubl
   p.initial_f_ion = o.initial_f_ion; p.convergence = o.convergence; p.max_n_relax = o.max_n_relax;
   p.relax = o.relax_solution; p.exact_phi = o.exact_phi; p.phi_abs = o.phi_abs; p.a0 = o.a_0;
   p.ivp.rtol = o.rtol; p.ivp.atol = o.atol; p.ivp.first_step = o.first_step; p.ivp.max_step = o.max_step;
+  p.ivp.max_nfev = (o.max_nfev == 0) ? 2000000ll : (o.max_nfev < 0 ? 0ll : o.max_nfev);
   p.out_tidal = o.structure_tidal;
   return p;
 }
@@ -372,8 +377,7 @@ k_helium(int B, HeSched sched, const int* __restrict__ order, const double* __re
   for (int k = 0; k < 6; ++k) p.rates[k] = o.rates[k];
   p.method = o.method; p.rtol = o.rtol; p.atol = o.atol; p.first_step = o.first_step; p.max_step = o.max_step;
   double* wb = work + (size_t)b * wstride;
-  HeWork w{wb, wb + nr, wb + 2 * nr, wb + 3 * nr, wb + 4 * nr, wb + 5 * nr, wb + 10 * nr,
-           wstride > (size_t)kHeWorkPerRadius * nr ? wb + kHeWorkPerRadius * nr : nullptr};
+  HeWork w{wb, wb + nr, wb + 2 * nr, wb + 3 * nr, wb + 4 * nr, wb + 5 * nr, wb + 10 * nr};
   HeOut out{f1 + (size_t)b * nr, f3 + (size_t)b * nr, scal + (size_t)b * 4,
             rates ? rates + (size_t)b * 11 * nr : nullptr, status + b};
 #if defined(PW_HE_TIMING)
@@ -742,7 +746,7 @@ __global__ void k_rt_reduce(int B, int nw, int nsplit, const double* __restrict_
 
 __global__ void k_chi2(int B, int nw, const double* __restrict__ spec, const double* __restrict__ data,
                        const double* __restrict__ sigma, double norm, const int* __restrict__ status,
-                       double* chi2) {
+                       int accept_warn, double* chi2) {
   __shared__ double red[40];
   const int b = blockIdx.x;
   double s = 0.0;
@@ -752,7 +756,7 @@ __global__ void k_chi2(int B, int nw, const double* __restrict__ spec, const dou
   }
   const double t = block_sum(s, red);
   if (threadIdx.x == 0) {
-    const bool bad = status && status[b] != PW_OK && status[b] != PW_WARN_HE_RELAX;
+    const bool bad = status && status[b] != PW_OK && !(accept_warn && status[b] == PW_WARN_HE_RELAX);
     chi2[b] = bad ? (1.0 / 0.0) : t;
   }
 }
@@ -788,7 +792,8 @@ __global__ void k_convolve_extend(int B, int nw, const double* __restrict__ spec
 // log-likelihood of advanced_tutorial.ipynb cell 15: -0.5 * sum((y - m)^2 / yerr^2 + log(yerr^2)),
 // -inf where the model failed (the notebook's `except RuntimeError`)
 __global__ void k_loglike(int B, int nw, const double* __restrict__ model, const double* __restrict__ y,
-                          const double* __restrict__ yerr, const int* __restrict__ status, double* out) {
+                          const double* __restrict__ yerr, const int* __restrict__ status, int accept_warn,
+                          double* out) {
   __shared__ double red[40];
   const int b = blockIdx.x;
   double s = 0.0;
@@ -799,7 +804,7 @@ __global__ void k_loglike(int B, int nw, const double* __restrict__ model, const
   }
   const double t = block_sum(s, red);
   if (threadIdx.x == 0) {
-    const bool bad = status && status[b] != PW_OK && status[b] != PW_WARN_HE_RELAX;
+    const bool bad = status && status[b] != PW_OK && !(accept_warn && status[b] == PW_WARN_HE_RELAX);
     out[b] = bad ? -(1.0 / 0.0) : -0.5 * t;
   }
 }
@@ -927,7 +932,23 @@ __global__ void k_mu0(int B, const double* __restrict__ hfrac, double* mu0) {
 // ------------------------------------------------------------------------------------
 extern "C" {
 
-const char* pwb_version(void) { return "p_winds_b200 0.1 (sm_100a)"; }
+// PW_SRC_HASH: sha256 (first 16 hex digits) of csrc/* and include/pwinds_b200.h, passed by the build
+// (__graft_entry__.build / build.sh) so that a shipped binary can be matched to its sources.
+#ifndef PW_SRC_HASH
+#define PW_SRC_HASH "unknown"
+#endif
+const char* pwb_version(void) { return "p_winds_b200 0.2 (sm_100a) src:" PW_SRC_HASH; }
+
+int pwb_sizeof_opts(int which) {
+  switch (which) {
+    case 0: return (int)sizeof(pwb_h_opts);
+    case 1: return (int)sizeof(pwb_he_opts);
+    case 2: return (int)sizeof(pwb_o_opts);
+    case 3: return (int)sizeof(pwb_c_opts);
+    case 4: return (int)sizeof(pwb_rt_opts);
+    default: return -1;
+  }
+}
 
 int pwb_create(int device, pwb_ctx** out) {
   if (!out) return -1;
@@ -1145,7 +1166,7 @@ static int launch_helium(pwb_ctx* c, cudaStream_t s, int B, const double* d_T, c
   }
   const int* ord = sorted ? order : nullptr;
   const int blocks = sched.warp0[sched.nseg];
-  const size_t ws = he_work_doubles(Nr, o->relax_solution, o->max_n_relax, o->method);
+  const size_t ws = (size_t)kHeWorkPerRadius * Nr;
   if (o->method == PW_HE_RK45)
     k_helium<true><<<blocks, 32, 0, s>>>(B, sched, ord, d_T, d_hfrac, d_vs, d_rs, d_rhos, sstride, d_r, Nr, d_v, d_rho,
                                          d_f_h, *o, c->lsoda_tab.as<LsodaTables>(), work, ws, d_f1, d_f3, d_scal,
@@ -1169,7 +1190,7 @@ int pwb_he_population_batch(pwb_ctx* c, int B, const double* d_T, const double* 
   if (B <= 0) return 0;
   if (Nr < 2) return fail(c, "pwb_he_population_batch: radius profile needs >= 2 points");
   if (o->method < 0 || o->method > 2) return fail(c, "pwb_he_population_batch: unsupported method");
-  if (c->he_work.ensure(sizeof(double) * he_work_doubles(Nr, o->relax_solution, o->max_n_relax, o->method) * B) ||
+  if (c->he_work.ensure(sizeof(double) * (size_t)kHeWorkPerRadius * Nr * B) ||
       c->he_order.ensure(sizeof(int) * (size_t)B))
     return fail(c, "out of device memory");
   return launch_helium(c, (cudaStream_t)stream, B, d_T, d_hfrac, d_vs, d_rs, d_rhos, sstride, d_r, Nr, d_v, d_rho,
@@ -1419,7 +1440,7 @@ int pwb_forward_batch(pwb_ctx* c, int B, const double* d_T, const double* d_mdot
   if (c->fw_f.ensure(sizeof(double) * (bn * 5 + B)) || c->fw_scal.ensure(sizeof(double) * (size_t)B * 8) ||
       c->fw_he.ensure(sizeof(double) * (size_t)B * 4) || c->fw_n.ensure(sizeof(double) * bn) ||
       c->fw_v.ensure(sizeof(double) * bn) || c->fw_T.ensure(sizeof(double) * B) ||
-      c->he_work.ensure(sizeof(double) * he_work_doubles(Nr, heopts->relax_solution, heopts->max_n_relax, heopts->method) * B) ||
+      c->he_work.ensure(sizeof(double) * (size_t)kHeWorkPerRadius * Nr * B) ||
       c->he_order.ensure(sizeof(int) * (size_t)B) || c->rt_ncol.ensure(sizeof(double) * bn) ||
       c->rt_sums.ensure(sizeof(double) * (size_t)B * 4) ||
       c->rt_partial.ensure(sizeof(double) * (size_t)B * nsplit * Nw) ||
@@ -1459,11 +1480,18 @@ int pwb_forward_batch(pwb_ctx* c, int B, const double* d_T, const double* d_mdot
                    c->rt_partial.as<double>(), c->rt_tau.as<double>());
 }
 
+int pwb_set_relax_warning_policy(pwb_ctx* c, int accept) {
+  if (!c) return -1;
+  c->accept_relax_warning = accept ? 1 : 0;
+  return 0;
+}
+
 int pwb_chi2_batch(pwb_ctx* c, int B, const double* d_spectrum, int Nw, const double* d_data,
                    const double* d_sigma, double norm, const int* d_status, double* d_chi2, void* stream) {
   if (!c) return -1;
   if (B <= 0) return 0;
-  k_chi2<<<B, 128, 0, (cudaStream_t)stream>>>(B, Nw, d_spectrum, d_data, d_sigma, norm, d_status, d_chi2);
+  k_chi2<<<B, 128, 0, (cudaStream_t)stream>>>(B, Nw, d_spectrum, d_data, d_sigma, norm, d_status,
+                                              c->accept_relax_warning, d_chi2);
   c->launches++;
   PWB_CUDA(c, cudaGetLastError());
   return 0;
@@ -1488,7 +1516,8 @@ int pwb_loglike_batch(pwb_ctx* c, int B, const double* d_model, int Nw, const do
                       const int* d_status, double* d_out, void* stream) {
   if (!c) return -1;
   if (B <= 0) return 0;
-  k_loglike<<<B, 128, 0, (cudaStream_t)stream>>>(B, Nw, d_model, d_y, d_yerr, d_status, d_out);
+  k_loglike<<<B, 128, 0, (cudaStream_t)stream>>>(B, Nw, d_model, d_y, d_yerr, d_status,
+                                                 c->accept_relax_warning, d_out);
   c->launches++;
   PWB_CUDA(c, cudaGetLastError());
   return 0;

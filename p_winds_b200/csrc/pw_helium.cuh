@@ -114,7 +114,7 @@ struct HeRhs {
     // detour through logarithms to avoid overflow, which cannot happen in binary64
     // here (k1 * rho < 1e45); its round trip carries ~|log|*eps ~ 1e-14 relative
     // rounding noise, the plain product 2e-16.  The product is the default; build with
-    // -DPW_HE_LOGEXP for the literal form (tests/test_parity_gpu.py covers both).
+    // -DPW_HE_LOGEXP for the literal form (host build: tests/test_hostsim_stages.py compares both).
     c[0] = (kc[0] * rho_) * fh_;
     c[1] = (kc[1] * rho_) * fh_;
     c[2] = (kc[2] * rho_) * fh_;
@@ -193,14 +193,8 @@ struct HeWork {
   double *rn, *tau1, *tau3, *tau1h, *tau3h;
   double* w;      // 5*Nr: [0,Nr) dr*density, [Nr,3Nr) previous profiles, [3Nr,5Nr) RK45 output staging
   double* slope;  // 5*Nr: np.interp slopes (fp[j+1]-fp[j])/(xp[j+1]-xp[j]) of v, rho, fh, tau1, tau3
-  double* hist;   // (max_n_relax+1)*2*Nr or null: the profiles after every pass (he_relax_cycle)
 };
-constexpr int kHeWorkPerRadius = 15;  // doubles of HeWork per radius and model, without `hist`
-// doubles of scratch per model: the fixed part + the per-pass history of the relax loop
-PW_HD size_t he_work_doubles(int nr, int relax, int max_n_relax, int method) {
-  const bool hist = relax && max_n_relax + 1 > 3 && max_n_relax + 1 <= 32 && method == 0 /*PW_HE_ODEINT*/;
-  return (size_t)nr * (kHeWorkPerRadius + (hist ? 2 * (max_n_relax + 1) : 0));
-}
+constexpr int kHeWorkPerRadius = 15;  // doubles of HeWork per radius and model
 
 // slope table of one interpolated profile, exactly as numpy forms each slope
 PW_HD_NOINLINE void he_slopes(const double* xp, const double* fp, int n, double* out) {
@@ -264,41 +258,27 @@ PW_HD bool he_solve(const HeParams& p, HeRhs& rhs, const LsodaTables& tab, int n
       s.new_call();  // the next output radius is a new lsoda call: nslast = nst
     }
   }
-  // odeint stops at the first failing output point (ODEintWarning) and leaves the
-  // remaining rows of its zero-initialised result array untouched
-  for (int q = k; q < nr; ++q) { f1[q] = 0.0; f3[q] = 0.0; }
+  // odeint stops at the first failing output point (ODEintWarning).  scipy does not
+  // initialise its result array, so rows k.. of the reference's output are stale heap: there
+  // is nothing to reproduce, and the callers below discard f1 / f3 of a failed solve.
   *nfe += s.nfe; *nst += s.nst; *nje += s.nje;
   return ok;
 }
 
-// Exact shortcut of the relax loop (helium.py:723-763).  A pass maps the clamped profiles
-// (f1, f3) of the previous pass to new ones and nothing else carries over, so when the
-// profiles after pass `it` are bit-for-bit those after an earlier pass j the loop has entered
-// a cycle of period P = it - j: every later pass repeats one already made, including its
-// (failed) convergence test, and the reference runs on to max_n_relax.  This happens where
-// odeint gives up in the first interval of a relax pass (all-zero rows -> the same optical
-// depths as the last time) -- the models that would otherwise cost 2-4x any other.  Returns
-// the earlier pass j whose profiles equal those of pass `it`, or -1.
-constexpr int kHeMaxPass = 32;
-PW_HD_NOINLINE int he_relax_cycle(const double* hist, const unsigned long long* hh, int it, int nr) {
-  for (int j = it - 1; j >= 0; --j) {
-    if (hh[j] != hh[it]) continue;
-    const double* a = hist + (size_t)j * 2 * nr;
-    const double* b = hist + (size_t)it * 2 * nr;
-    bool same = true;
-    for (int i = 0; i < 2 * nr && same; ++i) same = (a[i] == b[i]);
-    if (same) return j;
-  }
-  return -1;
-}
-
-PW_HD unsigned long long he_hash_mix(unsigned long long h, double x) {
-  union { double d; unsigned long long u; } c;
-  c.d = x;
-  h ^= c.u + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2);
-  return h;
-}
-
+// Failure classes of the reference (helium.py):
+//   status 2  the first solve warns / comes back short -> RuntimeError (:691-697, :708-710).
+//             A short solve_ivp output inside the relax loop (:741-745) ends the reference with
+//             a shape-mismatch ValueError at :753; the engine files it under status 2 as well.
+//             Profiles NaN.
+//   status 3  an `odeint` of the relax loop warns (:736).  The reference does not check it
+//             and carries on with the rows scipy left uninitialised, so its result for such a
+//             model is not reproducible (tests/golden/he_failure_classes.npz records the
+//             run-to-run spread of the unmodified reference).  What IS deterministic is the
+//             class itself -- everything up to the first warning is.  The engine therefore
+//             stops at that warning: status 3, n_relax = the pass that warned, and f1 / f3 =
+//             the profiles of the last pass that completed (the state the failing pass started
+//             from).  chi^2 / log-likelihood treat status 3 as a failed model unless asked
+//             otherwise (include/pwinds_b200.h).
 // `r` radius profile in planetary radii (shared), v / rho / f_h per model.
 template <bool kRk45>
 PW_HD void he_population_model(const HeParams& p, const LsodaTables& tab, const double* __restrict__ r,
@@ -372,11 +352,7 @@ PW_HD void he_population_model(const HeParams& p, const LsodaTables& tab, const 
   // pass 0 = the first solve (helium.py:688-718); passes 1..max_n_relax = the relax loop
   // (:723-763).  One call site keeps a single copy of the integrator in the kernel.
   const int n_pass = p.relax ? p.max_n_relax + 1 : 1;
-  const bool track = (w.hist != nullptr) && n_pass > 3 && n_pass <= kHeMaxPass && p.method == PW_HE_ODEINT;
-  unsigned long long hh[kHeMaxPass];
-  int cnt[kHeMaxPass][3];
   for (int it = 0; it < n_pass; ++it) {
-    const int nfe0 = nfe, nst0 = nst, nje0 = nje;
     double s1 = 0.0, s3 = 0.0;
     if (it > 0) {
       ++n_relax;
@@ -399,7 +375,11 @@ PW_HD void he_population_model(const HeParams& p, const LsodaTables& tab, const 
         status = PW_FAIL_HE_SOLVER;  // helium.py:693-697, :708-710 (short solve_ivp output)
         break;
       }
-      status = PW_WARN_HE_RELAX;     // helium.py:736 is outside the warnings->error guard
+      // helium.py:736 is outside the warnings->error guard: the reference's result is undefined
+      // from here on (see above).  Stop, and hand back the last completed pass.
+      status = PW_WARN_HE_RELAX;
+      for (int i = 0; i < nr; ++i) { f1[i] = p1[i]; f3[i] = p3[i]; }
+      break;
     }
     clamp();
     if (it > 0) {
@@ -407,34 +387,6 @@ PW_HD void he_population_model(const HeParams& p, const LsodaTables& tab, const 
       for (int i = 0; i < nr; ++i) { d1 += f1[i] - p1[i]; d3 += f3[i] - p3[i]; }
       const double rel1 = fabs(d1) / s1, rel3 = fabs(d3) / s3;
       if (rel1 < p.convergence && rel3 < p.convergence) break;
-    }
-    if (track) {
-      double* hrow = w.hist + (size_t)it * 2 * nr;
-      unsigned long long hv = 0;
-      for (int i = 0; i < nr; ++i) {
-        hrow[i] = f1[i]; hrow[nr + i] = f3[i];
-        hv = he_hash_mix(he_hash_mix(hv, f1[i]), f3[i]);
-      }
-      hh[it] = hv;
-      cnt[it][0] = nfe - nfe0; cnt[it][1] = nst - nst0; cnt[it][2] = nje - nje0;
-      const int j = (it >= 1 && it < n_pass - 1) ? he_relax_cycle(w.hist, hh, it, nr) : -1;
-      if (j >= 0) {
-        // the remaining passes m = it+1 .. n_pass-1 repeat passes of the cycle (pass m does the
-        // work of pass j + (m-j) mod P, P = it - j; of pass `it` when that is j itself, since
-        // it starts from the profiles of pass it-1): same work counters, and the loop ends
-        // on the profiles of the pass that n_pass-1 maps to (status already carries the
-        // odeint warning, set in one of the repeated passes)
-        const int P = it - j;
-        for (int m = it + 1; m < n_pass; ++m) {
-          const int rr = (m - j) % P, src = (rr == 0) ? it : j + rr;
-          nfe += cnt[src][0]; nst += cnt[src][1]; nje += cnt[src][2];
-        }
-        const int fin = j + (n_pass - 1 - j) % P;
-        const double* hf = w.hist + (size_t)fin * 2 * nr;
-        for (int i = 0; i < nr; ++i) { f1[i] = hf[i]; f3[i] = hf[nr + i]; }
-        n_relax = p.max_n_relax;
-        break;
-      }
     }
   }
   if (status == PW_FAIL_HE_SOLVER) {

@@ -228,7 +228,8 @@ PW_HD void h_pass_solve(const HParams& p, const double* __restrict__ r, int nr, 
   ++s->n_solves;
   if (pass > 0) s->n_relax = pass;
   if (got != nr) {
-    s->status = PW_FAIL_H_SOLVER;  // len(f_r) != len(r) -> RuntimeError (:458-460, :511-513)
+    // len(f_r) != len(r) -> RuntimeError (:458-460, :511-513); or the engine's own work limit
+    s->status = st.limit ? PW_FAIL_WORK_LIMIT : PW_FAIL_H_SOLVER;
     s->done = 1;
     return;
   }

@@ -20,10 +20,17 @@ struct Rk45Opts {
   double rtol, atol;
   double first_step;  // <= 0: select automatically
   double max_step;    // <= 0: infinity
+  // Work limit (right-hand-side evaluations per solve); <= 0: none, as in scipy.  scipy's RK45
+  // has no step limit: on a stiff start it crawls at a step just above 10 ulp(t) -- e.g.
+  // hydrogen.ion_fraction at T0 = 5000 K, Mdot = 7.2e9 g/s, h = 0.85, tidal takes 1.9e8
+  // evaluations (hours in Python) before it fails.  The engine gives such a model up early and
+  // says so (status PW_FAIL_WORK_LIMIT), instead of holding a GPU thread for minutes.
+  long long max_nfev = 0;
 };
 
 struct Rk45Stats {
   int nfev, naccept, nreject;
+  int limit = 0;  // 1: stopped by Rk45Opts::max_nfev
 };
 
 #define PW_RK_C2 (1.0 / 5)
@@ -64,7 +71,8 @@ PW_HD_NOINLINE int rk45_solve(RHS& rhs, const double* __restrict__ t_eval, int n
   const double sqrtN = sqrt((double)N);
 
   double t = t0, y[N], f[N], K[7][N];
-  int nfev = 0, nacc = 0, nrej = 0;
+  long long nfev = 0;
+  int nacc = 0, nrej = 0;
   for (int c = 0; c < N; ++c) y[c] = y0[c];
   rhs(t, y, f); ++nfev;
 
@@ -123,7 +131,11 @@ PW_HD_NOINLINE int rk45_solve(RHS& rhs, const double* __restrict__ t_eval, int n
     double h = 0.0, t_new = t, y_new[N];
     while (!accepted) {
       if (ha < min_step) {  // TOO_SMALL_STEP -> solver.status = 'failed'
-        if (st) { st->nfev = nfev; st->naccept = nacc; st->nreject = nrej; }
+        if (st) { st->nfev = (int)(nfev < 2000000000 ? nfev : 2000000000); st->naccept = nacc; st->nreject = nrej; }
+        return n_out;
+      }
+      if (o.max_nfev > 0 && nfev >= o.max_nfev) {  // work limit (no scipy counterpart, see Rk45Opts)
+        if (st) { st->nfev = (int)(nfev < 2000000000 ? nfev : 2000000000); st->naccept = nacc; st->nreject = nrej; st->limit = 1; }
         return n_out;
       }
       h = ha * 1.0;
@@ -206,7 +218,7 @@ PW_HD_NOINLINE int rk45_solve(RHS& rhs, const double* __restrict__ t_eval, int n
     for (int c = 0; c < N; ++c) { y[c] = y_new[c]; f[c] = K[6][c]; }
     if (1.0 * (t - t_bound) >= 0) finished = true;
   }
-  if (st) { st->nfev = nfev; st->naccept = nacc; st->nreject = nrej; }
+  if (st) { st->nfev = (int)(nfev < 2000000000 ? nfev : 2000000000); st->naccept = nacc; st->nreject = nrej; }
   return n_out;
 }
 

@@ -12,6 +12,9 @@ from . import _lib
 STATUS_MESSAGES = {
     1: 'The solver ``solve_ivp`` failed to obtain a solution.',   # hydrogen.py:459
     2: 'The solver ``odeint`` failed to obtain a solution.',      # helium.py:696
+    # no reference counterpart: the reference's RK45 has no step limit and would crawl for minutes to hours
+    5: 'The solver ``solve_ivp`` was given up after max_nfev right-hand-side evaluations '
+       '(stiff start; the reference itself needs ~1e8 evaluations here before it fails).',
 }
 HE_METHODS = {'odeint': 0, 'LSODA': 1, 'RK45': 2}
 O_METHODS = {'Radau': 0, 'odeint': 1, 'RK45': 2}
@@ -78,6 +81,7 @@ class Engine:
         wl, fl = self.dev(wavelength_angstrom), self.dev(flux_cgs)
         self._check(self.lib.pwb_set_sed(self.ctx, _ptr(wl), _ptr(fl), wl.numel(), self._stream()))
         self._keep['sed'] = (wl, fl)
+        self._sed_key = None   # an uncached upload invalidates what set_sed_cached remembers
 
     def set_sed_cached(self, wavelength_angstrom, flux_cgs):
         wl = np.ascontiguousarray(wavelength_angstrom, dtype=float)
@@ -119,14 +123,17 @@ class Engine:
     def h_opts(planet_radius, planet_mass, star_mass=1.0, semimajor_axis=1.0, initial_f_ion=0.0,
                relax_solution=False, convergence=0.01, max_n_relax=10, exact_phi=False,
                phi_abs=0.0, a_0=0.0, rtol=1e-3, atol=1e-6, first_step=None, max_step=None,
-               structure_tidal=False):
+               structure_tidal=False, max_nfev=0):
+        """`max_nfev`: RK45 right-hand-side evaluations per solve before a model is given up with
+        status 5 (0 = the default of 2 000 000; < 0 = no limit, like the reference -- a GPU thread may then run
+        for minutes on a model the reference itself needs hours to fail on)."""
         return _lib.HOpts(float(planet_radius), float(planet_mass), float(star_mass),
                           float(semimajor_axis), float(initial_f_ion), float(convergence),
                           int(max_n_relax), int(bool(relax_solution)), int(bool(exact_phi)),
                           float(phi_abs), float(a_0), float(rtol), float(atol),
                           float(first_step) if first_step else 0.0,
                           float(max_step) if (max_step and np.isfinite(max_step)) else 0.0,
-                          int(bool(structure_tidal)))
+                          int(bool(structure_tidal)), int(max_nfev))
 
     def h_ion_fraction_batch(self, T, mdot, h_fraction, mu0, r, opts, return_rates=False):
         T, mdot, hf, mu0, r = (self.dev(x).reshape(-1) for x in (T, mdot, h_fraction, mu0, r))
@@ -264,6 +271,7 @@ class Engine:
         self._check(self.lib.pwb_set_geometry(self.ctx, _ptr(i0), _ptr(rm), i0.numel(), _ptr(r),
                                               r.numel(), self._stream()))
         self._geo_nr = r.numel()
+        self._geo_key = None   # an uncached upload invalidates what set_geometry_cached remembers
 
     def set_geometry_phases(self, maps, radius_profile_si):
         """Phase-averaged transit (advanced_tutorial.ipynb cell 11): `maps` is a sequence of
@@ -371,6 +379,12 @@ class Engine:
         return {'spectrum': e(B, nw), 'f_r': e(B, nr), 'f_1': e(B, nr), 'f_3': e(B, nr),
                 'v': e(B, nr), 'rho': e(B, nr), 'hscal': e(B, 8), 'hescal': e(B, 4),
                 'status': torch.zeros(B, dtype=torch.int32, device=self.device)}
+
+    def set_relax_warning_policy(self, accept):
+        """How chi2_batch / loglike_batch score models of status 3 (an odeint of the helium relax
+        loop warned; the reference's own result is undefined there).  False (default): failed
+        model, +inf / -inf.  True: score the spectrum of the last completed relax pass."""
+        self._check(self.lib.pwb_set_relax_warning_policy(self.ctx, 1 if accept else 0))
 
     def chi2_batch(self, spectrum, data, sigma, norm=1.0, status=None):
         spectrum = self.dev(spectrum)

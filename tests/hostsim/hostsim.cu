@@ -12,7 +12,14 @@
 
 using namespace pw;
 
+#ifndef PW_SRC_HASH
+#define PW_SRC_HASH "unknown"
+#endif
+extern "C" const char* hs_version(void) { return "hostsim src:" PW_SRC_HASH; }
+
 extern "C" {
+
+long long hs_h_max_nfev = 0;  // work limit of the hydrogen RK45 solve (0 = none, like scipy); set by tests
 
 void hs_parker(const double* r, int n, double* v, double* rho) {
   for (int i = 0; i < n; ++i) parker_point(r[i], &v[i], &rho[i]);
@@ -48,6 +55,7 @@ int hs_h_ion_fraction(const double* model /*T, mdot, h, mu0*/, const double* opt
   p.initial_f_ion = opts[4]; p.convergence = opts[5]; p.max_n_relax = (int)opts[6];
   p.relax = (int)opts[7]; p.exact_phi = (int)opts[8]; p.phi_abs = opts[9]; p.a0 = opts[10];
   p.ivp.rtol = opts[11]; p.ivp.atol = opts[12]; p.ivp.first_step = opts[13]; p.ivp.max_step = opts[14];
+  p.ivp.max_nfev = hs_h_max_nfev;
   p.out_tidal = (int)opts[15];
   SedTables t{n_h, 0, 0, gw, s_h, s_he};
   std::vector<double> buf(10 * nr + 40);
@@ -67,8 +75,6 @@ int hs_h_ion_fraction(const double* model /*T, mdot, h, mu0*/, const double* opt
 
 extern "C" {
 
-int hs_no_relax_cycle = 0;  // set to 1 by tests to run every relax pass literally
-
 // model: [T, h_fraction, vs, rs, rhos]; opts: [r_pl, y0_0, y0_1, relax, max_n_relax, convergence,
 //   method, rtol, atol, first_step, max_step]; rates[6]
 int hs_he_population(const double* model, const double* opts, const double* rates, const double* r,
@@ -83,12 +89,9 @@ int hs_he_population(const double* model, const double* opts, const double* rate
   p.max_n_relax = (int)opts[4]; p.convergence = opts[5]; p.method = (int)opts[6];
   p.rtol = opts[7]; p.atol = opts[8]; p.first_step = opts[9]; p.max_step = opts[10];
   for (int i = 0; i < 6; ++i) p.rates[i] = rates[i];
-  // opts[11] (optional, default on): 0 disables the relax-cycle shortcut (no pass history)
-  const size_t ws = he_work_doubles(nr, p.relax, p.max_n_relax, p.method);
-  std::vector<double> buf(ws);
+  std::vector<double> buf((size_t)kHeWorkPerRadius * nr);
   double* b = buf.data();
-  HeWork w{b, b + nr, b + 2 * nr, b + 3 * nr, b + 4 * nr, b + 5 * nr, b + 10 * nr,
-           (ws > (size_t)kHeWorkPerRadius * nr && !hs_no_relax_cycle) ? b + kHeWorkPerRadius * nr : nullptr};
+  HeWork w{b, b + nr, b + 2 * nr, b + 3 * nr, b + 4 * nr, b + 5 * nr, b + 10 * nr};
   int status = 0;
   HeOut o{f1, f3, scal, rates_out, &status};
   if (p.method == PW_HE_RK45) he_population_model<true>(p, tab, r, v, rho, f_h, nr, w, o);

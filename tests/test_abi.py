@@ -27,6 +27,22 @@ def test_header_symbols_exported(built):
     assert b'sm_100a' in lib.pwb_version()
 
 
+def test_option_blocks_match_the_compiled_layout(built):
+    """ctypes mirrors of the option structs vs sizeof in the library (no GPU needed)."""
+    from p_winds_b200 import _lib
+    lib = _lib.load()
+    for which, cls in enumerate((_lib.HOpts, _lib.HeOpts, _lib.OOpts, _lib.COpts, _lib.RtOpts)):
+        assert lib.pwb_sizeof_opts(which) == C.sizeof(cls), cls.__name__
+
+
+def test_library_reports_the_hash_of_its_sources(built):
+    """pwb_version() carries the sha256 of csrc/ + the header it was built from; build() rebuilds on a
+    content mismatch (not on mtimes), so the binary that ships to the GPU box is checkable there."""
+    from p_winds_b200 import _lib
+    v = _lib.load().pwb_version().decode()
+    assert v.endswith('src:' + built.source_hash()), v
+
+
 def test_library_contains_sm100a_code(built):
     import subprocess
     out = subprocess.run(['cuobjdump', '-lelf', built.LIB], capture_output=True, text=True).stdout

@@ -103,32 +103,142 @@ def test_forward_tight_tolerances_per_model(eng, name):
 
 
 # --------------------------------------------------------------------------- P3
-@pytest.mark.parametrize('name', ['anchors_default', 'anchors_default_tidal'])
-def test_forward_default_tolerances_statistical(eng, name):
-    d = golden(name)
-    o = _forward(eng, d['T0'], d['mdot'], d['h_fraction'], tight=False, tidal=bool(d['tidal']))
-    ref_ok = d['status'] != 1
-    gpu_ok = o['status'] != 1
-    # which models fail is part of the contract; a model sitting on the RK45
-    # min-step boundary may flip under 1-ulp noise (it does in the reference too)
-    assert (ref_ok != gpu_ok).sum() <= 1
-    assert (~gpu_ok).sum() >= 3
-    both = ref_ok & gpu_ok & (d['status'] == 0) & (o['status'] == 0)
-    assert both.sum() >= 15
-    e_fr = _rel(o['f_r'][both][:, 1:], d['f_r'][both][:, 1:]).max(axis=1)
-    e_f1 = _rel(o['f_1'][both], d['f_1'][both]).max(axis=1)
-    ipk = np.argmax(d['f_3'][both], axis=1)
-    e_f3 = _rel(o['f_3'][both], d['f_3'][both])[np.arange(both.sum()), ipk]
-    e_sp = _rel(o['spectrum'][both], d['spectrum'][both]).max(axis=1)
-    # oracle self-noise: f_r median 1e-12 / 9 % > 1e-6 / max 3e-3;
-    # f1 median 4.9e-6 / max 2.7e-5 (+ f_r noise); f3@peak 7.3e-6 / 1.3e-4; spectrum 7.5e-7 / 3.5e-5
-    assert np.median(e_fr) < 1e-6 and e_fr.max() < 2e-2
-    assert np.median(e_f1) < 2e-5 and e_f1.max() < 5e-3
-    assert np.median(e_f3) < 5e-5
-    assert np.median(e_sp) < 3e-6 and e_sp.max() < 1e-4
-    # the relax loops took the reference's number of passes for (almost) every model
+def _p3_forward(eng, d):
+    """The 272 anchor triples of tests/golden/anchors_p3.npz through forward_batch (reference
+    default tolerances), non-tidal and tidal halves, reassembled in fixture order."""
+    keys = ('status', 'f_r', 'f_1', 'f_3', 'spectrum', 'hscal')
+    o = {}
+    for tidal in (False, True):
+        m = d['tidal'] == tidal
+        part = _forward(eng, d['T0'][m], d['mdot'][m], d['h_fraction'][m], tight=False, tidal=tidal)
+        for k in keys:
+            if k not in o:
+                o[k] = np.zeros((len(d['T0']),) + part[k].shape[1:], dtype=part[k].dtype)
+            o[k][m] = part[k]
+    return o
+
+
+def test_p3_anchor_protocol(eng):
+    """SURVEY.md 8(c) protocol P3 as written, thresholds taken from the fixture.  At the reference's
+    default tolerances its own output moves under 1-ulp input noise (tests/golden/anchors_p3.npz:
+    K = 4 perturbed runs of the unmodified reference per model).  Pass =
+      * status agrees wherever the reference's own status is stable under that noise;
+      * per quantity: median engine-vs-reference deviation <= 2 x the median self-noise (floored at the
+        1e-10 of the deterministic maps); the fraction of models above the stated tolerance (1e-6
+        fractions, 1e-5 flux) <= the reference's own fraction + 5 points;
+      * per model: deviation <= max(stated, 3 x that model's own noise).  K = 4 runs do not sample a
+        chaotic model's noise fully, so the reference is held to the same rule (its 4th run against
+        the noise of the other three) and the engine may miss it on <= that share of models + 5 points."""
+    d = golden('anchors_p3')
+    o = _p3_forward(eng, d)
+    ref_st, st = d['status'], o['status']
+    # status 9: the reference did not finish within 90 s (RK45 crawling); the engine gives up (5) or fails (1)
+    crawl = ref_st == 9
+    assert np.isin(st[crawl], (1, 5)).all()
+    stable = (d['status_flips'] == 0) & ~crawl
+    mism = (st != ref_st) & stable
+    assert mism.sum() <= 2, np.flatnonzero(mism)
+    assert (st[ref_st == 1] == 1).mean() > 0.95 and (ref_st == 1).sum() >= 60
+    both = (ref_st == 0) & (st == 0)
+    assert both.sum() >= 150
+    ipk = np.argmax(d['f_3'], axis=1)
+    rows = np.arange(len(ipk))
+    dev = {'f_r': _rel(o['f_r'][:, 1:], d['f_r'][:, 1:]).max(axis=1),
+           'f_1': _rel(o['f_1'], d['f_1']).max(axis=1),
+           'f_3_peak': _rel(o['f_3'][rows, ipk], d['f_3'][rows, ipk]),
+           'spectrum': _rel(o['spectrum'], d['spectrum']).max(axis=1)}
+    stated = {'f_r': 1e-6, 'f_1': 1e-6, 'f_3_peak': 1e-6, 'spectrum': 1e-5}
+    report = {}
+    for k, e in dev.items():
+        e = e[both]
+        runs = d['noise_%s_runs' % k][both]                 # [n, K]
+        noise = np.nanmax(runs, axis=1)
+        med_ref = np.nanmedian(runs)
+        exc_ref = np.nanmean(runs > stated[k])
+        assert np.median(e) <= max(2 * med_ref, 1e-10), (k, np.median(e), med_ref)
+        assert (e > stated[k]).mean() <= exc_ref + 0.05, (k, (e > stated[k]).mean(), exc_ref)
+        miss = (e > np.maximum(stated[k], 3 * noise)).mean()
+        # the reference against the same rule: run K against the noise of runs 1..K-1
+        own = np.nanmax(runs[:, :-1], axis=1)
+        miss_ref = np.nanmean(runs[:, -1] > np.maximum(stated[k], 3 * own))
+        assert miss <= miss_ref + 0.05, (k, miss, miss_ref)
+        report[k] = (float(np.median(e)), float(med_ref), float(miss), float(miss_ref))
+    print('P3 (median engine, median self-noise, per-model miss engine, reference):', report)
     assert np.isfinite(o['spectrum'][both]).all()
-    assert np.isnan(o['spectrum'][~gpu_ok]).all()          # failed models carry no spectrum
+    assert np.isnan(o['spectrum'][(st == 1) | (st == 5)]).all()          # failed models carry no spectrum
+
+
+def test_helium_failure_classes_match_reference(eng):
+    """Status classes 2 / 3 of helium.population_fraction (helium.py:691-697, :736) on models of the bench
+    grid and of the strip around them, against the unmodified reference (tests/golden/
+    he_failure_classes.npz: 34 class-2, 32 class-3 models and 40 neighbours that succeed; each run
+    three times, plus four times under 1-ulp SED noise).  The class is compared wherever the
+    reference's own class is stable under that noise.  For class 3 the reference's *profiles* differ
+    from run to run (key f_1_run_spread: scipy leaves the rows after the failing point
+    uninitialised) -- nothing to compare; the engine returns the last completed pass, finite and
+    clamped, and chi^2 scores such a model +inf unless the caller opts in."""
+    d = golden('he_failure_classes')
+    o = _forward(eng, d['T0'], d['mdot'], d['h_fraction'])
+    st, ref = o['status'], d['status']
+    stable = (d['status_perturbed'] == ref[:, None]).all(axis=1)
+    assert (ref == 2).sum() >= 20 and (ref == 3).sum() >= 20
+    assert (d['f_1_run_spread'][ref == 3] > 0).sum() >= 10       # the reference is not reproducible there
+    assert (d['f_1_run_spread'][ref != 3] == 0).all()
+    flips = (st != ref) & stable
+    print('helium failure classes: %d of %d stable models differ; unstable models: %d, of which %d differ'
+          % (flips.sum(), stable.sum(), (~stable).sum(), ((st != ref) & ~stable).sum()))
+    assert flips.sum() <= 2, (np.flatnonzero(flips), st[flips], ref[flips])
+    w = st == 3
+    assert np.isfinite(o['f_1'][w]).all() and ((o['f_1'][w] >= 0) & (o['f_1'][w] <= 1)).all()
+    assert np.isfinite(o['spectrum'][w]).all() and np.isnan(o['spectrum'][st == 2]).all()
+    n_relax = o['hescal'][:, 0]
+    assert (n_relax[w] >= 1).all() and (n_relax[w] <= 10).all()
+    # chi^2 policy (pwb_set_relax_warning_policy): status 3 is a failed model by default
+    data, sigma = np.ones(200), np.full(200, 1e-3)
+    c0 = eng.chi2_batch(o['spectrum'], data, sigma, 1.0, o['status']).cpu().numpy()
+    assert np.isinf(c0[w]).all() and np.isinf(c0[st == 2]).all() and np.isfinite(c0[st == 0]).all()
+    eng.set_relax_warning_policy(True)
+    try:
+        c1 = eng.chi2_batch(o['spectrum'], data, sigma, 1.0, o['status']).cpu().numpy()
+    finally:
+        eng.set_relax_warning_policy(False)
+    assert np.isfinite(c1[w]).all() and np.isinf(c1[st == 2]).all()
+
+
+def test_bench_grid_status_map_matches_reference(eng):
+    """Every model of the 64 x 64 bench grid: the engine's status against the status the unmodified
+    reference ends with (tests/golden/bench_grid_status.npz, oracle/make_anchors.py scan: 4076 ok,
+    11 class 2, 9 class 3).  Models on a class boundary can flip under round-off (the reference's do
+    under 1-ulp noise, see he_failure_classes.npz), so a handful of differences is allowed -- and they
+    have to lie next to a model the reference itself fails."""
+    d = golden('bench_grid_status')
+    o = _forward(eng, d['T0'], d['mdot'], np.full(len(d['T0']), 0.9))
+    st, ref = o['status'].reshape(64, 64), d['status'].reshape(64, 64).astype(int)
+    diff = st != ref
+    print('bench grid: engine', {int(k): int((st == k).sum()) for k in np.unique(st)},
+          'reference', {int(k): int((ref == k).sum()) for k in np.unique(ref)}, 'differ', int(diff.sum()))
+    assert diff.sum() <= 12
+    assert abs(int((st != 0).sum()) - int((ref != 0).sum())) <= 8
+    strip = (d['mdot'].reshape(64, 64) > 10 ** 11.2)      # all helium failures of the reference lie here
+    assert not diff[~strip].any()
+
+
+def test_hydrogen_work_limit(eng):
+    """A model on which the reference's RK45 crawls (1.9e8 right-hand sides, hours in Python, before it
+    raises): the engine gives it up after max_nfev evaluations with status 5 and says so."""
+    from p_winds_b200.engine import Engine
+    from p_winds_b200 import hydrogen
+    ho = Engine.h_opts(1.39, 0.73, 1.07, 0.04634, relax_solution=True, exact_phi=True, structure_tidal=True,
+                       max_nfev=200000)
+    he_h = 0.15 / 0.85
+    o = eng.h_ion_fraction_batch(np.array([5000.0, 9000.0]), np.array([7.196857e+09, 1e10]), np.array([0.85, 0.85]),
+                                 np.full(2, (1 + 4 * he_h) / (1 + he_h)), R, ho)
+    st = o['status'].cpu().numpy()
+    assert st[0] == 5 and st[1] == 0
+    assert o['scal'][0, 5].item() >= 200000 and np.isnan(o['f_r'][0].cpu().numpy()).all()
+    with pytest.raises(RuntimeError, match='max_nfev'):
+        hydrogen.ion_fraction(R, 1.39, 5000., 0.85, 7.196857e+09, 0.73, (1 + 4 * he_h) / (1 + he_h), 1.07, 0.04634,
+                              spectrum_at_planet=_spectrum_dict(), exact_phi=True, relax_solution=True)
 
 
 def test_status_map_on_a_wide_grid_matches_oracle(eng, oracle, sed):

@@ -107,6 +107,55 @@ def test_forward_model_anchors(oracle, sed, name, idx):
         assert o['mu_bar'] == d['mu_bar'][i]
 
 
+def test_p3_anchor_fixture_and_oracle(oracle, sed):
+    """tests/golden/anchors_p3.npz (oracle/make_anchors.py: 272 triples through the unmodified reference,
+    each with K = 4 one-ulp-perturbed re-runs): shape of the fixture, and the oracle bit for bit on a
+    sample of it incl. failing models."""
+    d = golden('anchors_p3')
+    geo = golden('geometry')
+    n = len(d['T0'])
+    assert n >= 256 and (d['tidal']).sum() >= 100 and (~d['tidal']).sum() >= 100
+    assert (d['status'] == 1).sum() >= 60 and (d['status'] == 0).sum() >= 150
+    for k in ('f_r', 'f_1', 'f_3_peak', 'spectrum'):
+        runs = d['noise_%s_runs' % k]
+        assert runs.shape == (n, int(d['k_noise'])) and np.nanmax(runs) > 0
+    rng = np.random.default_rng(3)
+    ok = np.flatnonzero(d['status'] == 0)
+    idx = np.concatenate([rng.choice(ok, 5, replace=False), np.flatnonzero(d['status'] == 1)[:3]])
+    for i in idx:
+        s = oracle.Setup(sed, r=R, tidal=bool(d['tidal'][i]), i0=geo['i0'], r_map=geo['r_map'])
+        o = oracle.forward_model(s, float(d['T0'][i]), float(d['mdot'][i]), float(d['h_fraction'][i]))
+        assert o['status'] == int(d['status'][i])
+        if o['status'] == 0:
+            for key in ('f_r', 'f_1', 'f_3', 'spectrum'):
+                assert np.array_equal(o[key], d[key][i]), (i, key)
+
+
+def test_helium_failure_class_fixture_and_oracle(oracle, sed):
+    """tests/golden/he_failure_classes.npz: >= 20 models of each helium failure class from the unmodified
+    reference; class-3 results are not reproducible run to run (recorded), the class is.  The oracle
+    returns the same class."""
+    d = golden('he_failure_classes')
+    geo = golden('geometry')
+    st = d['status']
+    assert (st == 2).sum() >= 20 and (st == 3).sum() >= 20 and (st == 0).sum() >= 20
+    assert (d['f_1_run_spread'][st == 3] > 1e-3).sum() >= 10
+    assert (d['f_1_run_spread'][st != 3] == 0).all()
+    s = oracle.Setup(sed, r=R, i0=geo['i0'], r_map=geo['r_map'])
+    for c in (0, 2, 3):
+        for i in np.flatnonzero(st == c)[:4]:
+            o = oracle.forward_model(s, float(d['T0'][i]), float(d['mdot'][i]), 0.9)
+            assert o['status'] == c, (i, c, o['status'])
+            if c == 3:       # the documented convention: the last completed pass, finite and clamped
+                assert np.isfinite(o['f_1']).all() and (o['f_1'] <= 1).all() and np.isfinite(o['spectrum']).all()
+
+
+def test_bench_grid_status_fixture():
+    d = golden('bench_grid_status')
+    assert len(d['status']) == 4096 and (d['status'] == 0).sum() > 4000
+    assert (d['status'] == 2).sum() >= 5 and (d['status'] == 3).sum() >= 5
+
+
 def test_failure_map_in_fixtures():
     """The reference fails on a large part of a wide grid; the fixtures
     must contain both outcomes so that status parity is actually exercised."""
