@@ -67,6 +67,7 @@ struct pwb_ctx {
   bool sed_ready = false;
   // LSODA coefficient tables
   DevBuf lsoda_tab;
+  DevBuf exp_wide;   // 2^((i - 4096) / 256), i = 0 .. 4096 (pw_exp_neg_wide)
   // geometry / pixel table
   // One slot per transit phase (advanced_tutorial.ipynb cell 11 averages the spectrum over
   // `sample_phases`); slot 0 alone is the single-geometry case of transit.radiative_transfer_2d.
@@ -137,7 +138,7 @@ __global__ void k_parker_tidal(const double* __restrict__ r, int n, double cs, d
 // State between passes lives in global memory: HState per model + kHFieldsPerRadius*Nr doubles
 // (rn, v, rho, phi, tau, f, fprev).  The host enqueues max_n_relax + 1 rounds; a finished
 // model's CTA / thread returns at once.
-constexpr int kHFieldsPerRadius = 7;
+constexpr int kHFieldsPerRadius = 10;  // rn, v, rho, phi, tau, f, fprev, and the three np.interp slope tables
 
 __device__ __forceinline__ HParams h_params(const pwb_h_opts& o, double T, double mdot, double hfrac, double mu0) {
   HParams p;
@@ -192,6 +193,7 @@ k_h_fields(int B, int pass, const double* __restrict__ T, const double* __restri
   for (int i = threadIdx.x; i < nr; i += blockDim.x) {
     g[i] = w.rn[i]; g[nr + i] = w.v[i]; g[2 * nr + i] = w.rho[i];
     g[3 * nr + i] = w.phi[i]; g[4 * nr + i] = w.tau[i];
+    g[7 * nr + i] = w.colh[i]; g[8 * nr + i] = w.colhe[i]; g[9 * nr + i] = w.rcm[i];
   }
 }
 
@@ -238,7 +240,8 @@ k_h_solve(int B, int lanes, int pass, const double* __restrict__ T, const double
   double* g = fields + (size_t)b * kHFieldsPerRadius * nr;
   HWork w;
   w.rn = g; w.v = g + nr; w.rho = g + 2 * nr; w.phi = g + 3 * nr; w.tau = g + 4 * nr;
-  w.f = g + 5 * nr; w.fprev = g + 6 * nr; w.colh = nullptr; w.colhe = nullptr; w.rcm = nullptr; w.red = nullptr;
+  w.f = g + 5 * nr; w.fprev = g + 6 * nr; w.colh = g + 7 * nr; w.colhe = g + 8 * nr; w.rcm = g + 9 * nr;
+  w.red = nullptr;
   h_pass_solve(p, r, nr, w, pass, &s);
   state[b] = s;
 }
@@ -639,19 +642,16 @@ k_rt_formal_tau(int B, int nw, int nr, pwb_rt_opts o, const double* __restrict__
   }
 }
 
-// grid = (B, pixel splits, lambda tiles).  Thread <-> wavelength bin; every thread
-// accumulates sum_p I0_p exp(-N_p Phi_lambda) over its split of the active pixels.
-// Pixels are staged through shared memory in chunks with their interpolated column
-// density, so the inner loop is 2 LDS + 1 DMUL + exp + 1 DFMA per (pixel, lambda).
-#define PW_RT_CHUNK 256
+// Pixel sum of the 'formal' broadening: tau(b, lambda) comes from the table k_rt_formal_tau made.
+// grid = (B, pixel segments, lambda tiles), thread <-> wavelength bin; every thread accumulates
+// sum_p I0_p exp(-tau_p(lambda)) over its segment of the active pixels, k_rt_reduce adds the segments.
+// (The 'average' method, where tau = N_p Phi(lambda) separates, runs in k_rt_sum2 below.)
 __global__ void __launch_bounds__(256)
 k_rt_sum(int B, int nw, int nr, pwb_rt_opts o, const double* __restrict__ wl, const double* __restrict__ T,
          const double* __restrict__ ncol, const double* __restrict__ sums, const int* __restrict__ status,
          const int* __restrict__ px_lo, const double* __restrict__ px_whi, const double* __restrict__ px_wlo,
          const double* __restrict__ px_i0, const double* __restrict__ meta, int nsplit, double* out /*[B][nsplit][nw]*/,
          double* tau_out /*[B][nr][nw] or null*/, const double* __restrict__ tau_tab /*'formal': [B][nr][nw]*/) {
-  __shared__ double s_ncol[1024];
-  __shared__ double s_np[PW_RT_CHUNK], s_i0[PW_RT_CHUNK];
   __shared__ double s_e2[64];
   if (threadIdx.x < 64) s_e2[threadIdx.x] = kExp2Tab64Dev[threadIdx.x];
   const unsigned e2 = (unsigned)__cvta_generic_to_shared(s_e2);
@@ -684,48 +684,191 @@ k_rt_sum(int B, int nw, int nr, pwb_rt_opts o, const double* __restrict__ wl, co
     }
     return;
   }
-  for (int i = threadIdx.x; i < nr; i += blockDim.x) s_ncol[i] = ncol[(size_t)b * nr + i];
-  // Phase B: Voigt sum for this wavelength ('average' broadening, transit.py:479-513)
-  RtParams p;
-  p.n_lines = o.n_lines;
-  for (int q = 0; q < 8; ++q) { p.w0[q] = o.central_wavelength[q]; p.fosc[q] = o.oscillator_strength[q]; p.aij[q] = o.einstein_coefficient[q]; }
-  p.mass = o.particle_mass; p.v_bulk = o.bulk_los_velocity; p.rv_planet = o.planet_radial_velocity;
-  p.nz = o.z_grid_size; p.turbulence = o.turbulence_broadening; p.t_is_profile = o.temperature_is_profile;
-  const double s_n = sums[(size_t)b * 4], s_v2n = sums[(size_t)b * 4 + 1], s_tn = sums[(size_t)b * 4 + 2];
-  const double vw2 = s_v2n / s_n;
-  const double temp = o.temperature_is_profile ? s_tn / s_n : T[b];
-  double phi = 0.0;
-  if (k < nw) phi = rt_phi_average(p, wl[k], temp, vw2);
+}
+
+// ---- pixel sum, 'average' broadening -----------------------------------------------------------
+// spectrum(lambda) = mean over phases of [ sum_p I0_p exp(-N_p Phi(lambda)) + depth ]  (transit.py:220-228,
+// advanced_tutorial.ipynb cell 11).  The active pixels of a phase are cut into the same S <= 16
+// segments whatever the batch (rt_nsplit), every segment is summed sequentially and the segment sums
+// are combined in segment order: a model's spectrum is bit-identical alone or inside any grid.
+//
+// Layout: a CTA owns one (model, wavelength tile) and G <= 4 pixel groups of TPG threads; a thread owns
+// TWO wavelength bins (k, k + TPG) of the tile, so one 16-byte shared-memory read (N_p, I0_p) feeds two
+// independent exp chains and no warp idles at Nw = 200 (4 x 100 threads).
+//   ext == 1  the CTA sums all S segments of all phases: group g takes segments g, g + G, ...; after
+//             each round the G segment sums meet in shared memory and group 0 adds them in segment
+//             order; depth, phase mean and the spectrum store follow -- no partial spectra in HBM, no
+//             reduce kernel.
+//   ext == S  (few models: fewer CTAs than SMs otherwise) blockIdx.z = segment, one phase per launch;
+//             the segment sums go to `part` [B][S][nw] and k_rt_reduce adds them in the same order.
+// Pixels are staged per group in chunks with their interpolated column density N_p (interp1d weights of
+// pwb_set_geometry).  Per chunk the group checks the largest tau it can meet (largest N_p times the
+// tile's largest Phi): below kExpWideCap the terms go through pw_exp_neg_wide (10 FP64 + 2 other
+// instructions), otherwise through pw_exp_neg_sum_sh (any tau, exact zero below e^-708).
+struct RtGeoSlots {
+  int n_geo;
+  const int* lo[16];
+  const double* whi[16];
+  const double* wlo[16];
+  const double* i0[16];
+  const double* meta[16];
+  double depth[16];
+};
+
+template <int kMaxThreads>
+__global__ void __launch_bounds__(kMaxThreads, (kMaxThreads <= 256) ? 3 : (kMaxThreads <= 512 ? 2 : 1))
+k_rt_sum2(int B, int nw, int nr, const __grid_constant__ pwb_rt_opts o, const double* __restrict__ wl,
+          const double* __restrict__ T, const double* __restrict__ ncol, const double* __restrict__ sums,
+          const int* __restrict__ status, const __grid_constant__ RtGeoSlots geo, int geo0, int S, int ext, int G,
+          int TPG, int Wt, int chunk, const double* __restrict__ exp_wide, double* __restrict__ spec /*[B][nw]*/,
+          double* __restrict__ part /*[B][S][nw], ext > 1*/, double* tau_out /*[B][nr][nw] or null*/) {
+  extern __shared__ double sm2[];
+  __shared__ double s_e2[64];
+  __shared__ int s_flag[4];
+  double* s_wide = sm2;                       // [kExpWideN + 1]  2^(i/256 - 16)
+  double* s_ncol = s_wide + kExpWideN + 1;    // [nr]
+  double* s_phi = s_ncol + nr;                // [Wt]
+  double* s_x = s_phi + Wt;                   // [G][Wt] segment sums of one round
+  double* s_px = s_x + (size_t)G * Wt;        // [G][chunk] pairs (N_p, I0_p); 16-byte aligned (even offsets + 1)
+  if ((reinterpret_cast<size_t>(s_px) & 15) != 0) s_px += 1;
+  const int t = threadIdx.x, b = blockIdx.x, tile = blockIdx.y;
+  const int g = t / TPG, u = t - g * TPG;
+  const int kbase = tile * Wt;
+  const int wt = min(Wt, nw - kbase);         // bins of this tile
+  const bool bad = status && status[b] != PW_OK && status[b] != PW_WARN_HE_RELAX;
+  if (bad) {
+    if (ext == 1) {
+      for (int k = t; k < wt; k += blockDim.x) spec[(size_t)b * nw + kbase + k] = nan("");
+    } else {
+      for (int k = t; k < wt; k += blockDim.x)
+        part[((size_t)b * S + blockIdx.z) * nw + kbase + k] = (blockIdx.z == 0) ? nan("") : 0.0;
+    }
+    return;
+  }
+  for (int i = t; i < 64; i += blockDim.x) s_e2[i] = kExp2Tab64Dev[i];   // (a tile of < 128 bins has < 64 threads)
+  for (int i = t; i <= kExpWideN; i += blockDim.x) s_wide[i] = exp_wide[i];
+  for (int i = t; i < nr; i += blockDim.x) s_ncol[i] = ncol[(size_t)b * nr + i];
+  {  // Phi(lambda) of the tile, 'average' broadening (transit.py:479-513), one bin per thread
+    const double s_n = sums[(size_t)b * 4], s_v2n = sums[(size_t)b * 4 + 1], s_tn = sums[(size_t)b * 4 + 2];
+    const double vw2 = s_v2n / s_n;
+    const double temp = o.temperature_is_profile ? s_tn / s_n : T[b];
+    for (int k = t; k < wt; k += blockDim.x)
+      s_phi[k] = rt_phi_average_raw(o.central_wavelength, o.oscillator_strength, o.einstein_coefficient, o.n_lines,
+                                    o.particle_mass, o.bulk_los_velocity, o.planet_radial_velocity,
+                                    o.turbulence_broadening, wl[kbase + k], temp, vw2);
+  }
   __syncthreads();
-  if (tau_out && split == 0 && k < nw)
-    for (int i = 0; i < nr; ++i) tau_out[((size_t)b * nr + i) * nw + k] = s_ncol[i] * phi;
-  // Phase C: pixel sum
-  const int n_act = (int)meta[0];
-  const int per = (n_act + nsplit - 1) / nsplit;
-  const int p0 = split * per, p1 = min(n_act, p0 + per);
-  double acc = 0.0;
-  for (int start = p0; start < p1; start += PW_RT_CHUNK) {
-    const int q = start + threadIdx.x;
-    __syncthreads();
-    if (threadIdx.x < PW_RT_CHUNK) {
-      if (q < p1) {
-        const int lo = px_lo[q];
-        s_np[threadIdx.x] = px_whi[q] * s_ncol[lo + 1] + px_wlo[q] * s_ncol[lo];
-        s_i0[threadIdx.x] = px_i0[q];
-      } else {
-        s_np[threadIdx.x] = 0.0; s_i0[threadIdx.x] = 0.0;
+  if (tau_out && (ext == 1 || blockIdx.z == 0))
+    for (int k = t; k < wt; k += blockDim.x) {
+      const double ph = s_phi[k];
+      for (int i = 0; i < nr; ++i) tau_out[((size_t)b * nr + i) * nw + kbase + k] = s_ncol[i] * ph;
+    }
+  const bool v0 = u < wt, v1 = u + TPG < wt;
+  const double phi0 = v0 ? s_phi[u] : 0.0, phi1 = v1 ? s_phi[u + TPG] : 0.0;
+  double phi_max = 0.0;   // of the tile (every thread scans the shared copy once: Wt <= 512 reads)
+  for (int k = 0; k < wt; ++k) { const double x = fabs(s_phi[k]); phi_max = (x > phi_max || x != x) ? x : phi_max; }
+  const unsigned e2 = (unsigned)__cvta_generic_to_shared(s_e2);
+  const unsigned wide_top = (unsigned)__cvta_generic_to_shared(s_wide + kExpWideN);
+  double ec[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) ec[q] = kExpWideC[q];
+  double* my_px = s_px + (size_t)g * 2 * chunk;
+  const unsigned px_addr = (unsigned)__cvta_generic_to_shared(my_px);
+  double tot0 = 0.0, tot1 = 0.0;   // group 0: running sum over the phases
+  const int gi_end = (ext == 1) ? geo.n_geo : geo0 + 1;
+  for (int gi = geo0; gi < gi_end; ++gi) {
+    const int* __restrict__ px_lo = geo.lo[gi];
+    const double* __restrict__ px_whi = geo.whi[gi];
+    const double* __restrict__ px_wlo = geo.wlo[gi];
+    const double* __restrict__ px_i0 = geo.i0[gi];
+    const int n_act = (int)geo.meta[gi][0];
+    const int per = (n_act + S - 1) / S;
+    const int nchunk = (per + chunk - 1) / chunk;
+    double ph0 = 0.0, ph1 = 0.0;   // group 0: sum of this phase
+    const int n_round = (ext == 1) ? (S + G - 1) / G : 1;
+    for (int round = 0; round < n_round; ++round) {
+      const int seg = (ext == 1) ? round * G + g : (int)blockIdx.z;
+      const int p0 = min(n_act, seg * per), p1 = (seg < S) ? min(n_act, p0 + per) : p0;
+      double acc0 = 0.0, acc1 = 0.0;
+      for (int c = 0; c < nchunk; ++c) {
+        const int start = p0 + c * chunk;
+        const int cnt = max(0, min(chunk, p1 - start));
+        __syncthreads();
+        if (u == 0) s_flag[g] = 0;
+        __syncthreads();
+        bool big = false;
+        for (int j = u; j < cnt; j += TPG) {
+          const int q = start + j;
+          const int lo = px_lo[q];
+          const double np = px_whi[q] * s_ncol[lo + 1] + px_wlo[q] * s_ncol[lo];
+          my_px[2 * j] = np;
+          my_px[2 * j + 1] = px_i0[q];
+          big = big || !(np * phi_max < kExpWideCap);   // (NaN counts as big)
+        }
+        if (big) s_flag[g] = 1;
+        __syncthreads();
+        // two pixels x two bins per trip: four independent exp chains
+        unsigned a = px_addr;
+        const unsigned a_end = px_addr + ((unsigned)(cnt & ~1) << 4);
+        if (s_flag[g] == 0) {
+          for (; a != a_end; a += 32) {
+            double np_a, i0_a, np_b, i0_b;
+            asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(np_a), "=d"(i0_a) : "r"(a));
+            asm volatile("ld.shared.v2.f64 {%0, %1}, [%2+16];" : "=d"(np_b), "=d"(i0_b) : "r"(a));
+            const double e0a = pw_exp_neg_wide(-(np_a * phi0), wide_top, ec);
+            const double e1a = pw_exp_neg_wide(-(np_a * phi1), wide_top, ec);
+            const double e0b = pw_exp_neg_wide(-(np_b * phi0), wide_top, ec);
+            const double e1b = pw_exp_neg_wide(-(np_b * phi1), wide_top, ec);
+            acc0 = pw_fma(i0_a, e0a, acc0); acc1 = pw_fma(i0_a, e1a, acc1);
+            acc0 = pw_fma(i0_b, e0b, acc0); acc1 = pw_fma(i0_b, e1b, acc1);
+          }
+          if (cnt & 1) {
+            const double np = my_px[2 * (cnt - 1)], i0 = my_px[2 * (cnt - 1) + 1];
+            acc0 = pw_fma(i0, pw_exp_neg_wide(-(np * phi0), wide_top, ec), acc0);
+            acc1 = pw_fma(i0, pw_exp_neg_wide(-(np * phi1), wide_top, ec), acc1);
+          }
+        } else {
+#pragma unroll 2
+          for (int j = 0; j < cnt; ++j) {
+            const double np = my_px[2 * j], i0 = my_px[2 * j + 1];
+            acc0 = pw_fma(i0, pw_exp_neg_sum_sh(-(np * phi0), e2), acc0);
+            acc1 = pw_fma(i0, pw_exp_neg_sum_sh(-(np * phi1), e2), acc1);
+          }
+        }
+      }
+      if (ext > 1) {   // one segment per CTA: hand its sum to k_rt_reduce
+        if (seg == 0) { acc0 += geo.meta[gi][1]; acc1 += geo.meta[gi][1]; }   // lit pixels with tau = 0
+        if (v0) part[((size_t)b * S + seg) * nw + kbase + u] = acc0;
+        if (v1) part[((size_t)b * S + seg) * nw + kbase + u + TPG] = acc1;
+        return;
+      }
+      // the G segment sums of this round, added in segment order by group 0
+      if (g > 0 && seg < S) {
+        if (v0) s_x[(size_t)g * Wt + u] = acc0;
+        if (v1) s_x[(size_t)g * Wt + u + TPG] = acc1;
+      }
+      __syncthreads();
+      if (g == 0) {
+        if (round == 0) { acc0 += geo.meta[gi][1]; acc1 += geo.meta[gi][1]; }   // lit pixels with tau = 0
+        ph0 = (round == 0) ? acc0 : ph0 + acc0;
+        ph1 = (round == 0) ? acc1 : ph1 + acc1;
+        for (int q = 1; q < G && round * G + q < S; ++q) {
+          if (v0) ph0 += s_x[(size_t)q * Wt + u];
+          if (v1) ph1 += s_x[(size_t)q * Wt + u + TPG];
+        }
       }
     }
-    __syncthreads();
-    const int cnt = min(PW_RT_CHUNK, p1 - start);
-    if (k < nw) {  // (the warps past the last wavelength only help staging)
-#pragma unroll 4
-      for (int j = 0; j < cnt; ++j) acc = pw_fma(s_i0[j], pw_exp_neg_sum_sh(-(s_np[j] * phi), e2), acc);
+    if (g == 0) {
+      const double depth = geo.depth[gi];
+      if (depth != 0.0) { ph0 += depth; ph1 += depth; }
+      tot0 = (gi == 0) ? ph0 : tot0 + ph0;
+      tot1 = (gi == 0) ? ph1 : tot1 + ph1;
     }
   }
-  if (k < nw) {
-    if (split == 0) acc += meta[1];  // pixels with tau = 0
-    out[((size_t)b * nsplit + split) * nw + k] = acc;
+  if (g == 0) {
+    if (geo.n_geo > 1) { tot0 /= (double)geo.n_geo; tot1 /= (double)geo.n_geo; }
+    if (v0) spec[(size_t)b * nw + kbase + u] = tot0;
+    if (v1) spec[(size_t)b * nw + kbase + u + TPG] = tot1;
   }
 }
 
@@ -964,6 +1107,15 @@ int pwb_create(int device, pwb_ctx** out) {
   if (c->lsoda_tab.ensure(sizeof(LsodaTables)) != 0) { delete c; return -5; }
   k_lsoda_tables<<<1, 32>>>(c->lsoda_tab.as<LsodaTables>());
   c->launches++;
+  {  // table of pw_exp_neg_wide: correctly rounded 2^(j/256 - 16) from the host's long double exp2
+    std::vector<double> tab(kExpWideN + 1);
+    for (int i = 0; i <= kExpWideN; ++i) tab[i] = (double)exp2l((long double)(i - kExpWideN) / 256.0L);
+    if (c->exp_wide.ensure(sizeof(double) * tab.size()) != 0 ||
+        cudaMemcpy(c->exp_wide.p, tab.data(), sizeof(double) * tab.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
+      delete c;
+      return -5;
+    }
+  }
   if (cudaDeviceSynchronize() != cudaSuccess) { delete c; return -6; }
   cudaFuncSetAttribute(k_h_fields, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   cudaFuncSetAttribute(k_rt_los, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
@@ -975,7 +1127,7 @@ int pwb_create(int device, pwb_ctx** out) {
 void pwb_destroy(pwb_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
-  DevBuf* bufs[] = {&c->sed_gw, &c->sed_sh, &c->sed_she, &c->sed_scal, &c->lsoda_tab, &c->geo_r, &c->h_state, &c->h_fields, &c->he_order, &c->he_key, &c->he_work, &c->o_work, &c->rt_ncol, &c->rt_sums,
+  DevBuf* bufs[] = {&c->sed_gw, &c->sed_sh, &c->sed_she, &c->sed_scal, &c->lsoda_tab, &c->exp_wide, &c->geo_r, &c->h_state, &c->h_fields, &c->he_order, &c->he_key, &c->he_work, &c->o_work, &c->rt_ncol, &c->rt_sums,
                     &c->rt_partial, &c->rt_tau, &c->fw_f, &c->fw_scal, &c->fw_he, &c->fw_n, &c->fw_v, &c->fw_T, &c->misc};
   for (DevBuf* b : bufs) b->release();
   for (auto& G : c->geo) {
@@ -1380,6 +1532,58 @@ static int launch_rt(pwb_ctx* c, cudaStream_t s, int B, const double* d_n, const
     c->launches++;
     PWB_CUDA(c, cudaGetLastError());
     tau_tab = nullptr;
+  }
+  // 'average' broadening: k_rt_sum2 (see there).  With enough (model, tile) pairs to fill the GPU one
+  // CTA sums all pixel segments and phases and writes the spectrum; with fewer, one CTA per segment and
+  // phase + the reduce kernel.  Same segments, same order, same arithmetic: identical bits either way.
+  if (o->wind_broadening_method == 0) {
+    const int Wt = (Nw <= 512) ? Nw : 512;
+    const int tiles2 = (Nw + Wt - 1) / Wt;
+    const int TPG = (Wt + 1) / 2;
+    // (a CTA that sums all segments of a wide tile runs long: below ~16 CTAs per SM the last wave
+    // would leave SMs idle)
+    bool split = (long long)B * tiles2 < 16LL * c->sm_count && nsplit > 1;
+    if (getenv("PWB_RT_SPLIT")) split = nsplit > 1;
+    if (getenv("PWB_RT_NOSPLIT")) split = false;
+    int G = split ? 1 : std::max(1, std::min(std::min(2, nsplit), 512 / TPG));
+    int chunk = 1024;
+    if (const char* e = getenv("PWB_RT_G")) { const int v = atoi(e); if (!split && v >= 1 && v <= 4 && v * TPG <= 1024) G = std::min(v, nsplit); }
+    if (const char* e = getenv("PWB_RT_CHUNK")) { const int v = atoi(e); if (v >= 32 && v <= 4096) chunk = v; }
+    RtGeoSlots slots;
+    slots.n_geo = c->n_geo;
+    for (int g = 0; g < 16; ++g) {
+      pwb_ctx::Geo& Gg = c->geo[g < c->n_geo ? g : 0];
+      slots.lo[g] = Gg.px_lo.as<int>(); slots.whi[g] = Gg.px_whi.as<double>(); slots.wlo[g] = Gg.px_wlo.as<double>();
+      slots.i0[g] = Gg.px_i0.as<double>(); slots.meta[g] = Gg.px_meta.as<double>(); slots.depth[g] = Gg.depth;
+    }
+    const size_t smem = sizeof(double) * ((size_t)kExpWideN + 1 + Nr + Wt + (size_t)G * Wt + 2 * (size_t)G * chunk + 2);
+    if (smem > 200 * 1024) return fail(c, "pwb_rt2d_batch: radius profile too long for the pixel-sum kernel");
+    const int nt = G * TPG;
+    const int ext = split ? nsplit : 1;
+    dim3 grid2(B, tiles2, ext);
+    for (int g0 = 0; g0 < (split ? c->n_geo : 1); ++g0) {
+#define PW_RT_LAUNCH(MAXT)                                                                                         \
+      do {                                                                                                        \
+        PWB_CUDA(c, cudaFuncSetAttribute(k_rt_sum2<MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        k_rt_sum2<MAXT><<<grid2, nt, smem, s>>>(B, Nw, Nr, *o, d_wl, d_T, ncol, sums, d_status, slots, g0, nsplit,  \
+                                                ext, G, TPG, Wt, chunk, c->exp_wide.as<double>(), d_spectrum,    \
+                                                partial, g0 == 0 ? d_tau : nullptr);                              \
+      } while (0)
+      if (nt <= 256) PW_RT_LAUNCH(256);
+      else if (nt <= 512) PW_RT_LAUNCH(512);
+      else PW_RT_LAUNCH(1024);
+#undef PW_RT_LAUNCH
+      c->launches++;
+      PWB_CUDA(c, cudaGetLastError());
+      if (split) {
+        const size_t tot = (size_t)B * Nw;
+        k_rt_reduce<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(B, Nw, nsplit, partial, d_spectrum, c->geo[g0].depth,
+                                                                  g0 > 0, (g0 == c->n_geo - 1 && c->n_geo > 1) ? c->n_geo : 0);
+        c->launches++;
+        PWB_CUDA(c, cudaGetLastError());
+      }
+    }
+    return 0;
   }
   dim3 grid(B, nsplit, tiles);
   // spectrum = mean over the phases of (pixel sum + transit depth of the phase), summed in

@@ -110,18 +110,36 @@ struct HRhs {
   const double *rn, *phi, *v, *rho, *tau;
   int n, exact, hint;
   double k2, phi0;
+  // np.interp slopes (fp[j+1] - fp[j]) / (xp[j+1] - xp[j]) of phi (exact) or tau, of v and of rho,
+  // formed once per pass by h_pass_fields exactly as numpy forms them at every call: three of the
+  // five divisions of a right-hand side gone, bit-identical.  Null: evaluate np_interp_at literally.
+  const double *sp = nullptr, *sv = nullptr, *srho = nullptr;
   // hydrogen.py:431-448
   PW_HD void operator()(double x, const double* y, double* dydx) {
     const int j = bracket(rn, n, x, hint);
     hint = j;
-    double pp;
-    if (exact) pp = np_interp_at(rn, phi, n, x, j);
-    else pp = exp(-np_interp_at(rn, tau, n, x, j)) * phi0;
-    const double v_ = np_interp_at(rn, v, n, x, j);
-    const double rho_ = np_interp_at(rn, rho, n, x, j);
+    double pi_, v_, rho_;   // interpolated phi (or tau), v, rho
+    const double* pa = exact ? phi : tau;
+    bool done = false;
+    if (sp && j >= 0 && j < n - 1) {
+      const double x0 = rn[j];
+      if (x0 != x) {
+        const double d = x - x0;
+        pi_ = sp[j] * d + pa[j];
+        v_ = sv[j] * d + v[j];
+        rho_ = srho[j] * d + rho[j];
+        done = (pi_ == pi_) && (v_ == v_) && (rho_ == rho_);  // a NaN takes numpy's fall-back path below
+      }
+    }
+    if (!done) {
+      pi_ = np_interp_at(rn, pa, n, x, j);
+      v_ = np_interp_at(rn, v, n, x, j);
+      rho_ = np_interp_at(rn, rho, n, x, j);
+    }
+    const double pp = exact ? pi_ : exp(-pi_) * phi0;
     const double f = y[0];
-    const double term1 = (1. - f) / v_ * pp;
-    const double term2 = k2 * rho_ * (f * f) / v_;
+    const double term1 = PW_DIV(1. - f, v_) * pp;
+    const double term2 = PW_DIV(k2 * rho_ * (f * f), v_);
     dydx[0] = term1 - term2;
   }
 };
@@ -209,6 +227,22 @@ PW_HD void h_pass_fields(const HParams& p, const SedTables& sed, const double* _
     }
   }
   PW_SYNC();
+  // np.interp slopes for the right-hand side of this pass (HRhs), in the scratch the column
+  // densities no longer need: colh <- phi or tau, colhe <- v, rcm <- rho
+  {
+    const double* pa = p.exact_phi ? w.phi : w.tau;
+    for (int i = PW_TID; i < nr; i += PW_NT) {
+      double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+      if (i < nr - 1) {
+        const double dx = w.rn[i + 1] - w.rn[i];
+        s0 = (pa[i + 1] - pa[i]) / dx;
+        s1 = (w.v[i + 1] - w.v[i]) / dx;
+        s2 = (w.rho[i + 1] - w.rho[i]) / dx;
+      }
+      w.colh[i] = s0; w.colhe[i] = s1; w.rcm[i] = s2;
+    }
+  }
+  PW_SYNC();
 }
 
 // One thread.  solve_ivp(_fun, (r[0], r[-1]), [initial_f_ion], t_eval=r) (:451, :504) on the
@@ -221,6 +255,7 @@ PW_HD void h_pass_solve(const HParams& p, const double* __restrict__ r, int nr, 
   const double he_h = (1 - p.h_fraction) / p.h_fraction;
   for (int i = 0; i < nr; ++i) w.fprev[i] = w.f[i];
   HRhs rhs{w.rn, w.phi, w.v, w.rho, w.tau, nr, p.exact_phi, 0, q.k2, p.phi_abs / q.phi_unit};
+  rhs.sp = w.colh; rhs.sv = w.colhe; rhs.srho = w.rcm;   // slopes left by h_pass_fields (may be null)
   Rk45Stats st{0, 0, 0};
   const double y0 = p.initial_f_ion;
   const int got = rk45_solve<1>(rhs, w.rn, nr, &y0, p.ivp, w.f, &st);

@@ -247,20 +247,29 @@ PW_HD void rt_los_average(const double* __restrict__ r, const double* __restrict
 
 // Phase B: Phi(lambda) = sum_k sigma_k * voigt(dnu_k + shift_k, alpha_k, gamma_k)
 // for one wavelength (transit.py:436-453, :479-513, :523-534), 'average' method.
-PW_HD double rt_phi_average(const RtParams& p, double wl, double temp, double vw2) {
+// The line list comes in through pointers so that a kernel can hand over the arrays of its
+// (constant-bank) parameter block as they are: copying them into a local struct and indexing that
+// with the line number puts the copy in local memory.
+PW_HD double rt_phi_average_raw(const double* __restrict__ w0, const double* __restrict__ fosc,
+                                const double* __restrict__ aij, int n_lines, double mass, double v_bulk,
+                                double rv_planet, int turbulence, double wl, double temp, double vw2) {
   const double c_speed = 2.99792458e+08, k_b = 1.380649e-23;
   double phi = 0.0;
   const double nu_rest = c_speed / wl;
-  const double vt2 = p.turbulence ? (5.0 / 6 * k_b * temp / p.mass) : 0.0;  // sqrt(.)**2, :495
-  for (int k = 0; k < p.n_lines; ++k) {
-    const double nu0 = c_speed / p.w0[k];
-    const double gamma = p.aij[k] / 4 / kPi;
-    const double alpha = nu0 / c_speed * sqrt(k_b * temp / p.mass + vw2 + vt2);
-    const double shift = (p.v_bulk + p.rv_planet) / c_speed * nu0;
+  const double vt2 = turbulence ? (5.0 / 6 * k_b * temp / mass) : 0.0;  // sqrt(.)**2, :495
+  for (int k = 0; k < n_lines; ++k) {
+    const double nu0 = c_speed / w0[k];
+    const double gamma = aij[k] / 4 / kPi;
+    const double alpha = nu0 / c_speed * sqrt(k_b * temp / mass + vw2 + vt2);
+    const double shift = (v_bulk + rv_planet) / c_speed * nu0;
     const double prof = voigt_profile((nu_rest - nu0) + shift, alpha, gamma);
-    phi += prof * (2.654008854574474e-06 * p.fosc[k]);
+    phi += prof * (2.654008854574474e-06 * fosc[k]);
   }
   return phi;
+}
+PW_HD double rt_phi_average(const RtParams& p, double wl, double temp, double vw2) {
+  return rt_phi_average_raw(p.w0, p.fosc, p.aij, p.n_lines, p.mass, p.v_bulk, p.rv_planet, p.turbulence, wl, temp,
+                            vw2);
 }
 
 }  // namespace pw

@@ -390,6 +390,8 @@ class Engine:
         spectrum = self.dev(spectrum)
         B, nw = spectrum.shape
         data, sigma = self.dev(data).reshape(-1), self.dev(sigma).reshape(-1)
+        if status is not None:
+            status = self.dev(status, torch.int32).reshape(-1)
         chi2 = torch.empty(B, dtype=torch.float64, device=self.device)
         self._check(self.lib.pwb_chi2_batch(self.ctx, B, _ptr(spectrum), nw, _ptr(data), _ptr(sigma),
                                             float(norm), _ptr(status), _ptr(chi2), self._stream()))

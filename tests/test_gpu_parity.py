@@ -670,8 +670,62 @@ def test_retrieval_loop_phase_mean_convolution_likelihood(built, oracle):
     ll = eng.loglike_batch(conv, y, yerr, status).cpu().numpy()
     assert abs(ll[0] / oracle.log_likelihood(conv[0], y, yerr) - 1) < 1e-12
     assert ll[1] == -np.inf
+    assert ll[2] == -np.inf          # status 3: the reference's result is undefined -> failed by default
+    eng.set_relax_warning_policy(True)
+    ll = eng.loglike_batch(conv, y, yerr, status).cpu().numpy()
+    eng.set_relax_warning_policy(False)
+    assert ll[1] == -np.inf
     assert abs(ll[2] / oracle.log_likelihood(conv[2], y, yerr) - 1) < 1e-12
     assert ll[0] > ll[2]                                            # the true model wins
+
+
+def test_pixel_sum_kernels_agree_bit_for_bit(built, oracle):
+    """The two launch shapes of the pixel sum (k_rt_sum2): one CTA per model and wavelength tile summing
+    all pixel segments and phases with the segment sums combined in shared memory (large batches), and
+    one CTA per pixel segment and phase + k_rt_reduce (few models) -- same segments, same order ->
+    np.array_equal, for the quickstart sizes, a ragged tile (Nw = 150), five phases with their depths,
+    Nw = 4096, and an optically thick case that takes the general exp path (tau >> 11)."""
+    import os
+    from p_winds_b200.engine import Engine
+    from p_winds_b200 import lines
+    prof = golden('he_3_profile')
+    geo = golden('geometry')
+    w = lines.he_3_properties()
+    rto = Engine.rt_opts(w[:3], w[3:6], [w[6]] * 3, M_HE, bulk_los_velocity=-2E3)
+    r_si, n_si, v_si = prof['r'][::5].copy(), prof['n'][::5].copy(), prof['v'][::5].copy()
+    rng = np.random.default_rng(11)
+    B = 160
+    scale = 10 ** rng.uniform(-1, 1, B)
+    n = n_si[None, :] * scale[:, None]
+    v = np.tile(v_si, (B, 1))
+    T = rng.uniform(7000, 12000, B)
+    phases = np.linspace(-0.4, 0.4, 5)
+    maps = [oracle.draw_transit(0.12086, float(r_si[0]), 0.499, ph, 60, 3) for ph in phases]
+    maps = [(m[0], m[2], m[1]) for m in maps]
+    cases = [('quickstart', lambda e: e.set_geometry(geo['i0'], geo['r_map'], r_si), np.linspace(1.0827, 1.0832, 200) * 1e-6),
+             ('ragged', lambda e: e.set_geometry(geo['test_i0'], geo['test_r_map'], r_si), np.linspace(1.0827, 1.0832, 150) * 1e-6),
+             ('phases', lambda e: e.set_geometry_phases(maps, r_si), np.linspace(1.0826, 1.0834, 169) * 1e-6),
+             ('wide', lambda e: e.set_geometry(geo['i0'], geo['r_map'], r_si), np.linspace(1.0827, 1.0832, 4096) * 1e-6),
+             ('thick', lambda e: e.set_geometry(geo['i0'], geo['r_map'], r_si), np.linspace(1.0827, 1.0832, 200) * 1e-6)]
+    for name, setup, wl in cases:
+        if name == 'thick':
+            n = n * 300.0
+        eng = Engine(0)
+        setup(eng)
+        out = {}
+        for key in ('PWB_RT_SPLIT', 'PWB_RT_NOSPLIT'):
+            os.environ[key] = '1'
+            try:
+                out[key] = eng.rt2d_batch(n, v, T, wl, rto, return_tau=(name == 'ragged'))
+            finally:
+                del os.environ[key]
+        a, b2 = out['PWB_RT_SPLIT'], out['PWB_RT_NOSPLIT']
+        if name == 'ragged':
+            assert np.array_equal(a[1].cpu().numpy(), b2[1].cpu().numpy()), name
+            a, b2 = a[0], b2[0]
+        a, b2 = a.cpu().numpy(), b2.cpu().numpy()
+        assert np.isfinite(a).all() and (a.min() < 0.999 * a.max())
+        assert np.array_equal(a, b2), (name, np.max(np.abs(a - b2)))
 
 
 def test_config3_share_tidal_grid_properties(eng):
