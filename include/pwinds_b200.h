@@ -305,6 +305,9 @@ int pwb_fp64_peak(pwb_ctx* ctx, double* tflops, void* stream);
  *      pw_root), so that the GPU tests can compare them with numpy. */
 int pwb_selftest_arith(pwb_ctx* ctx, int n, const double* d_a, const double* d_b, const int* d_k,
                        double* d_quot, double* d_root, void* stream);
+/* ---- Self-test of the two e^x routines of the pixel sum (test hook): wide[i] = pw_exp_neg_wide(x[i])
+ *      (NaN outside its range -11 < x <= 0), general[i] = pw_exp_neg_sum_sh(x[i]) (any x <= 0). */
+int pwb_selftest_exp(pwb_ctx* ctx, int n, const double* d_x, double* d_wide, double* d_general, void* stream);
 
 #ifdef __cplusplus
 }

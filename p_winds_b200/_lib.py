@@ -90,6 +90,7 @@ SYMBOLS = {
     'pwb_chi2_batch': (_I, [_VP, _I, _VP, _I, _VP, _VP, _D, _VP, _VP, _VP]),
     'pwb_draw_transit': (_I, [_VP, _D, _D, _D, _D, _I, _I, _I, c_double_p, _VP, _VP, c_double_p, _VP]),
     'pwb_fp64_peak': (_I, [_VP, c_double_p, _VP]),
+    'pwb_selftest_exp': (_I, [_VP, _I, _VP, _VP, _VP, _VP]),
     'pwb_selftest_arith': (_I, [_VP, _I, _VP, _VP, _VP, _VP, _VP, _VP]),
 }
 

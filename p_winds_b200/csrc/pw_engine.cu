@@ -1737,6 +1737,37 @@ int pwb_selftest_arith(pwb_ctx* c, int n, const double* d_a, const double* d_b, 
   return 0;
 }
 
+// the two e^x of the pixel sum on arbitrary arguments (test hook)
+__global__ void k_selftest_exp(int n, const double* __restrict__ x, const double* __restrict__ exp_wide,
+                               double* __restrict__ wide, double* __restrict__ gen) {
+  extern __shared__ double sm_e[];
+  __shared__ double s_e2[64];
+  double* s_wide = sm_e;
+  for (int i = threadIdx.x; i < 64; i += blockDim.x) s_e2[i] = kExp2Tab64Dev[i];
+  for (int i = threadIdx.x; i <= kExpWideN; i += blockDim.x) s_wide[i] = exp_wide[i];
+  __syncthreads();
+  double ec[8];
+  for (int q = 0; q < 8; ++q) ec[q] = kExpWideC[q];
+  const unsigned top = (unsigned)__cvta_generic_to_shared(s_wide + kExpWideN);
+  const unsigned e2 = (unsigned)__cvta_generic_to_shared(s_e2);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const double v = x[i];
+    wide[i] = (v <= 0.0 && v > -kExpWideCap) ? pw_exp_neg_wide(v, top, ec) : nan("");
+    gen[i] = pw_exp_neg_sum_sh(v, e2);
+  }
+}
+
+int pwb_selftest_exp(pwb_ctx* c, int n, const double* d_x, double* d_wide, double* d_general, void* stream) {
+  if (!c) return -1;
+  if (n <= 0) return 0;
+  const size_t smem = sizeof(double) * (kExpWideN + 1);
+  PWB_CUDA(c, cudaFuncSetAttribute(k_selftest_exp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_selftest_exp<<<c->sm_count, 256, smem, (cudaStream_t)stream>>>(n, d_x, c->exp_wide.as<double>(), d_wide, d_general);
+  c->launches++;
+  PWB_CUDA(c, cudaGetLastError());
+  return 0;
+}
+
 int pwb_fp64_peak(pwb_ctx* c, double* tflops, void* stream) {
   if (!c) return -1;
   cudaStream_t s = (cudaStream_t)stream;

@@ -419,6 +419,13 @@ class Engine:
             self._stream()))
         return i0, depth.value, rm
 
+    def selftest_exp(self, x):
+        """(pw_exp_neg_wide(x), pw_exp_neg_sum_sh(x)) of the pixel-sum kernel (test hook)."""
+        x = self.dev(x).reshape(-1)
+        w, g = torch.empty_like(x), torch.empty_like(x)
+        self._check(self.lib.pwb_selftest_exp(self.ctx, x.numel(), _ptr(x), _ptr(w), _ptr(g), self._stream()))
+        return w, g
+
     def selftest_arith(self, a, b, k):
         """(a / b, a ** (1 / k)) through the device routines of the LSODA step (test hook)."""
         a = self.dev(a); b = self.dev(b)

@@ -951,6 +951,26 @@ def test_metals_chain_config5_lines_on_gpu(eng, oracle, sed):
         assert ref_c.min() < 0.999 * ref_c.max()      # the C II lines are actually there
 
 
+def test_pixel_sum_exponentials_on_gpu(eng):
+    """The two e^x of k_rt_sum2 against numpy: pw_exp_neg_wide (table of 4097 powers of two, series to
+    r^4; tau < 11) and pw_exp_neg_sum_sh (64-entry table, exponent arithmetic, exact zero below e^-708).
+    Relative error <= 3e-16 scaled by max(1, |x|) (the one-constant argument reduction), i.e. an absolute
+    error below one ulp of an O(1) sum."""
+    rng = np.random.default_rng(8)
+    x = -np.concatenate([10 ** rng.uniform(-14, np.log10(10.99), 300000), rng.uniform(0, 10.99, 300000),
+                         [0.0, 1e-300, 10.99, np.log(2) / 256, np.log(2) / 512, 5.5]])
+    w, g = (t.cpu().numpy() for t in eng.selftest_exp(x))
+    ref = np.exp(x)
+    assert np.max(np.abs(w / ref - 1) / np.maximum(1.0, -x)) < 3e-16
+    assert np.max(np.abs(w - ref)) < 1.2e-16
+    assert np.max(np.abs(g / ref - 1) / np.maximum(1.0, -x)) < 3e-16
+    assert w[600000] == 1.0 and g[600000] == 1.0
+    far = -np.array([11.5, 50.0, 700.0, 707.9, 708.5, 1e4, 1e7, 1e12])
+    w2, g2 = (t.cpu().numpy() for t in eng.selftest_exp(far))
+    assert np.isnan(w2).all()
+    assert np.max(np.abs(g2[:4] / np.exp(far[:4]) - 1) / 708) < 3e-16 and (g2[4:] == 0).all()
+
+
 def test_step_arithmetic_on_gpu(eng):
     """The device build of the LSODA step replaces `a / b` by the fast path of the IEEE division
     algorithm (csrc/pw_common.cuh PW_DIV) and pow(a, 1/k) by a Newton root (pw_root).  Over the
