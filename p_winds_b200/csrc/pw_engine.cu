@@ -307,9 +307,12 @@ k_he_order(int B, const double* __restrict__ key, const int* __restrict__ status
   if (t == 0) { s_lo = ~0ull; s_hi = 0ull; }
   for (int i = t; i < kHeBuckets; i += blockDim.x) hist[i] = 0;
   __syncthreads();
+  // bucket range over the models that will be integrated: a failed one (key 0) would stretch the range
+  // to zero and squeeze every valid key into the top percent of the buckets
   unsigned long long lo = ~0ull, hi = 0ull;
   for (int b = t; b < B; b += blockDim.x) {
     const unsigned long long k = key_bits(b);
+    if (k == 0ull) continue;
     lo = k < lo ? k : lo;
     hi = k > hi ? k : hi;
   }
@@ -318,7 +321,10 @@ k_he_order(int B, const double* __restrict__ key, const int* __restrict__ status
   __syncthreads();
   lo = s_lo; hi = s_hi;
   const double scale = (hi > lo) ? (double)(kHeBuckets - 1) / (double)(hi - lo) : 0.0;
-  auto bucket = [&](int b) { return (kHeBuckets - 1) - (int)((double)(key_bits(b) - lo) * scale); };  // 0 = costliest
+  auto bucket = [&](int b) {   // 0 = costliest; failed models last
+    const unsigned long long k = key_bits(b);
+    return (k == 0ull || k < lo) ? kHeBuckets - 1 : (kHeBuckets - 1) - (int)((double)(k - lo) * scale);
+  };
   for (int b = t; b < B; b += blockDim.x) atomicAdd(&hist[bucket(b)], 1);
   __syncthreads();
   // exclusive scan of the histogram (4 buckets per thread + block scan through shared memory)

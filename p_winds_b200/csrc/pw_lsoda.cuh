@@ -9,7 +9,7 @@
 // restatement of the published algorithm: Nordsieck history array, variable-order
 // Adams (1..12) / BDF (1..5) with automatic stiffness switching, chord iteration
 // with a finite-difference Jacobian, step/order selection from the three error
-// estimates, output by interpolation (intdy).  tests/test_hostsim_lsoda.py holds
+// estimates, output by interpolation (intdy).  tests/test_hostsim_solvers.py holds
 // the host build to scipy's own `odeint(full_output=True)` step/feval/jacobian
 // counters and to its solution on the anchor models.
 #pragma once

@@ -10,7 +10,7 @@
 //   _ivp/ivp.py             t_eval bookkeeping (points <= t of each accepted step,
 //                           side='right'; a failed solve returns fewer points)
 // Trace parity (identical nfev / accepted steps on the host build) is checked in
-// tests/test_hostsim_rk45.py against scipy itself.
+// tests/test_hostsim_solvers.py against scipy itself.
 #pragma once
 #include "pw_common.cuh"
 

@@ -22,7 +22,7 @@ inline double erfcx_pos(double y) {  // host build (tests only): glibc has no er
 #endif
 
 // Re w(x + i y), y >= 0, w(z) = exp(-z^2) erfc(-i z).  Relative accuracy ~1e-15
-// (checked against scipy.special.wofz in tests/test_hostsim_voigt.py and on the GPU).
+// (checked against scipy.special.wofz in tests/test_hostsim_stages.py::test_wofz_against_scipy and on the GPU).
 PW_HD double wofz_re(double xin, double y) {
   const double x = fabs(xin);
   const double a = 0.518321480430085929872;   // pi / sqrt(-log(eps*0.5))

@@ -131,3 +131,26 @@ def test_host_helpers_match_reference_formulas(oracle):
     w0, f, a = oracle.he3_lines()
     l = lines.he_3_properties()
     assert list(l[:3]) == list(w0) and list(l[3:6]) == list(f) and l[6] == a[0]
+
+
+def test_spectrum_dict_with_unit_objects():
+    """tools.spectrum_to_cgs: the spectrum dict of tools.make_spectrum_from_file carries unit *objects*
+    (tools.py:405-408).  astropy is absent here, so the stand-in's objects (scale + dims) exercise that
+    branch; strings and objects must agree, and a non-cgs unit must be converted."""
+    import sys
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, 'oracle', 'standins'))
+    import astropy.units as u     # the stand-in
+    from p_winds_b200 import tools
+    wl = np.array([100.0, 500.0, 911.0])
+    fl = np.array([1.0, 2.0, 3.0])
+    a = tools.spectrum_to_cgs({'wavelength': wl, 'flux_lambda': fl, 'wavelength_unit': 'angstrom',
+                               'flux_unit': 'erg / (s cm2 angstrom)'})
+    b = tools.spectrum_to_cgs({'wavelength': wl, 'flux_lambda': fl, 'wavelength_unit': u.angstrom,
+                               'flux_unit': u.erg / u.s / u.cm ** 2 / u.angstrom})
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[0], wl)
+    c = tools.spectrum_to_cgs({'wavelength': wl / 10, 'flux_lambda': fl * 1e-2, 'wavelength_unit': u.nm,
+                               'flux_unit': u.W / u.m ** 2 / u.nm})
+    assert np.allclose(c[0], wl, rtol=1e-14) and np.allclose(c[1], fl * 1e-2 * 1e3 / 10, rtol=1e-14)
+    with pytest.raises(ValueError):
+        tools.spectrum_to_cgs({'wavelength': wl, 'flux_lambda': fl, 'wavelength_unit': 'parsec-ish'})

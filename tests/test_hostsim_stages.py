@@ -1,6 +1,7 @@
 """Parity tier P1 for the physics stages: the host build of the device code against
 the oracle (== the reference, see test_oracle_vs_golden.py)."""
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
@@ -172,6 +173,38 @@ def test_helium_stage_default_tolerance_envelope(hostsim, oracle, sed, T0, md):
     assert abs(f3[ipk] / oh['f_3'][ipk] - 1) < 1e-3
     for k, key in ((1, 'nfe'), (2, 'nst'), (3, 'nje')):
         assert abs(scal[k] / sum(oh[key]) - 1) < 0.10, key
+
+
+def test_helium_rhs_literal_logexp_build(built, hostsim, oracle, sed):
+    """-DPW_HE_LOGEXP: the right-hand side with the reference's literal exp(log k1 + log rho + log coef)
+    (helium.py:637-652) instead of the product k1 * rho * coef the engine uses.  Both
+    host builds on the same model: same status and relax count, populations equal far inside odeint's
+    own noise -- the detour through logarithms only adds ~1e-14 of rounding."""
+    import subprocess
+    lib = os.path.join(os.path.dirname(built.HOSTSIM), 'libhostsim_logexp.so')
+    src = os.path.join(os.path.dirname(built.HOSTSIM), '..', 'hostsim', 'hostsim.cu')
+    want = built.source_hash([src])
+    if built._lib_hash(lib, b'hostsim src:') != want:
+        subprocess.check_call([built.NVCC, '-Wno-deprecated-gpu-targets', '-O2', '-std=c++17', '--expt-relaxed-constexpr',
+                               '--expt-extended-lambda', '-Xcompiler', '-fPIC,-ffp-contract=off', '-shared',
+                               '-DPW_HE_LOGEXP', '-DPW_SRC_HASH="%s"' % want, '-o', lib, src])
+    alt = C.CDLL(lib)
+    rates = np.array(oracle.he_radiative_processes(sed))
+    T0, md = 9100., 10 ** 10.27
+    f_r, vs, rs, rhos, v, rho = _he_inputs(oracle, sed, T0, md, False)
+    st0, a1, a3, sc0 = _he_host(hostsim, rates, T0, 0.9, vs, rs, rhos, R, v, rho, f_r)
+    st1, b1, b3, sc1 = _he_host(alt, rates, T0, 0.9, vs, rs, rhos, R, v, rho, f_r)
+    assert st0 == st1 == 0 and sc0[0] == sc1[0]
+    assert not np.array_equal(a1, b1)                       # it is a different build
+    # default tolerance: ~1e-14 of input noise is amplified to odeint's own noise floor (f_1 ~5e-6 median,
+    # 5e-5 at the 90th percentile over tests/golden/anchors_p3.npz) -- the envelope of the P3 host test
+    assert np.max(np.abs(a1 / b1 - 1)) < 1e-4
+    ipk = np.argmax(a3)
+    assert abs(a3[ipk] / b3[ipk] - 1) < 1e-3
+    # tight tolerances: the two forms agree to rounding
+    st0, a1, a3, _ = _he_host(hostsim, rates, T0, 0.9, vs, rs, rhos, R, v, rho, f_r, method=1, rtol=1e-10, atol=1e-16)
+    st1, b1, b3, _ = _he_host(alt, rates, T0, 0.9, vs, rs, rhos, R, v, rho, f_r, method=1, rtol=1e-10, atol=1e-16)
+    assert st0 == st1 == 0 and np.max(np.abs(a1 / b1 - 1)) < 1e-9
 
 
 def test_wofz_against_scipy(hostsim):
