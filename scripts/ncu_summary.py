@@ -6,6 +6,9 @@
         the source lines of one kernel with the most executed thread instructions, their share of the
         stall samples, and the size of the hot loop (SASS instructions executed at least once per
         ten model-steps)
+    python scripts/ncu_summary.py sass out.txt a.ncu-rep k_helium n_model_steps
+        the hot loop of one kernel as SASS, in address order: every instruction executed at least once
+        per ten model-steps with its warp-level and thread-level execution counts (lanes per issue)
 Needs `ncu` on PATH (reads reports; no GPU)."""
 import collections
 import csv
@@ -97,8 +100,45 @@ def lines(out, rep, kernel, model_steps, top=40):
             w.writerow([k[0], k[1], '%.2f' % (100 * v / tt), '%.2f' % (100 * smp[k] / ts), src[k][:100]])
 
 
+def sass(out, rep, kernel, model_steps):
+    rows = list(csv.reader(io.StringIO(ncu(['-i', rep, '--page', 'source', '--csv', '--print-source', 'sass',
+                                            '-k', 'regex:' + kernel]))))
+    hdr, body = None, []
+    for r in rows:
+        if r and r[0] == 'Address':
+            hdr = r
+            continue
+        if hdr is not None and len(r) >= 8 and r[0].startswith('0x'):
+            body.append(r)
+    i_a = hdr.index('Address') if 'Address' in hdr else 0
+    i_src = hdr.index('Source')
+    i_i, i_t, i_s = (hdr.index(k) for k in ('Instructions Executed', 'Thread Instructions Executed', '# Samples'))
+    seen, keep, tot_t, tot_i = set(), [], 0, 0
+    for r in body:
+        if r[i_a] in seen:
+            continue
+        seen.add(r[i_a])
+        try:
+            n_i, n_t, n_s = int(r[i_i]), int(r[i_t]), int(r[i_s])
+        except ValueError:
+            continue
+        tot_t += n_t
+        tot_i += n_i
+        if n_t >= model_steps / 10:
+            keep.append((r[i_a], n_i, n_t, n_s, r[i_src]))
+    with open(out, 'w') as fh:
+        fh.write('# %s: %d SASS instructions, %d in the hot loop (executed at least once per ten model-steps, '
+                 '%.1f KB); %.0f thread instructions and %.0f warp instructions per model-step\n'
+                 % (kernel, len(seen), len(keep), len(keep) * 16 / 1024, tot_t / model_steps, tot_i / model_steps))
+        fh.write('# address  warp_instructions  thread_instructions  lanes_per_issue  stall_samples  sass\n')
+        for a, n_i, n_t, n_s, src in keep:
+            fh.write('%s %11d %12d %5.2f %6d  %s\n' % (a, n_i, n_t, n_t / max(n_i, 1), n_s, src))
+
+
 if __name__ == '__main__':
     if sys.argv[1] == 'summary':
         summary(sys.argv[2], sys.argv[3:])
+    elif sys.argv[1] == 'sass':
+        sass(sys.argv[2], sys.argv[3], sys.argv[4], float(sys.argv[5]))
     else:
         lines(sys.argv[2], sys.argv[3], sys.argv[4], float(sys.argv[5]) if len(sys.argv) > 5 else 0)
