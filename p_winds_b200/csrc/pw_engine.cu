@@ -402,6 +402,53 @@ k_helium(int B, HeSched sched, const int* __restrict__ order, const double* __re
 #endif
 }
 
+#if defined(PW_HE_PS_KERNEL)
+// Experiment (developer build): the same stage with the lanes of a warp aligned block by block
+// (he_population_ps): every lane of the warp stays in the kernel until the warp's last model is done,
+// because the warp votes on the block to run next.
+__global__ void __launch_bounds__(32, PW_HE_MINBLOCKS)
+k_helium_ps(int B, HeSched sched, const int* __restrict__ order, const double* __restrict__ T,
+            const double* __restrict__ hfrac, const double* __restrict__ vs, const double* __restrict__ rs,
+            const double* __restrict__ rhos, int sstride, const double* __restrict__ r, int nr,
+            const double* __restrict__ v, const double* __restrict__ rho, const double* __restrict__ f_h, pwb_he_opts o,
+            const LsodaTables* __restrict__ tab, double* work, size_t wstride, double* f1, double* f3, double* scal,
+            double* rates, int* status) {
+  __shared__ double s_e2[32];
+  s_e2[threadIdx.x] = kExp2TabDev[threadIdx.x];
+  __syncwarp();
+  const int lane = threadIdx.x, warp = blockIdx.x;
+  int seg = 0;
+#pragma unroll
+  for (int q = 1; q < 4; ++q)
+    if (q < sched.nseg && warp >= sched.warp0[q]) seg = q;
+  const int slot = sched.slot0[seg] + (warp - sched.warp0[seg]) * sched.lanes[seg] + lane;
+  bool has = lane < sched.lanes[seg] && slot < sched.slot0[seg + 1];
+  int b = 0;
+  if (has) {
+    b = order ? order[slot] : slot;
+    if (status[b] != PW_OK) {  // upstream failure: propagate NaNs
+      const double nan_ = nan("");
+      for (int i = 0; i < nr; ++i) { f1[(size_t)b * nr + i] = nan_; f3[(size_t)b * nr + i] = nan_; }
+      for (int k = 0; k < 4; ++k) scal[(size_t)b * 4 + k] = 0.0;
+      has = false;
+    }
+  }
+  HeParams p;
+  p.e2tab = (unsigned)__cvta_generic_to_shared(s_e2);
+  p.T = T[b]; p.h_fraction = hfrac[b];
+  p.vs = vs[(size_t)b * sstride]; p.rs = rs[(size_t)b * sstride]; p.rhos = rhos[(size_t)b * sstride];
+  p.r_pl = o.planet_radius; p.y0[0] = o.initial_state[0]; p.y0[1] = o.initial_state[1];
+  p.relax = o.relax_solution; p.max_n_relax = o.max_n_relax; p.convergence = o.convergence;
+  for (int k = 0; k < 6; ++k) p.rates[k] = o.rates[k];
+  p.method = o.method; p.rtol = o.rtol; p.atol = o.atol; p.first_step = o.first_step; p.max_step = o.max_step;
+  double* wb = work + (size_t)b * wstride;
+  HeWork w{wb, wb + nr, wb + 2 * nr, wb + 3 * nr, wb + 4 * nr, wb + 5 * nr, wb + 10 * nr};
+  HeOut out{f1 + (size_t)b * nr, f3 + (size_t)b * nr, scal + (size_t)b * 4,
+            rates ? rates + (size_t)b * 11 * nr : nullptr, status + b};
+  he_population_ps(p, *tab, r, v + (size_t)b * nr, rho + (size_t)b * nr, f_h + (size_t)b * nr, nr, w, out, has);
+}
+#endif
+
 // oxygen.ion_fraction: one thread per model (Radau / LSODA / RK45 replica), `lanes` models per warp
 __global__ void __launch_bounds__(32)
 k_oxygen(int B, int lanes, const double* __restrict__ T, const double* __restrict__ hfrac,
@@ -1325,6 +1372,16 @@ static int launch_helium(pwb_ctx* c, cudaStream_t s, int B, const double* d_T, c
   const int* ord = sorted ? order : nullptr;
   const int blocks = sched.warp0[sched.nseg];
   const size_t ws = (size_t)kHeWorkPerRadius * Nr;
+#if defined(PW_HE_PS_KERNEL)
+  if (o->method != PW_HE_RK45 && getenv("PWB_HE_PS")) {
+    k_helium_ps<<<blocks, 32, 0, s>>>(B, sched, ord, d_T, d_hfrac, d_vs, d_rs, d_rhos, sstride, d_r, Nr, d_v, d_rho,
+                                      d_f_h, *o, c->lsoda_tab.as<LsodaTables>(), work, ws, d_f1, d_f3, d_scal,
+                                      d_rates, d_status);
+    c->launches++;
+    PWB_CUDA(c, cudaGetLastError());
+    return 0;
+  }
+#endif
   if (o->method == PW_HE_RK45)
     k_helium<true><<<blocks, 32, 0, s>>>(B, sched, ord, d_T, d_hfrac, d_vs, d_rs, d_rhos, sstride, d_r, Nr, d_v, d_rho,
                                          d_f_h, *o, c->lsoda_tab.as<LsodaTables>(), work, ws, d_f1, d_f3, d_scal,

@@ -406,4 +406,215 @@ PW_HD void he_population_model(const HeParams& p, const LsodaTables& tab, const 
   *out.status = status;
 }
 
+
+#if defined(__CUDACC__) && defined(PW_HE_PS_KERNEL)
+// ---------------------------------------------------------------------------------------------
+// EXPERIMENT (developer build -DPW_HE_PS_KERNEL, scripts/he_ps.py; not in the shipped library).
+// The same model, scheduled by the warp (device only; method 'odeint' / 'LSODA').  Measured on the
+// 64 x 64 grid: bit-identical to he_population_model and SLOWER -- 71 ms against
+// 35 ms with the production schedule, 90 ms against 75 ms at 32 models per warp.  The control build
+// (-DPW_PS_FREE: same state machine, no vote) takes 101 ms at one model per warp against 48 ms: cut into
+// blocks behind a switch the step keeps ~110 values alive across every block and the compiler spills
+// (1840 bytes of stack against 1280), which costs more than the alignment of the lanes recovers (2.5x over
+// the unaligned state machine at 32 models per warp).  Kept as the record of the experiment.
+//
+// he_population_model runs one model per lane from start to end; the lanes of a warp drift apart
+// (different numbers of corrector iterations, rejected steps, Jacobians, order changes) and the
+// hardware serialises them: at eight models per warp an instruction is issued for two of them on
+// average.  Here every lane keeps its model in the same registers, but the step is cut into blocks
+// (Lsoda::ps_*) and the WARP picks which block runs next: the one most lanes are waiting in, or one a
+// lane has waited `kPsMaxWait` picks for.  Lanes in that phase execute the block together from its
+// first instruction, the others skip it; nothing is shared between lanes, and every lane executes
+// exactly the statements of he_population_model in the same order: bit-identical results
+// (scripts/he_ps.py compares f1, f3, counters and status of the whole grid with torch.equal).
+//
+// Phases of a lane: kPsPredict .. kPsOrder (the LSODA step), kHeEmit (outputs the last step passed),
+// kHePass (end of a solve + beginning of the next relax pass: O(Nr) work), kHeDone.
+enum { kHeEmit = 6, kHePass = 7, kHeDone = 8, kHeNPhase = 9 };
+constexpr int kPsMaxWait = 6;
+
+__device__ __forceinline__ void he_population_ps(const HeParams& p, const LsodaTables& tab, const double* __restrict__ r,
+                                                 const double* __restrict__ v, const double* __restrict__ rho,
+                                                 const double* __restrict__ f_h, int nr, const HeWork& w,
+                                                 const HeOut& out, bool has_model) {
+  // ---- per-model constants (he_population_model, same statements) ----
+  const double rs_cm = p.rs * 7.1492E+09;
+  const double alpha_unit = (rs_cm * rs_cm) * p.vs * 1E5;
+  const double m_h = 1.67262192E-24 / (p.rhos * (rs_cm * rs_cm * rs_cm));
+  const double phi_unit = p.vs * 1E5 / p.rs / 7.1492E+09;
+  const double a_1 = p.rates[2] / (rs_cm * rs_cm), a_3 = p.rates[3] / (rs_cm * rs_cm);
+  const double he_fraction = 1 - p.h_fraction;
+  const double k2 = he_fraction / (p.h_fraction + 4 * he_fraction) / m_h;
+  HeRhs rhs;
+  int phase = kHeDone;
+  if (has_model) {
+    const double a_r1 = 1.54E-13 * pw_pow(p.T / 1E4, -0.486) / alpha_unit;
+    const double a_r3 = 2.10E-13 * pw_pow(p.T / 1E4, -0.778) / alpha_unit;
+    const double phi_1 = p.rates[0] / phi_unit, phi_3 = p.rates[1] / phi_unit;
+    const double a_h_1 = p.rates[4] / (rs_cm * rs_cm), a_h_3 = p.rates[5] / (rs_cm * rs_cm);
+    double q13, q31a, q31b, bq_he, bq_hep;
+    he_collision(p.T, &q13, &q31a, &q31b, &bq_he, &bq_hep);
+    q13 /= alpha_unit; q31a /= alpha_unit; q31b /= alpha_unit; bq_he /= alpha_unit; bq_hep /= alpha_unit;
+    const double bq31 = 5E-10 / alpha_unit;
+    const double ba31 = 1.272E-4 / phi_unit;
+    const double k1 = p.h_fraction / (p.h_fraction + 4 * he_fraction) / m_h;
+    for (int i = 0; i < nr; ++i) w.rn[i] = r[i] * p.r_pl / p.rs;
+    {
+      double c = 0.0, ch = 0.0;
+      for (int i = nr - 1; i >= 0; --i) {
+        const double dr = (i < nr - 1) ? (w.rn[i + 1] - w.rn[i]) : (w.rn[nr - 1] - w.rn[nr - 2]);
+        w.w[i] = dr * rho[i];
+        c += w.w[i];
+        ch += w.w[i] * (1 - f_h[i]);
+        w.tau1h[i] = k1 * a_h_1 * ch;
+        w.tau3h[i] = k1 * a_h_3 * ch;
+        w.tau1[i] = (p.y0[0] * k2 * a_1 * c + w.tau1h[i]);
+        w.tau3[i] = (p.y0[1] * k2 * a_3 * c + w.tau3h[i]);
+      }
+    }
+    rhs.rn = w.rn; rhs.v = v; rhs.rho = rho; rhs.fh = f_h; rhs.tau1 = w.tau1; rhs.tau3 = w.tau3;
+    rhs.slope = w.slope;
+    rhs.e2tab = p.e2tab;
+    rhs.n = nr;
+    he_slopes(w.rn, v, nr, w.slope);
+    he_slopes(w.rn, rho, nr, w.slope + nr);
+    he_slopes(w.rn, f_h, nr, w.slope + 2 * nr);
+    rhs.kc[0] = k1 * a_r1; rhs.kc[1] = k1 * a_r3; rhs.kc[2] = k1 * q13; rhs.kc[3] = k1 * q31a;
+    rhs.kc[4] = k1 * q31b; rhs.kc[5] = k1 * bq31; rhs.kc[6] = k1 * bq_he; rhs.kc[7] = k1 * bq_hep;
+    rhs.phi1 = phi_1; rhs.phi3 = phi_3; rhs.ba31 = ba31;
+    phase = kHePass;
+  }
+  LsodaOpts lo;
+  if (p.method == PW_HE_ODEINT) { lo.rtol = 1.49012e-8; lo.atol = 1.49012e-8; }
+  else { lo.rtol = p.rtol; lo.atol = p.atol; }
+  lo.mxstep = (p.method == PW_HE_ODEINT) ? 500 : 2000000000;
+  lo.hmax = (p.max_step > 0.) ? p.max_step : 0.;
+  lo.h0 = (p.first_step > 0.) ? p.first_step : 0.;
+  double hi_rows[Lsoda<2, HeRhs>::kHiDoubles];
+  Lsoda<2, HeRhs> s(rhs, tab, lo, hi_rows);
+  int nfe = 0, nst = 0, nje = 0, n_relax = 0, status = PW_OK;
+  int it = -1;          // pass being integrated (-1: none yet)
+  int k = 1;            // next output radius
+  bool ok = true;       // the running solve has met no problem
+  double s1 = 0.0, s3 = 0.0;
+  double* f1 = out.f1;
+  double* f3 = out.f3;
+  double* p1 = w.w + nr;
+  double* p3 = w.w + 2 * nr;
+  const int n_pass = p.relax ? p.max_n_relax + 1 : 1;
+  int wait = 0;
+  const unsigned full = 0xffffffffu;
+  for (;;) {
+    // ---- the warp's choice: most populated phase, unless some lane has waited too long ----
+#if defined(PW_PS_FREE)   // control experiment: no vote, every lane runs the block it is in (the code shape alone)
+    if (__all_sync(full, phase == kHeDone)) break;
+    const int run = phase;
+    if (phase == kHeDone) continue;
+#else
+    const unsigned peers = __match_any_sync(full, phase);
+    unsigned key = 0;
+    if (phase != kHeDone)
+      key = ((wait >= kPsMaxWait) ? (1u << 16) : 0u) | ((unsigned)__popc(peers) << 8) | (unsigned)(kHeNPhase - phase);
+    key = __reduce_max_sync(full, key);
+    if (key == 0) break;   // every lane is done
+    const int run = kHeNPhase - (int)(key & 0xffu);
+    if (phase != run) { ++wait; continue; }
+    wait = 0;
+#endif
+    switch (run) {
+      case Lsoda<2, HeRhs>::kPsPredict: phase = s.ps_predict(); break;
+      case Lsoda<2, HeRhs>::kPsIter: phase = s.ps_iter(); break;
+      case Lsoda<2, HeRhs>::kPsJac: phase = s.ps_jac(); break;
+      case Lsoda<2, HeRhs>::kPsTest: phase = s.ps_test(); break;
+      case Lsoda<2, HeRhs>::kPsFail: phase = s.ps_fail(); break;
+      case Lsoda<2, HeRhs>::kPsOrder: phase = s.ps_order(); break;
+      case kHeEmit: {
+        // a step has ended (Lsoda::kPsStepDone == kHeEmit): he_solve's loop body after advance_one()
+        if (s.ps_rc < 0) { ok = false; phase = kHePass; break; }
+        while (k < nr && s.reached(w.rn[k])) {
+          double yo[2];
+          s.intdy(w.rn[k], yo);
+          f1[k] = yo[0];
+          f3[k] = yo[1];
+          ++k;
+          s.new_call();
+        }
+        if (k < nr) { s.ps_new_step(); phase = Lsoda<2, HeRhs>::kPsPredict; }
+        else phase = kHePass;
+      } break;
+      default: {   // kHePass: end of pass `it` (if any), then the beginning of the next one
+        bool finished = false;
+        if (it >= 0) {
+          nfe += s.nfe; nst += s.nst; nje += s.nje;
+          if (!ok) {
+            if (it == 0 || p.method != PW_HE_ODEINT) {
+              status = PW_FAIL_HE_SOLVER;
+            } else {
+              status = PW_WARN_HE_RELAX;
+              for (int i = 0; i < nr; ++i) { f1[i] = p1[i]; f3[i] = p3[i]; }
+            }
+            finished = true;
+          } else {
+            for (int i = 0; i < nr; ++i) {   // clamp, helium.py:715-718
+              if (f1[i] < 0) f1[i] = 1E-15;
+              if (f3[i] < 0) f3[i] = 1E-15;
+              if (f1[i] > 1.0) f1[i] = 1.0;
+              if (f3[i] > 1.0) f3[i] = 1.0;
+            }
+            if (it > 0) {
+              double d1 = 0.0, d3 = 0.0;
+              for (int i = 0; i < nr; ++i) { d1 += f1[i] - p1[i]; d3 += f3[i] - p3[i]; }
+              const double rel1 = fabs(d1) / s1, rel3 = fabs(d3) / s3;
+              if (rel1 < p.convergence && rel3 < p.convergence) finished = true;
+            }
+            if (it + 1 >= n_pass) finished = true;
+          }
+        }
+        if (finished) {
+          if (status == PW_FAIL_HE_SOLVER) {
+            const double nan_ = nan("");
+            for (int i = 0; i < nr; ++i) { f1[i] = nan_; f3[i] = nan_; }
+          } else if (out.rates) {
+            HeRhs rr = rhs;
+            for (int i = 0; i < nr; ++i) {
+              double y[2] = {f1[i], f3[i]}, t[11];
+              rr.coeffs_out(w.rn[i]);
+              rr.eval(y, nullptr, t);
+              for (int q = 0; q < 11; ++q) out.rates[q * nr + i] = t[q] * phi_unit;
+            }
+          }
+          out.scal[0] = (double)n_relax; out.scal[1] = (double)nfe; out.scal[2] = (double)nst; out.scal[3] = (double)nje;
+          *out.status = status;
+          phase = kHeDone;
+          break;
+        }
+        ++it;
+        s1 = 0.0; s3 = 0.0;
+        if (it > 0) {
+          ++n_relax;
+          double c1 = 0.0, c3 = 0.0;
+          for (int i = nr - 1; i >= 0; --i) {
+            c1 += w.w[i] * f1[i];
+            c3 += w.w[i] * f3[i];
+            w.tau1[i] = k2 * a_1 * c1 + w.tau1h[i];
+            w.tau3[i] = k2 * a_3 * c3 + w.tau3h[i];
+          }
+          for (int i = 0; i < nr; ++i) { s1 += f1[i]; s3 += f3[i]; p1[i] = f1[i]; p3[i] = f3[i]; }
+        }
+        he_slopes(w.rn, w.tau1, nr, w.slope + 3 * nr);
+        he_slopes(w.rn, w.tau3, nr, w.slope + 4 * nr);
+        // he_solve: first call of the pass
+        rhs.j = 0; rhs.jc = -2; rhs.xc = nan("");
+        f1[0] = p.y0[0];
+        f3[0] = p.y0[1];
+        k = 1;
+        ok = s.begin(w.rn[0], p.y0, w.rn[1]) >= 0;
+        if (ok && k < nr) { s.ps_new_step(); phase = Lsoda<2, HeRhs>::kPsPredict; }
+        else phase = kHePass;   // (begin failed, or a one-point grid: the pass ends at once)
+      } break;
+    }
+  }
+}
+#endif
+
 }  // namespace pw

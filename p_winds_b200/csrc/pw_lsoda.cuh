@@ -949,6 +949,312 @@ struct Lsoda {
     for (int i = 0; i < N; ++i) yout[i] = yh[1][i];
   }
 
+#if defined(PW_HE_PS_KERNEL)
+  // ---- the same step, cut into phases (experiment, see he_population_ps in pw_helium.cuh) -------
+  // advance_one() + stoda() as a resumable state machine: every ps_*() below runs ONE block of the
+  // step -- exactly the statements of the code above, in the same order -- and returns the phase the
+  // integration is in afterwards.  The helium kernel keeps one model per lane and lets the WARP decide
+  // which block runs next (the phase most of its lanes are waiting in), so that lanes execute a block
+  // together from its first instruction instead of drifting through the step at different offsets;
+  // see he_population_ps (pw_helium.cuh).  The locals of stoda() that live across blocks are members.
+  enum { kPsPredict = 0, kPsIter = 1, kPsJac = 2, kPsTest = 3, kPsFail = 4, kPsOrder = 5, kPsStepDone = 6 };
+  double ps_told, ps_rh, ps_pdh, ps_del, ps_dsm, ps_pnorm, ps_rhup, ps_rate, ps_delp;
+  int ps_ncf, ps_m, ps_rc;
+  bool ps_reload, ps_rescale, ps_finish, ps_cfail, ps_efail, ps_fresh;
+
+  PW_HD void ps_new_step() { ps_fresh = true; }   // the next ps_predict() starts a new advance_one()
+
+  PW_HD int ps_step_done() {   // tail of advance_one()
+    if (kflag == 0) {
+      if (meth != mused) {
+        tsw = tn;
+        maxord = mxordn;
+        if (meth == 2) maxord = mxords;
+        jstart = -1;
+      }
+      ps_rc = 0;
+    } else {
+      ps_rc = (kflag == -1) ? -4 : -5;
+    }
+    return kPsStepDone;
+  }
+
+  PW_HD int ps_predict() {
+    if (ps_fresh) {
+      ps_fresh = false;
+      if (nst != 0 || jstart != 0) {  // label 250 (skipped on the very first pass)
+        if ((nst - nslast) >= o.mxstep) { ps_rc = -1; return kPsStepDone; }
+        if (!ewset(yh[1])) { ps_rc = -6; return kPsStepDone; }
+      }
+      if (!(o.rtol >= kEps && o.atol >= 0.)) {
+        const double tolsf = kEps * vmnorm(yh[1]);
+        if (tolsf > 1.) { ps_rc = (nst == 0) ? -3 : -2; return kPsStepDone; }
+      }
+      if ((tn + h) == tn) ++nhnil;
+      // stoda() entry
+      kflag = 0;
+      ps_told = tn;
+      ps_ncf = 0;
+      ps_cfail = false; ps_efail = false;
+      ierpj = 0; iersl = 0; jcur = 0;
+      ps_rh = 0.; ps_pdh = 0.; ps_del = 0.; ps_dsm = 0.;
+      ps_m = 0;
+      ps_reload = false; ps_rescale = false; ps_finish = false;
+      if (jstart == 0) {
+        lmax = maxord + 1;
+        nq = 1; l = 2; ialth = 2; rmax = 10000.; rc = 0.; el0 = 1.; crate = 0.7;
+        hold = h; nslp = 0; ipup = miter;
+        icount = 20; irflag = 0; pdest = 0.; pdlast = 0.; ratio = 5.;
+        meth_tab = 1;
+        ps_reload = true;
+      }
+      if (jstart == -1) {
+        ipup = miter;
+        lmax = maxord + 1;
+        if (ialth == 1) ialth = 2;
+        if (meth != mused) {
+          meth_tab = meth;
+          ialth = l;
+          ps_reload = true;
+        }
+        if (h != hold) {
+          ps_rh = PW_DIV(h, hold);
+          h = hold;
+          ps_rescale = true;
+        }
+      }
+    }
+    if (ps_reload) {
+      resetcoeff();
+      ps_reload = false;
+    }
+    if (ps_rescale) {
+      scaleh(&ps_rh, &ps_pdh);
+      ps_rescale = false;
+      if (ps_finish) {
+        rmax = 10.;
+        endstoda();
+        return ps_step_done();
+      }
+    }
+    if (fabs(rc - 1.) > 0.3 /*ccmax*/) ipup = miter;
+    if (nst >= nslp + 20 /*msbp*/) ipup = miter;
+    tn += h;
+    pascal(1.);
+    ps_pnorm = vmnorm(yh[1]);
+    // correction(): labels 220 ff.
+    ps_m = 0; ps_rate = 0.; ps_del = 0.; ps_delp = 0.;
+#pragma unroll
+    for (int i = 0; i < N; ++i) y[i] = yh[1][i];
+    f.at(tn);
+    return kPsIter;
+  }
+
+  // second half of a corrector iteration: chord / functional update, convergence test
+  PW_HD int ps_iter_b() {
+    double del;
+    if (ps_m == 0) {
+#pragma unroll
+      for (int i = 0; i < N; ++i) acor[i] = 0.;
+    }
+    if (miter == 0) {
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+        savf[i] = h * savf[i] - yh[2][i];
+        y[i] = savf[i] - acor[i];
+      }
+      del = vmnorm(y);
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+        y[i] = yh[1][i] + el0 * savf[i];
+        acor[i] = savf[i];
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < N; ++i) y[i] = h * savf[i] - (yh[2][i] + acor[i]);
+      solsy(y);
+      del = vmnorm(y);
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+        acor[i] += y[i];
+        y[i] = yh[1][i] + el0 * acor[i];
+      }
+    }
+    ps_del = del;
+    bool conv = (del <= 100. * ps_pnorm * kEps);
+    if (!conv && (ps_m != 0 || meth != 1)) {
+      if (ps_m != 0) {
+        double rm = 1024.;
+        if (del <= (1024. * ps_delp)) rm = PW_DIV(del, ps_delp);
+        ps_rate = (rm > ps_rate) ? rm : ps_rate;
+        const double c2 = 0.2 * crate;
+        crate = (rm > c2) ? rm : c2;
+      }
+      const double c15 = 1.5 * crate;
+      const double dcon = PW_RDIV(del * ((c15 < 1.) ? c15 : 1.), tq2 * conit, rtc);
+      if (dcon <= 1.) {
+        if (ps_rate != 0.) {
+          const double pd = PW_DIV(ps_rate, fabs(h * el0));
+          pdest = (pd > pdest) ? pd : pdest;
+        }
+        if (pdest != 0.) pdlast = pdest;
+        conv = true;
+      }
+    }
+    if (conv) return kPsTest;
+    ++ps_m;
+    if (ps_m == 3 /*maxcor*/ || (ps_m >= 2 && del > 2. * ps_delp)) {
+      if (miter == 0 || jcur == 1) { ps_cfail = true; return kPsFail; }
+      ipup = miter;
+      ps_m = 0; ps_rate = 0.; ps_del = 0.;
+#pragma unroll
+      for (int i = 0; i < N; ++i) y[i] = yh[1][i];
+    } else {
+      ps_delp = del;
+    }
+    return kPsIter;
+  }
+
+  PW_HD int ps_iter() {
+    f.eval(y, savf);
+    ++nfe;
+    if (ps_m == 0 && ipup > 0) return kPsJac;   // this iteration needs the Jacobian first
+    return ps_iter_b();
+  }
+
+  PW_HD int ps_jac() {
+    prja();
+    ipup = 0;
+    rc = 1.;
+    nslp = nst;
+    crate = 0.7;
+    if (ierpj != 0) { ps_cfail = true; return kPsFail; }
+    return ps_iter_b();
+  }
+
+  PW_HD int ps_test() {
+    jcur = 0;
+    ps_dsm = PW_RDIV((ps_m == 0) ? ps_del : vmnorm(acor), tq2, rtq2);
+    if (!(ps_dsm <= 1.)) { ps_cfail = false; ps_efail = true; return kPsFail; }
+    ps_efail = false;
+    // successful step
+    kflag = 0;
+    ++nst;
+    hu = h;
+    nqu = nq;
+    rtq2u = rtq2;
+    mused = meth;
+#pragma unroll
+    for (int j = 1; j <= kF + 1; ++j) {
+      const bool on = (j <= l);
+      const double r = elp[j];
+#pragma unroll
+      for (int i = 0; i < N; ++i)
+        if (on) yh[j][i] += r * acor[i];
+    }
+    if (PW_UNLIKELY(nq > kF)) {
+#pragma unroll 1
+      for (int j = kF + 2; j <= l; ++j) {
+        const double r = elp[j];
+        for (int i = 0; i < N; ++i) yhs_[(j) * N + i] += r * acor[i];
+      }
+    }
+    --icount;
+    if (icount < 0) {
+      methodswitch(ps_dsm, ps_pnorm, &ps_pdh, &ps_rh);
+      if (meth != mused) {
+        ps_rescale = true;
+        ps_finish = true;
+        return kPsPredict;
+      }
+    }
+    --ialth;
+    if (ialth != 0) {
+      if (!(ialth > 1 || l == lmax)) row_set(lmax, acor);
+      endstoda();
+      return ps_step_done();
+    }
+    ps_rhup = 0.;
+    if (l != lmax) {
+      double top[N];
+      row_get(lmax, top);
+#pragma unroll
+      for (int i = 0; i < N; ++i) savf[i] = acor[i] - top[i];
+      const double dup = PW_RDIV(vmnorm(savf), tq3, rtq3);
+      ps_rhup = pw_step_ratio(dup, l + 1, 1.4, 0.0000014);
+    }
+    return kPsOrder;
+  }
+
+  // corrector failure (label 430) or error-test failure (label 500): take the prediction back
+  PW_HD int ps_fail() {
+    tn = ps_told;
+    rmax = 2.;
+    pascal(-1.);
+    if (ps_cfail) {
+      ps_cfail = false;
+      ++ps_ncf;
+      if (h == 0. || ps_ncf == 10 /*mxncf*/) {
+        kflag = -2;
+        hold = h;
+        jstart = 1;
+        return ps_step_done();
+      }
+      ps_rh = 0.25;
+      ipup = miter;
+      ps_rescale = true;
+      return kPsPredict;
+    }
+    --kflag;
+    if (h == 0.) {
+      kflag = -1; hold = h; jstart = 1;
+      return ps_step_done();
+    }
+    if (kflag <= -3) {
+      if (kflag == -10) {
+        kflag = -1; hold = h; jstart = 1;
+        return ps_step_done();
+      }
+      ps_rh = 0.1;
+      h *= ps_rh;
+#pragma unroll
+      for (int i = 0; i < N; ++i) y[i] = yh[1][i];
+      f.at_cold(tn);
+      f.eval_cold(y, savf);
+      ++nfe;
+#pragma unroll
+      for (int i = 0; i < N; ++i) yh[2][i] = h * savf[i];
+      ipup = miter;
+      ialth = 5;
+      if (nq != 1) {
+        nq = 1;
+        l = 2;
+        ps_reload = true;
+      }
+      return kPsPredict;
+    }
+    ps_rhup = 0.;
+    return kPsOrder;
+  }
+
+  PW_HD int ps_order() {
+    int orderflag;
+    orderswitch(ps_rhup, ps_dsm, &ps_pdh, &ps_rh, &orderflag);
+    if (!ps_efail) {
+      if (orderflag == 0) {
+        endstoda();
+        return ps_step_done();
+      }
+      ps_finish = true;
+    } else if (orderflag == 0) {
+      ps_rh = (ps_rh < 0.2) ? ps_rh : 0.2;
+    }
+    if (orderflag == 2) ps_reload = true;
+    ps_rescale = true;
+    return kPsPredict;
+  }
+#endif  // PW_HE_PS_KERNEL
+
   // One `lsoda(..., itask = 1)` call: advance to tout and interpolate.
   // First call initialises from (t0, y0).  Returns istate.
   PW_HD int call(double t0, const double* y0, double tout, double* yout) {
