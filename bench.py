@@ -380,20 +380,20 @@ def run_ours(args):
     kernels = {
         'k_helium': {'ms': t_he, 'share_of_step': t_he / (t_h + t_he + t_rt), 'flop': w_he,
                      'achieved_tflops': w_he / (t_he * 1e-3) / 1e12,
-                     'note': 'latency bound: %.0f dependent RHS evaluations per model (max %.0f, counting the '
-                             'relax passes the cycle shortcut does not re-run), one thread per model, '
-                             'cost-ordered schedule' % (nfe_he / B, float(he['scal'][:, 1].max()))},
+                     'note': 'latency bound: %.0f dependent RHS evaluations per model (max %.0f), one thread per '
+                             'model, cost-ordered schedule' % (nfe_he / B, float(he['scal'][:, 1].max()))},
         'k_h_fields+k_h_solve+k_h_finish': {'ms': t_h, 'share_of_step': t_h / (t_h + t_he + t_rt), 'flop': w_h,
                        'achieved_tflops': w_h / (t_h * 1e-3) / 1e12},
-        'k_rt_los+k_rt_sum+k_rt_reduce': {'ms': t_rt, 'share_of_step': t_rt / (t_h + t_he + t_rt),
+        'k_rt_los+k_rt_sum2': {'ms': t_rt, 'share_of_step': t_rt / (t_h + t_he + t_rt),
                                            'flop': w_rt, 'achieved_tflops': w_rt / (t_rt * 1e-3) / 1e12,
                                            'note': 'flop = the reference algorithm (every lit pixel, 20-flop exp); '
                                                    'the kernel merges equal-radius pixels (%d -> %d terms) and '
-                                                   'uses a 12-instruction exp' % (px, eng.n_active_pixels())},
+                                                   'needs 10 FP64 instructions per term (ncu: FP64 pipe 72 %% busy)'
+                                                   % (px, eng.n_active_pixels())},
     }
     dom = max(kernels, key=lambda k: kernels[k]['ms'])
     # DRAM bytes of the dominant kernel per launch, from the committed `ncu --set full` capture
-    # (profiles/r1_ncu_full_summary.csv: dram__bytes_read.sum + dram__bytes_write.sum); null if absent
+    # (profiles/r2_ncu_full_summary.csv: dram__bytes_read.sum + dram__bytes_write.sum); null if absent
     traffic = None
     try:
         import csv
@@ -412,7 +412,7 @@ def run_ours(args):
     roofline = {'bound': 'fp64', 'kernel': dom, 'achieved': kernels[dom]['achieved_tflops'],
                 'peak': fp64_peak, 'unit': 'TFLOP/s', 'frac': kernels[dom]['achieved_tflops'] / fp64_peak,
                 'traffic': traffic,
-                'traffic_source': 'profiles/r1_ncu_full_summary.csv (ncu --set full capture of k_helium, bytes per launch); '
+                'traffic_source': 'profiles/r2_ncu_full_summary.csv (ncu --set full capture of k_helium, bytes per launch); '
                                   'not an HBM-bound kernel' if traffic is not None else None,
                 'peak_source': 'FP64 DFMA microbenchmark run in this process (pwb_fp64_peak); '
                                'MEASURED_PEAKS.json has no FP64 figure; no tensor cores on this path',
