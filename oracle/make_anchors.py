@@ -7,6 +7,7 @@ TEST INFRASTRUCTURE.  Run in the build container only (needs /root/reference):
     python oracle/make_anchors.py ridge     # off-grid models of the strip where helium fails
     python oracle/make_anchors.py p3        # tests/golden/anchors_p3.npz
     python oracle/make_anchors.py classes   # tests/golden/he_failure_classes.npz
+    python oracle/make_anchors.py tight     # tests/golden/anchors_tight_grid.npz
 
 ``anchors_p3.npz``: 272 (T0, Mdot, h) triples (144 non-tidal, 128 tidal, T0 from 5000 K so
 that the models the reference fails on are in it).  For each triple the reference's own
@@ -56,6 +57,15 @@ def _init():
     _G['sp'] = mg.spectrum_dict()
     geo = np.load(os.path.join(OUT, 'geometry.npz'))
     _G['geom'] = (geo['i0'], geo['r_map'])
+
+
+def _run_tight(args):
+    """One model at the tight solver tolerances of parity tier P2 (H rtol 1e-10 / atol 1e-13, He
+    method='LSODA' rtol 1e-10 / atol 1e-16)."""
+    T, md, h, tidal = args
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        return _G['mg'].one_model(_G['sp'], _G['geom'], float(T), float(md), float(h), bool(tidal), True)
 
 
 def _run(args):
@@ -182,6 +192,24 @@ def p3(pool):
                                                           nz[k][ok].max()))
 
 
+def tight(pool):
+    """tests/golden/anchors_tight_grid.npz: 100 models over the parameter box of the bench grids at the
+    tight tolerances, where BASELINE's 1e-6 (fractions) / 1e-5 (transit depth) hold model by model."""
+    trip = [(T, md, 0.9, False) for T in np.linspace(9000, 13000, 8) for md in np.logspace(9.5, 12, 8)]
+    trip += [(T, md, h, True) for T in np.linspace(9000, 13000, 6) for md in np.logspace(9.5, 11.8, 3)
+             for h in (0.85, 0.95)]
+    res = pool.map(_run_tight, trip, chunksize=1)
+    keys = ('status', 'f_r', 'mu_bar', 'v', 'rho', 'f_1', 'f_3', 'spectrum', 'vs', 'rs', 'rhos')
+    d = {k: np.array([o[k] for o in res]) for k in keys}
+    d['T0'] = np.array([t[0] for t in trip])
+    d['mdot'] = np.array([t[1] for t in trip])
+    d['h_fraction'] = np.array([t[2] for t in trip])
+    d['tidal'] = np.array([t[3] for t in trip])
+    np.savez_compressed(os.path.join(OUT, 'anchors_tight_grid.npz'), **d)
+    st = d['status']
+    print('anchors_tight_grid: %d models, status histogram %s' % (len(trip), {int(k): int((st == k).sum()) for k in np.unique(st)}))
+
+
 def classes(pool):
     parts = []
     for name, fn in (('bench_grid_status.npz', scan), ('ridge_status.npz', scan_ridge)):
@@ -240,3 +268,5 @@ if __name__ == '__main__':
             p3(pool)
         if what in ('classes', 'all'):
             classes(pool)
+        if what in ('tight', 'all'):
+            tight(pool)

@@ -102,6 +102,29 @@ def test_forward_tight_tolerances_per_model(eng, name):
     assert np.max(_rel(o['spectrum'], d['spectrum'])) < 1e-7
 
 
+def test_forward_tight_grid_100_models(eng):
+    """BASELINE.json's tolerances, model by model, over the parameter box of the bench grids: 64
+    non-tidal + 36 tidal models through the unmodified reference at tight solver tolerances
+    (tests/golden/anchors_tight_grid.npz, oracle/make_anchors.py tight).  Ion and population fractions
+    within 1e-6, He 10830 transit spectrum within 1e-5 (measured: ~1e-7 and ~1e-9)."""
+    d = golden('anchors_tight_grid')
+    worst = {'f_r': 0.0, 'f_1': 0.0, 'f_3': 0.0, 'spectrum': 0.0, 'mu': 0.0}
+    for tidal in (False, True):
+        m = d['tidal'] == tidal
+        o = _forward(eng, d['T0'][m], d['mdot'][m], d['h_fraction'][m], tight=True, tidal=tidal)
+        assert (o['status'] == 0).all() and (d['status'][m] == 0).all()
+        worst['f_r'] = max(worst['f_r'], np.max(_rel(o['f_r'][:, 1:], d['f_r'][m][:, 1:])))
+        worst['mu'] = max(worst['mu'], np.max(_rel(o['hscal'][:, 0], d['mu_bar'][m])))
+        worst['f_1'] = max(worst['f_1'], np.max(_rel(o['f_1'], d['f_1'][m])))
+        f3 = d['f_3'][m]
+        big = f3 > 1e-3 * f3.max(axis=1, keepdims=True)
+        worst['f_3'] = max(worst['f_3'], np.max(_rel(o['f_3'][big], f3[big])))
+        worst['spectrum'] = max(worst['spectrum'], np.max(_rel(o['spectrum'], d['spectrum'][m])))
+    print('tight grid, worst relative deviations over 100 models:', {k: float('%.2e' % v) for k, v in worst.items()})
+    assert worst['f_r'] < 1e-6 and worst['mu'] < 1e-6 and worst['f_1'] < 1e-6 and worst['f_3'] < 1e-6
+    assert worst['spectrum'] < 1e-5
+
+
 # --------------------------------------------------------------------------- P3
 def _p3_forward(eng, d):
     """The 272 anchor triples of tests/golden/anchors_p3.npz through forward_batch (reference

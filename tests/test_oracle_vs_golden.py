@@ -131,6 +131,20 @@ def test_p3_anchor_fixture_and_oracle(oracle, sed):
                 assert np.array_equal(o[key], d[key][i]), (i, key)
 
 
+def test_tight_grid_fixture_and_oracle(oracle, sed):
+    """tests/golden/anchors_tight_grid.npz: shape, and the oracle bit for bit on a sample."""
+    d = golden('anchors_tight_grid')
+    geo = golden('geometry')
+    assert len(d['T0']) == 100 and (d['status'] == 0).all()
+    for i in (3, 40, 70, 99):
+        s = oracle.Setup(sed, r=R, tidal=bool(d['tidal'][i]), i0=geo['i0'], r_map=geo['r_map'],
+                         h_tol=dict(rtol=1e-10, atol=1e-13), he_method='LSODA', he_tol=dict(rtol=1e-10, atol=1e-16))
+        o = oracle.forward_model(s, float(d['T0'][i]), float(d['mdot'][i]), float(d['h_fraction'][i]))
+        assert o['status'] == 0
+        for key in ('f_r', 'f_1', 'f_3', 'spectrum'):
+            assert np.array_equal(o[key], d[key][i]), (i, key)
+
+
 def test_helium_failure_class_fixture_and_oracle(oracle, sed):
     """tests/golden/he_failure_classes.npz: >= 20 models of each helium failure class from the unmodified
     reference; class-3 results are not reproducible run to run (recorded), the class is.  The oracle
