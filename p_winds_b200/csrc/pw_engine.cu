@@ -295,7 +295,7 @@ __global__ void k_he_key(int B, const double* __restrict__ rhos, int sstride, co
 
 constexpr int kHeBuckets = 4096;
 __global__ void __launch_bounds__(1024, 1)
-k_he_order(int B, const double* __restrict__ key, const int* __restrict__ status, int* __restrict__ order) {
+k_he_order(int B, const double* __restrict__ key, const int* __restrict__ status, int* __restrict__ order, int coarse) {
   __shared__ int hist[kHeBuckets];
   __shared__ unsigned long long s_lo, s_hi;
   const int t = threadIdx.x;
@@ -323,7 +323,8 @@ k_he_order(int B, const double* __restrict__ key, const int* __restrict__ status
   const double scale = (hi > lo) ? (double)(kHeBuckets - 1) / (double)(hi - lo) : 0.0;
   auto bucket = [&](int b) {   // 0 = costliest; failed models last
     const unsigned long long k = key_bits(b);
-    return (k == 0ull || k < lo) ? kHeBuckets - 1 : (kHeBuckets - 1) - (int)((double)(k - lo) * scale);
+    const int q = (k == 0ull || k < lo) ? kHeBuckets - 1 : (kHeBuckets - 1) - (int)((double)(k - lo) * scale);
+    return (q / coarse) * coarse;   // `coarse` buckets merged into one class (order inside a class: as it falls)
   };
   for (int b = t; b < B; b += blockDim.x) atomicAdd(&hist[bucket(b)], 1);
   __syncthreads();
@@ -1307,7 +1308,7 @@ int pwb_h_ion_fraction_batch(pwb_ctx* c, int B, const double* d_T, const double*
 // 40 % in fours, the cheapest 30 % eight to a warp -- is the measured optimum for the 64 x 64
 // retrieval grid on one B200 (scripts/sweep_sched.py: 62.6 ms, flat within 3 % around it; one
 // lane count for all: 75-90 ms); all lane counts are scaled up together when the
-// batch would otherwise need more warps than the GPU keeps resident (8 per SM at 255 registers).
+// batch would otherwise need more warps than the GPU takes in one wave (7 per SM, see he_schedule).
 // PWB_HE_SCHED="f:L,f:L,..." overrides the pattern, PWB_HE_LANES=L forces one lane count and the
 // caller's order.
 static HeSched he_schedule(pwb_ctx* c, int B, bool* sorted) {
@@ -1331,7 +1332,11 @@ static HeSched he_schedule(pwb_ctx* c, int B, bool* sorted) {
     const int v = atoi(e);
     if (v >= 1 && v <= 32) { nseg = 1; frac[0] = 1.0; lanes[0] = v; *sorted = false; }
   } else if (!getenv("PWB_HE_SCHED")) {
-    double per_sm = 8.0;
+    // Warps the schedule may ask for per SM.  The register file holds 8 of these 255-register warps, but a
+    // grid of exactly 8 x SMs does not land evenly: the stragglers start when the first warps finish and
+    // the kernel takes a quarter longer (24 576 models: 67.5 ms at 8, 52.6 ms at 7, 53.9 at 6;
+    // scripts/he_big.py).  7 leaves the slack.
+    double per_sm = 7.0;
     if (const char* e2 = getenv("PWB_HE_CAP")) { const double v = atof(e2); if (v >= 1. && v <= 32.) per_sm = v; }
     const double capacity = per_sm * c->sm_count;
     double warps = 0;
@@ -1366,7 +1371,13 @@ static int launch_helium(pwb_ctx* c, cudaStream_t s, int B, const double* d_T, c
   if (sorted) {
     if (c->he_key.ensure(sizeof(double) * (size_t)B)) return fail(c, "out of device memory");
     k_he_key<<<(B + 127) / 128, 128, 0, s>>>(B, d_rhos, sstride, d_r, Nr, d_rho, d_status, c->he_key.as<double>());
-    k_he_order<<<1, 1024, 0, s>>>(B, c->he_key.as<double>(), d_status, order);
+    // A batch that takes several waves of warps (more models than 32 lanes x 7 warps x SMs) is sorted into
+    // 128 cost classes only: with the fine sort every warp of a wave holds models of the same cost, the
+    // warps of an SM move through the same phases in step and finish together; mixing within a class
+    // staggers them (196 608 models: 263 -> 233 ms; scripts/he_coarse.sh).  One wave: fine sort (55 vs 57 ms).
+    int coarse = ((long long)B > 32LL * 7 * c->sm_count) ? 32 : 1;
+    if (const char* e = getenv("PWB_HE_COARSE")) { const int v = atoi(e); if (v >= 1 && v <= kHeBuckets) coarse = v; }
+    k_he_order<<<1, 1024, 0, s>>>(B, c->he_key.as<double>(), d_status, order, coarse);
     c->launches += 2;
   }
   const int* ord = sorted ? order : nullptr;
