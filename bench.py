@@ -397,7 +397,7 @@ def run_ours(args):
     traffic = None
     try:
         import csv
-        with open(os.path.join(ROOT, 'profiles', 'r1_ncu_full_summary.csv')) as fh:
+        with open(os.path.join(ROOT, 'profiles', 'r2_ncu_full_summary.csv')) as fh:
             rows = list(csv.reader(fh))
         hdr = rows[0]
         for row in rows[1:]:

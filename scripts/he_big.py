@@ -30,7 +30,7 @@ def prep(big):
     return (Td, hfd, h['scal'][:, 1].contiguous(), h['scal'][:, 2].contiguous(), h['scal'][:, 3].contiguous(), r, h['v'], h['rho'], h['f_r'], heo), h['status']
 
 
-for big in (False, True):
+for big in ((False,) if os.environ.get("SMALL_ONLY") else (False, True)):
     args, st = prep(big)
     for cap in os.environ.get('CAPS', '8').split(','):
         os.environ.pop('PWB_HE_SCHED', None); os.environ.pop('PWB_HE_CAP', None)
