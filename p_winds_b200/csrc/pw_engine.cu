@@ -747,8 +747,9 @@ k_rt_sum(int B, int nw, int nr, pwb_rt_opts o, const double* __restrict__ wl, co
 // are combined in segment order: a model's spectrum is bit-identical alone or inside any grid.
 //
 // Layout: a CTA owns one (model, wavelength tile) and G <= 4 pixel groups of TPG threads; a thread owns
-// TWO wavelength bins (k, k + TPG) of the tile, so one 16-byte shared-memory read (N_p, I0_p) feeds two
-// independent exp chains and no warp idles at Nw = 200 (4 x 100 threads).
+// TWO adjacent wavelength bins (2u, 2u + 1) of the tile, so one 16-byte shared-memory read (N_p, I0_p) feeds two
+// independent exp chains, no warp idles at Nw = 200 (2 x 100 threads), and a thread's two results leave in
+// one 16-byte store: a warp writes 512 contiguous bytes of the spectrum.
 //   ext == 1  the CTA sums all S segments of all phases: group g takes segments g, g + G, ...; after
 //             each round the G segment sums meet in shared memory and group 0 adds them in segment
 //             order; depth, phase mean and the spectrum store follow -- no partial spectra in HBM, no
@@ -768,6 +769,16 @@ struct RtGeoSlots {
   const double* meta[16];
   double depth[16];
 };
+
+// two adjacent results of one thread: one 16-byte store where both exist and the address allows it
+__device__ __forceinline__ void store_pair(double* p, double a, double b, bool va, bool vb) {
+  if (va && vb && (reinterpret_cast<size_t>(p) & 15) == 0) {
+    *reinterpret_cast<double2*>(p) = make_double2(a, b);
+  } else {
+    if (va) p[0] = a;
+    if (vb) p[1] = b;
+  }
+}
 
 template <int kMaxThreads>
 __global__ void __launch_bounds__(kMaxThreads, (kMaxThreads <= 256) ? 3 : (kMaxThreads <= 512 ? 2 : 1))
@@ -817,8 +828,9 @@ k_rt_sum2(int B, int nw, int nr, const __grid_constant__ pwb_rt_opts o, const do
       const double ph = s_phi[k];
       for (int i = 0; i < nr; ++i) tau_out[((size_t)b * nr + i) * nw + kbase + k] = s_ncol[i] * ph;
     }
-  const bool v0 = u < wt, v1 = u + TPG < wt;
-  const double phi0 = v0 ? s_phi[u] : 0.0, phi1 = v1 ? s_phi[u + TPG] : 0.0;
+  const int k0 = 2 * u, k1 = 2 * u + 1;       // this thread's bins within the tile
+  const bool v0 = k0 < wt, v1 = k1 < wt;
+  const double phi0 = v0 ? s_phi[k0] : 0.0, phi1 = v1 ? s_phi[k1] : 0.0;
   double phi_max = 0.0;   // of the tile (every thread scans the shared copy once: Wt <= 512 reads)
   for (int k = 0; k < wt; ++k) { const double x = fabs(s_phi[k]); phi_max = (x > phi_max || x != x) ? x : phi_max; }
   const unsigned e2 = (unsigned)__cvta_generic_to_shared(s_e2);
@@ -892,14 +904,13 @@ k_rt_sum2(int B, int nw, int nr, const __grid_constant__ pwb_rt_opts o, const do
       }
       if (ext > 1) {   // one segment per CTA: hand its sum to k_rt_reduce
         if (seg == 0) { acc0 += geo.meta[gi][1]; acc1 += geo.meta[gi][1]; }   // lit pixels with tau = 0
-        if (v0) part[((size_t)b * S + seg) * nw + kbase + u] = acc0;
-        if (v1) part[((size_t)b * S + seg) * nw + kbase + u + TPG] = acc1;
+        store_pair(part + ((size_t)b * S + seg) * nw + kbase + k0, acc0, acc1, v0, v1);
         return;
       }
       // the G segment sums of this round, added in segment order by group 0
       if (g > 0 && seg < S) {
-        if (v0) s_x[(size_t)g * Wt + u] = acc0;
-        if (v1) s_x[(size_t)g * Wt + u + TPG] = acc1;
+        if (v0) s_x[(size_t)g * Wt + k0] = acc0;
+        if (v1) s_x[(size_t)g * Wt + k1] = acc1;
       }
       __syncthreads();
       if (g == 0) {
@@ -907,8 +918,8 @@ k_rt_sum2(int B, int nw, int nr, const __grid_constant__ pwb_rt_opts o, const do
         ph0 = (round == 0) ? acc0 : ph0 + acc0;
         ph1 = (round == 0) ? acc1 : ph1 + acc1;
         for (int q = 1; q < G && round * G + q < S; ++q) {
-          if (v0) ph0 += s_x[(size_t)q * Wt + u];
-          if (v1) ph1 += s_x[(size_t)q * Wt + u + TPG];
+          if (v0) ph0 += s_x[(size_t)q * Wt + k0];
+          if (v1) ph1 += s_x[(size_t)q * Wt + k1];
         }
       }
     }
@@ -921,8 +932,7 @@ k_rt_sum2(int B, int nw, int nr, const __grid_constant__ pwb_rt_opts o, const do
   }
   if (g == 0) {
     if (geo.n_geo > 1) { tot0 /= (double)geo.n_geo; tot1 /= (double)geo.n_geo; }
-    if (v0) spec[(size_t)b * nw + kbase + u] = tot0;
-    if (v1) spec[(size_t)b * nw + kbase + u + TPG] = tot1;
+    store_pair(spec + (size_t)b * nw + kbase + k0, tot0, tot1, v0, v1);
   }
 }
 
