@@ -1605,7 +1605,9 @@ static int launch_rt(pwb_ctx* c, cudaStream_t s, int B, const double* d_n, const
     const size_t smem = sizeof(double) * (4 * (size_t)Nr + 4 * (size_t)o->z_grid_size);
     if (smem > 100 * 1024) return fail(c, "pwb_rt2d_batch: z_grid_size too large for the 'formal' kernel");
     dim3 g1(Nr, B);
-    k_rt_formal_tau<<<g1, 256, smem, s>>>(B, Nw, Nr, *o, c->geo_r.as<double>(), d_n, d_v, d_T, d_wl, d_status, tau_tab);
+    // threads own wavelengths: no more warps than the bins need (Nw = 200: 7 warps, not 8)
+    const int nt_formal = std::min(256, ((Nw + 31) / 32) * 32);
+    k_rt_formal_tau<<<g1, nt_formal, smem, s>>>(B, Nw, Nr, *o, c->geo_r.as<double>(), d_n, d_v, d_T, d_wl, d_status, tau_tab);
     c->launches++;
     PWB_CUDA(c, cudaGetLastError());
   } else {
