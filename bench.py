@@ -465,7 +465,7 @@ def run_ours(args):
             t = max_over_ranks(e0.elapsed_time(e1))
             best = t if (best is None or _ == 1) else min(best, t)
         stl = outl['status']
-        cnt = torch.stack([(stl == k).sum() for k in range(5)]).to(torch.float64)
+        cnt = torch.stack([(stl == k).sum() for k in range(6)]).to(torch.float64)
         if world > 1:
             dist.all_reduce(cnt)
         return best, [int(x) for x in cnt.tolist()]
@@ -509,7 +509,7 @@ def run_ours(args):
         with mp.get_context('fork').Pool(cores, initializer=_cpu_init) as pool:
             cpu_base, _ = cpu_loop(T, md, hf, max(64, 2 * cores), pool, cores)
 
-    hist = torch.stack([(out['status'] == k).sum() for k in range(5)]).to(torch.float64)
+    hist = torch.stack([(out['status'] == k).sum() for k in range(6)]).to(torch.float64)
     if world > 1:
         dist.all_reduce(hist)
     hist = [int(x) for x in hist.tolist()]
@@ -528,7 +528,7 @@ def run_ours(args):
                 'cpu_baseline': cpu_base, 'per_rank': per_rank, 'cfg3': cfg3_line, 'large_batch': large,
                 'highres_batch': highres,
                 'status_histogram': {'ok': hist[0], 'h_solver_failed': hist[1], 'he_solver_failed': hist[2],
-                                     'he_relax_warning': hist[3], 'nan': hist[4],
+                                     'he_relax_warning': hist[3], 'nan': hist[4], 'h_work_limit': hist[5],
                                      'note': 'status 3 = an odeint of the helium relax loop warned: the reference\'s own '
                                              'result is undefined there; chi2 = +inf by default'},
                 'models_ok_frac': hist[0] / n_global, 'wall_s_timed_region': wall_dev}

@@ -32,7 +32,11 @@ enum pwb_status {
   PWB_OK = 0,
   PWB_FAIL_H_SOLVER = 1,   /* hydrogen.py:458-460, :511-513 RuntimeError */
   PWB_FAIL_HE_SOLVER = 2,  /* helium.py:693-697, :708-710 RuntimeError */
-  PWB_WARN_HE_RELAX = 3,   /* helium.py:736 odeint warning inside the relax loop */
+  /* helium.py:736: an odeint of the relax loop warned.  The reference does not check that call and goes on
+   * with rows scipy left uninitialised (its result is not reproducible); the engine stops at the warning:
+   * profiles / spectrum of the last completed pass, n_relax = the pass that warned.  chi^2 and
+   * log-likelihood treat the model as failed unless pwb_set_relax_warning_policy(ctx, 1). */
+  PWB_WARN_HE_RELAX = 3,
   PWB_FAIL_NAN = 4,
   /* The hydrogen RK45 solve was given up after pwb_h_opts.max_nfev right-hand-side evaluations.
    * No reference equivalent: scipy's RK45 has no step limit; on a stiff start (cold, dense winds,
