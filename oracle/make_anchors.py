@@ -8,6 +8,7 @@ TEST INFRASTRUCTURE.  Run in the build container only (needs /root/reference):
     python oracle/make_anchors.py p3        # tests/golden/anchors_p3.npz
     python oracle/make_anchors.py classes   # tests/golden/he_failure_classes.npz
     python oracle/make_anchors.py tight     # tests/golden/anchors_tight_grid.npz
+    python oracle/make_anchors.py lya       # tests/golden/anchors_lya.npz (BASELINE configs[1])
 
 ``anchors_p3.npz``: 272 (T0, Mdot, h) triples (144 non-tidal, 128 tidal, T0 from 5000 K so
 that the models the reference fails on are in it).  For each triple the reference's own
@@ -210,6 +211,57 @@ def tight(pool):
     print('anchors_tight_grid: %d models, status histogram %s' % (len(trip), {int(k): int((st == k).sum()) for k in np.unique(st)}))
 
 
+LYA = dict(w0=1215.67e-10, f=0.4164, a=6.265e8, m=1.67262192369e-27)   # SURVEY.md 8(d), cfg 2 (caller-supplied line)
+
+
+def _run_lya(args):
+    """BASELINE configs[1]: hydrogen-only chain + Ly-alpha radiative transfer through the unmodified reference
+    (hydrogen.ion_fraction -> parker.structure -> n(H I) -> transit.radiative_transfer_2d)."""
+    T, md, h, tight = args
+    mg = _G['mg']
+    from p_winds import hydrogen, parker, transit
+    he_h = (1 - h) / h
+    mu_0 = (1 + 4 * he_h) / (1 + he_h)
+    o = dict(status=0, f_r=np.full(100, np.nan), mu_bar=np.nan, spectrum=np.full(200, np.nan))
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        try:
+            f_r, mu = hydrogen.ion_fraction(mg.R, mg.R_PL, float(T), float(h), float(md), mg.M_PL, mu_0,
+                                            spectrum_at_planet=_G['sp'], exact_phi=True, initial_f_ion=0.0,
+                                            relax_solution=True, return_mu=True, **(mg.TIGHT_H if tight else {}))
+        except RuntimeError:
+            o['status'] = 1
+            return o
+        vs = parker.sound_speed(float(T), mu)
+        rs = parker.radius_sonic_point(mg.M_PL, vs)
+        rhos = parker.density_sonic_point(float(md), rs, vs)
+        v, rho = parker.structure(mg.R * mg.R_PL / rs)
+        n_h1 = (1 - f_r) * rho * rhos * h / (h + 4 * (1 - h)) / 1.67262192369e-24 * 1E6
+        wl = np.linspace(1214.0, 1217.4, 200) * 1e-10
+        i0, r_map = _G['geom']
+        spec = transit.radiative_transfer_2d(i0, r_map, mg.R * (mg.R_PL * 71492000), n_h1, v * vs * 1000, LYA['w0'],
+                                             LYA['f'], LYA['a'], wl, float(T), LYA['m'])
+    o.update(f_r=f_r, mu_bar=mu, spectrum=spec)
+    return o
+
+
+def lya(pool):
+    """tests/golden/anchors_lya.npz: 5 x 5 models at tight tolerances (values) and the status map of the 32 x 32
+    grid of BASELINE configs[1] at the reference's defaults."""
+    trip = [(T, md, 0.9, True) for T in np.linspace(9000, 13000, 5) for md in np.logspace(9.5, 12, 5)]
+    res = pool.map(_run_lya, trip, chunksize=1)
+    d = {k: np.array([o[k] for o in res]) for k in ('status', 'f_r', 'mu_bar', 'spectrum')}
+    d['T0'] = np.array([t[0] for t in trip]); d['mdot'] = np.array([t[1] for t in trip])
+    TT, MM = np.meshgrid(np.linspace(10000, 13000, 32), np.logspace(9.5, 12, 32), indexing='ij')
+    grid = pool.map(_run_lya, [(t, m, 0.9, False) for t, m in zip(TT.ravel(), MM.ravel())], chunksize=8)
+    d['grid_T0'] = TT.ravel(); d['grid_mdot'] = MM.ravel()
+    d['grid_status'] = np.array([o['status'] for o in grid], dtype=np.int8)
+    d['grid_spectrum_min'] = np.array([np.nanmin(o['spectrum']) if o['status'] == 0 else np.nan for o in grid])
+    np.savez_compressed(os.path.join(OUT, 'anchors_lya.npz'), **d)
+    print('anchors_lya: tight status', np.bincount(d['status']), 'grid status', np.bincount(d['grid_status']),
+          'deepest core %.3f' % np.nanmin(d['grid_spectrum_min']))
+
+
 def classes(pool):
     parts = []
     for name, fn in (('bench_grid_status.npz', scan), ('ridge_status.npz', scan_ridge)):
@@ -270,3 +322,5 @@ if __name__ == '__main__':
             classes(pool)
         if what in ('tight', 'all'):
             tight(pool)
+        if what in ('lya', 'all'):
+            lya(pool)

@@ -607,6 +607,44 @@ def test_config2_lyman_alpha_hydrogen_only(eng, oracle, sed):
     assert (sp1[ok].min(axis=1) < 0.95 * cont).all()
 
 
+def test_config2_lyman_alpha_against_reference_fixture(eng):
+    """BASELINE configs[1] against the unmodified reference (tests/golden/anchors_lya.npz, made by
+    oracle/make_anchors.py lya: hydrogen.ion_fraction -> parker.structure -> n(H I) ->
+    transit.radiative_transfer_2d with the caller-supplied Ly-alpha line).  25 models at tight solver
+    tolerances: ion fractions within 1e-6, Ly-alpha transit spectrum within 1e-5, model by model; the 32 x 32
+    grid at the reference's defaults: same status for every model, line cores as deep."""
+    from p_winds_b200.engine import Engine
+    d = golden('anchors_lya')
+    m_p = 1.67262192369e-27
+    wl = np.linspace(1214.0, 1217.4, 200) * 1e-10
+    rto = Engine.rt_opts([1215.67e-10], [0.4164], [6.265e8], m_p)
+    sc = eng.sed_scalars()
+    heo = Engine.he_opts(1.39, [sc[k] for k in ('he_phi_1', 'he_phi_3', 'he_a_1', 'he_a_3', 'he_a_h_1', 'he_a_h_3')],
+                         (1.0, 0.0), True)
+    ho = Engine.h_opts(1.39, 0.73, relax_solution=True, exact_phi=True, rtol=1e-10, atol=1e-13)
+    n = len(d['T0'])
+    o = eng.forward_batch(d['T0'], d['mdot'], np.full(n, 0.9), R, ho, heo, rto, wl, species='h1')
+    st = o['status'].cpu().numpy()
+    assert (st == 0).all() and (d['status'] == 0).all()
+    f_r, spec = o['f_r'].cpu().numpy(), o['spectrum'].cpu().numpy()
+    e_f = np.max(_rel(f_r[:, 1:], d['f_r'][:, 1:]))
+    live = d['spectrum'] > 1e-12                   # saturated cores: compare absolutely there
+    e_s = np.max(_rel(spec[live], d['spectrum'][live]))
+    print('Ly-alpha, 25 models at tight tolerances: f_r %.2e, spectrum %.2e' % (e_f, e_s))
+    assert e_f < 1e-6 and e_s < 1e-5
+    assert np.max(np.abs(spec[~live] - d['spectrum'][~live])) < 1e-12 if (~live).any() else True
+    assert d['spectrum'].min() < 0.5 * d['spectrum'].max()          # the line is there
+    ho = Engine.h_opts(1.39, 0.73, relax_solution=True, exact_phi=True)
+    og = eng.forward_batch(d['grid_T0'], d['grid_mdot'], np.full(1024, 0.9), R, ho, heo, rto, wl, species='h1')
+    stg = og['status'].cpu().numpy()
+    assert np.array_equal(stg, d['grid_status'].astype(stg.dtype))
+    smin = og['spectrum'].cpu().numpy().min(axis=1)
+    ok = stg == 0
+    # default tolerances: the H stage is only reproducible to its RK45 noise (P3); the core depth follows f_r
+    assert np.median(np.abs(smin[ok] - d['grid_spectrum_min'][ok])) < 1e-6
+    assert np.max(np.abs(smin[ok] - d['grid_spectrum_min'][ok])) < 5e-3
+
+
 def test_config5_size_radiative_transfer(eng, oracle):
     """BASELINE config 5 sizes: 512 x 512 transit cells, 4096 wavelength bins, He 10830 +
     C II + O I line sets.  The reference needs 11.9 s and 34 GB per model and line set

@@ -145,6 +145,23 @@ def test_tight_grid_fixture_and_oracle(oracle, sed):
             assert np.array_equal(o[key], d[key][i]), (i, key)
 
 
+def test_lyman_alpha_fixture_and_oracle(oracle, sed):
+    """tests/golden/anchors_lya.npz (BASELINE configs[1], unmodified reference): the oracle's hydrogen-only
+    chain + Ly-alpha radiative transfer bit for bit on a sample."""
+    d = golden('anchors_lya')
+    geo = golden('geometry')
+    assert len(d['T0']) == 25 and (d['status'] == 0).all() and len(d['grid_status']) == 1024
+    wl = np.linspace(1214.0, 1217.4, 200) * 1e-10
+    s = oracle.Setup(sed, r=R, i0=geo['i0'], r_map=geo['r_map'], wl=wl,
+                     lines=(np.array([1215.67e-10]), np.array([0.4164]), np.array([6.265e8])),
+                     mass=1.67262192369e-27, h_tol=dict(rtol=1e-10, atol=1e-13), species='h1')
+    for i in (0, 7, 24):
+        o = oracle.forward_model(s, float(d['T0'][i]), float(d['mdot'][i]), 0.9)
+        assert o['status'] == 0
+        assert np.array_equal(o['f_r'], d['f_r'][i])
+        assert np.max(np.abs(o['spectrum'] - d['spectrum'][i])) <= 1e-15 * np.max(d['spectrum'][i])
+
+
 def test_helium_failure_class_fixture_and_oracle(oracle, sed):
     """tests/golden/he_failure_classes.npz: >= 20 models of each helium failure class from the unmodified
     reference; class-3 results are not reproducible run to run (recorded), the class is.  The oracle
