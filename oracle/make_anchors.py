@@ -9,6 +9,7 @@ TEST INFRASTRUCTURE.  Run in the build container only (needs /root/reference):
     python oracle/make_anchors.py classes   # tests/golden/he_failure_classes.npz
     python oracle/make_anchors.py tight     # tests/golden/anchors_tight_grid.npz
     python oracle/make_anchors.py lya       # tests/golden/anchors_lya.npz (BASELINE configs[1])
+    python oracle/make_anchors.py tidal     # tests/golden/tidal_grid_status.npz (sample of BASELINE configs[3])
 
 ``anchors_p3.npz``: 272 (T0, Mdot, h) triples (144 non-tidal, 128 tidal, T0 from 5000 K so
 that the models the reference fails on are in it).  For each triple the reference's own
@@ -119,6 +120,19 @@ def scan(pool):
     np.savez_compressed(os.path.join(OUT, 'bench_grid_status.npz'), T0=T, mdot=M, status=st.astype(np.int8))
     print('bench grid status histogram', {int(k): int((st == k).sum()) for k in np.unique(st)})
     return T, M, st
+
+
+def scan_tidal(pool):
+    """tests/golden/tidal_grid_status.npz: the status the reference ends with on a 32 x 32 x 2 sample of the
+    north-star grid (BASELINE configs[3]: T0 9000-13000 K, Mdot 10^9.5-10^12 g/s, h = 0.85 / 0.95, tidal term)."""
+    TT, MM, HH = np.meshgrid(np.linspace(9000, 13000, 32), np.logspace(9.5, 12, 32), np.array([0.85, 0.95]), indexing='ij')
+    T, M, H = TT.ravel(), MM.ravel(), HH.ravel()
+    res = pool.map(_run, [(t, m, h, True, -1) for t, m, h in zip(T, M, H)], chunksize=8)
+    st = np.array([o['status'] for o in res], dtype=np.int8)
+    smin = np.array([np.nanmin(o['spectrum']) if o['status'] in (0, 3) else np.nan for o in res])
+    np.savez_compressed(os.path.join(OUT, 'tidal_grid_status.npz'), T0=T, mdot=M, h_fraction=H, status=st,
+                        spectrum_min=smin)
+    print('tidal grid status histogram', {int(k): int((st == k).sum()) for k in np.unique(st)})
 
 
 def ridge_grid():
@@ -324,3 +338,5 @@ if __name__ == '__main__':
             tight(pool)
         if what in ('lya', 'all'):
             lya(pool)
+        if what in ('tidal', 'all'):
+            scan_tidal(pool)

