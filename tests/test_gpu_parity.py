@@ -806,6 +806,41 @@ def test_pixel_sum_kernels_agree_bit_for_bit(built, oracle):
         assert np.array_equal(a, b2), (name, np.max(np.abs(a - b2)))
 
 
+@pytest.mark.parametrize('nw', [1, 2, 3, 63, 511, 513, 1025])
+def test_pixel_sum_odd_shapes(built, oracle, nw):
+    """Tile and pair edge cases of k_rt_sum2 (one bin, an odd bin count, one bin past a tile boundary,
+    fewer than 64 threads per CTA), a single model, both launch shapes, against the oracle."""
+    import os
+    from p_winds_b200.engine import Engine
+    from p_winds_b200 import lines
+    prof = golden('he_3_profile')
+    geo = golden('geometry')
+    w = lines.he_3_properties()
+    w0, f, a = np.array(w[:3]), np.array(w[3:6]), np.array([w[6]] * 3)
+    rto = Engine.rt_opts(w0, f, a, M_HE, bulk_los_velocity=-2E3)
+    r_si, n_si, v_si = prof['r'][::5].copy(), prof['n'][::5].copy(), prof['v'][::5].copy()
+    wl = np.linspace(1.0829, 1.0831, nw) * 1e-6 if nw > 1 else np.array([1.08303e-6])
+    eng = Engine(0)
+    eng.set_geometry(geo['test_i0'], geo['test_r_map'], r_si)
+    ref = oracle.radiative_transfer_2d(geo['test_i0'], geo['test_r_map'], r_si, n_si, v_si, w0, f, a, wl[:40], 9000., M_HE,
+                                       v_bulk=-2E3)
+    out = {}
+    for key in ('PWB_RT_SPLIT', 'PWB_RT_NOSPLIT'):
+        os.environ[key] = '1'
+        try:
+            out[key] = eng.rt2d_batch(n_si[None, :], v_si[None, :], np.array([9000.]), wl, rto).cpu().numpy()[0]
+        finally:
+            del os.environ[key]
+    assert np.array_equal(out['PWB_RT_SPLIT'], out['PWB_RT_NOSPLIT'])
+    assert out['PWB_RT_SPLIT'].shape == (nw,)
+    assert np.max(_rel(out['PWB_RT_SPLIT'][:40], ref)) < 1e-10
+    # a geometry without a single lit pixel inside the radius grid: the spectrum is the unocculted flux
+    far = np.full_like(geo['test_r_map'], 10 * r_si[-1])
+    eng.set_geometry(geo['test_i0'], far, r_si)
+    flat = eng.rt2d_batch(n_si[None, :], v_si[None, :], np.array([9000.]), wl, rto).cpu().numpy()[0]
+    assert np.max(np.abs(flat - geo['test_i0'].sum())) < 1e-12
+
+
 def test_config3_share_tidal_grid_properties(eng):
     """BASELINE configs[3] at full size for one GPU: every 8th model (one rank's interleaved share)
     of the 256 x 256 (T0, Mdot) x 3 h_fraction grid with the tidal Parker profile -- 24 576 models
