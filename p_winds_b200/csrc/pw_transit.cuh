@@ -198,13 +198,13 @@ PW_HD void los_cell(const double* __restrict__ r, const double* __restrict__ n, 
     const int hi = interp1d_hi(r, nr, d);
     const int lo = hi - 1;
     const double dx = r[hi] - r[lo];
-    const double whi = (d - r[lo]) / dx, wlo = (r[hi] - d) / dx;
+    const double whi = PW_DIV_INLINE(d - r[lo], dx), wlo = PW_DIV_INLINE(r[hi] - d, dx);
     nc = whi * n[hi] + wlo * n[lo];
     vc = whi * v[hi] + wlo * v[lo];
     if (tprof) tc = whi * tprof[hi] + wlo * tprof[lo];
   }
   *n_c = nc;
-  *vlos = vc * z / sqrt(z * z + b * b);
+  *vlos = PW_DIV_INLINE(vc * z, sqrt(z * z + b * b));
   if (t_c) *t_c = tc;
 }
 
