@@ -1,5 +1,7 @@
 """He singlet / triplet populations (reference: p_winds/helium.py), reference
 signatures; the work is done by k_helium (csrc/pw_helium.cuh, LSODA replica)."""
+import warnings
+
 import numpy as np
 
 from . import tools
@@ -112,6 +114,12 @@ def population_fraction(radius_profile, velocity, density, hydrogen_ion_fraction
     if status == 2:
         msg = STATUS_MESSAGES[2] if method == 'odeint' else STATUS_MESSAGES[1]
         raise RuntimeError(msg)
+    if status == 3:
+        # helium.py:736: the reference's user sees an ODEintWarning here and gets an array whose rows after the
+        # failing radius were never written; the engine returns the last relax pass that completed
+        warnings.warn('odeint warned inside the relax loop (pass %d): the populations of the last completed pass '
+                      'are returned; the reference result is undefined for this model.' % int(o['scal'][0, 0].cpu()),
+                      RuntimeWarning, stacklevel=2)
     f1, f3 = o['f_1'][0].cpu().numpy(), o['f_3'][0].cpu().numpy()
     if return_rates is True:
         rr = o['rates'][0].cpu().numpy()

@@ -399,6 +399,17 @@ def test_helium_reference_signature(eng, oracle, sed):
         oracle_mono(oracle, 500., 5e6), rel=1e-14)
     with pytest.raises(ValueError, match='no CPU fallback'):
         helium.population_fraction(r, v, rho, f_r, 1.39, T0, h, vs, rs, rhos, sp, method='Radau')
+    # status 3 through the reference signature: a RuntimeWarning (the reference's user sees scipy's ODEintWarning)
+    # and the populations of the last completed pass
+    c = golden('he_failure_classes')
+    i3 = int(np.flatnonzero(c['status'] == 3)[0])
+    o3 = _forward(eng, c['T0'][i3:i3 + 1], c['mdot'][i3:i3 + 1], c['h_fraction'][i3:i3 + 1])
+    assert o3['status'][0] == 3
+    with pytest.warns(RuntimeWarning, match='relax loop'):
+        g1, g3 = helium.population_fraction(r, o3['v'][0], o3['rho'][0], o3['f_r'][0], 1.39, float(c['T0'][i3]), 0.9,
+                                            float(o3['hscal'][0, 1]), float(o3['hscal'][0, 2]), float(o3['hscal'][0, 3]),
+                                            sp, initial_state=np.array([1.0, 0.0]), relax_solution=True)
+    assert np.array_equal(g1, o3['f_1'][0]) and np.array_equal(g3, o3['f_3'][0])
     with pytest.raises(ValueError, match='Either `spectrum_at_planet` must be provided'):
         helium.population_fraction(r, v, rho, f_r, 1.39, T0, h, vs, rs, rhos)
     assert helium.collision(9100.) == pytest.approx(tuple(oracle.he_collision(9100.)), rel=1e-15)
