@@ -812,13 +812,10 @@ def he_ion_fraction(r, v, rho, f_h, r_pl, T, h_fraction, vs, rs, rhos, sed=None,
 
     def solve(first):
         if method == 'odeint':
-            with warnings.catch_warnings():
-                warnings.filterwarnings('error' if first else 'ignore')
-                try:
-                    sol = odeint(fun, y0=initial_f_he_ion, t=rn, tfirst=True)
-                except Warning:
-                    return None
-            return np.copy(sol).T[0]
+            sol = _odeint_relax(fun, initial_f_he_ion, rn)
+            if sol is None:
+                return None if first else 'warned'
+            return sol.T[0]
         sol = solve_ivp(fun, (rn[0], rn[-1],), np.array([initial_f_he_ion, ]), t_eval=rn, method=method,
                         **options)
         out['nfev'].append(sol.nfev)
@@ -836,13 +833,28 @@ def he_ion_fraction(r, v, rho, f_h, r_pl, T, h_fraction, vs, rs, rhos, sed=None,
             if f is None:
                 out.update(status=2, f_he_ion=nan)
                 return out
+            out['n_relax'] = i + 1
+            if isinstance(f, str):      # odeint warned: stop, last completed pass (status 3)
+                out['status'] = 3
+                f = prev
+                break
             f[f < 0] = 1E-15
             f[f > 1.0] = 1.0
-            out['n_relax'] = i + 1
             if abs(np.sum(f - prev)) / np.sum(prev) < convergence:
                 break
     out['f_he_ion'] = f
     return out
+
+
+def _odeint_relax(fun, y0, rn):
+    """`odeint` as the relax loops of helium.ion_fraction / oxygen / carbon call it (unchecked).  Returns None
+    when it warned: the reference carries on with rows scipy left uninitialised, i.e. its result is undefined
+    from there on; the oracle (and the engine) stop at the warning -- status 3, last completed pass (see
+    he_population)."""
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter('always')
+        sol = odeint(fun, y0=y0, t=rn, tfirst=True)
+    return None if len(w) > 0 else np.copy(sol)
 
 
 # ----------------------------------------------------------------------------
@@ -988,9 +1000,13 @@ def o_ion_fraction(r, v, rho, f_h, f_he_ion, r_pl, T, h_fraction, vs, rs, rhos, 
             prev = np.copy(f)
             state['tau'] = k3 * a_oi * np.flip(np.cumsum(np.flip(dr * rho * (1 - f)))) + tau_h + tau_he
             if method == 'odeint':
-                with warnings.catch_warnings():
-                    warnings.simplefilter('ignore')
-                    f = np.copy(odeint(fun, y0=initial_f_o_ion, t=rn, tfirst=True)).T[0]
+                sol = _odeint_relax(fun, initial_f_o_ion, rn)
+                if sol is None:          # odeint warned: stop, last completed pass (status 3)
+                    out['status'] = 3
+                    out['n_relax'] = i + 1
+                    f = prev
+                    break
+                f = sol.T[0]
             else:
                 sol = solve_ivp(fun, (rn[0], rn[-1],), np.array([initial_f_o_ion, ]), t_eval=rn,
                                 method=method, **options)
@@ -1138,13 +1154,10 @@ def c_ion_fraction(r, v, rho, f_h, f_he_ion, r_pl, T, h_fraction, vs, rs, rhos, 
 
     def solve(first):
         if method == 'odeint':
-            with warnings.catch_warnings():
-                warnings.filterwarnings('error' if first else 'ignore')
-                try:
-                    sol = odeint(fun, y0=y0, t=rn, tfirst=True)
-                except Warning:
-                    return None
-            return np.copy(sol).T[0], np.copy(sol).T[1]
+            sol = _odeint_relax(fun, y0, rn)
+            if sol is None:
+                return None if first else 'warned'
+            return sol.T[0].copy(), sol.T[1].copy()
         sol = solve_ivp(fun, (rn[0], rn[-1],), y0, t_eval=rn, method=method, **options)
         out['nfev'].append(sol.nfev)
         if len(sol['y'][0]) != len(rn):
@@ -1171,6 +1184,11 @@ def c_ion_fraction(r, v, rho, f_h, f_he_ion, r_pl, T, h_fraction, vs, rs, rhos, 
             if res is None:          # the reference would crash on the next lines (shape mismatch)
                 out.update(status=2, f_cii=nan, f_ciii=nan.copy())
                 return out
+            if isinstance(res, str):  # odeint warned: stop, last completed pass (status 3)
+                out['status'] = 3
+                out['n_relax'] = i + 1
+                f2, f3 = p2, p3
+                break
             f2, f3 = res
             clamp(f2)
             clamp(f3)

@@ -1,6 +1,8 @@
 """C II / C III fractions (reference: p_winds/carbon.py), reference signatures; the work is done
 by k_carbon (csrc/pw_carbon.cuh) with the LSODA replica ('odeint', the reference default) or the
 Radau IIA replica (the method the exospheric-metals tutorial uses)."""
+import warnings
+
 import numpy as np
 
 from . import tools
@@ -76,6 +78,11 @@ def ion_fraction(radius_profile, velocity, density, hydrogen_ion_fraction, heliu
                                  helium_ion_fraction, opts, return_rates=return_rates is True)
     if int(o['status'].cpu()[0]) == 2:
         raise RuntimeError(STATUS_MESSAGES[2] if method == 'odeint' else STATUS_MESSAGES[1])
+    if int(o['status'].cpu()[0]) == 3:
+        # an `odeint` of the relax loop warned: the reference goes on with rows its solver never wrote (undefined
+        # result); the engine returns the last relax pass that completed
+        warnings.warn('odeint warned inside the relax loop: the fractions of the last completed pass are returned; '
+                      'the reference result is undefined for this model.', RuntimeWarning, stacklevel=2)
     f2, f3 = o['f_cii'][0].cpu().numpy(), o['f_ciii'][0].cpu().numpy()
     if return_rates is True:
         t = dict(zip(_TERM_ORDER, o['rates'][0].cpu().numpy()))

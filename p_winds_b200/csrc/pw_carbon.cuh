@@ -132,7 +132,6 @@ PW_HD bool c_solve(const CParams& p, CRhs& rhs, const LsodaTables& tab, int nr, 
     f2[k] = yo[0];
     f3[k] = yo[1];
   }
-  for (int q = k; q < nr; ++q) { f2[q] = 0.0; f3[q] = 0.0; }
   *nfev += s.nfe;
   return ok;
 }
@@ -218,6 +217,14 @@ PW_HD void c_ion_fraction_model(const CParams& p, const LsodaTables& tab, const 
       status = PW_FAIL_HE_SOLVER;  // RuntimeError of carbon.py:541-557
       break;
     }
+    if (!ok) {   // carbon.py:587
+      // An `odeint` of the relax loop warned.  The reference does not check it and carries on with rows scipy
+      // left uninitialised (helium.py:736 has the same pattern; pw_helium.cuh): undefined from here on.  Stop,
+      // hand back the last completed pass, status PW_WARN_HE_RELAX.
+      status = PW_WARN_HE_RELAX;
+      for (int i = 0; i < nr; ++i) { f2[i] = w.prev2[i]; f3[i] = w.prev3[i]; }
+      break;
+    }
     clamp();
     if (it > 0) {
       double d2 = 0.0, d3 = 0.0;
@@ -225,7 +232,7 @@ PW_HD void c_ion_fraction_model(const CParams& p, const LsodaTables& tab, const 
       if (fabs(d2) / s2 < p.convergence && fabs(d3) / s3 < p.convergence) break;  // :607-616
     }
   }
-  if (status != PW_OK) {
+  if (status == PW_FAIL_HE_SOLVER) {
     const double nan_ = nan("");
     for (int i = 0; i < nr; ++i) { f2[i] = nan_; f3[i] = nan_; }
   } else if (out.rates) {

@@ -87,7 +87,6 @@ PW_HD bool scalar_ode_solve(int method, double y0, const Rk45Opts& o, RHS& rhs, 
     if (s.call(rn[0], &y0, rn[k], yo) < 0) { ok = false; break; }
     f[k] = yo[0];
   }
-  for (int q = k; q < nr; ++q) f[q] = 0.0;
   *nfev += s.nfe;
   return ok;
 }
@@ -145,6 +144,14 @@ PW_HD void he_ion_fraction_model(const HeIonParams& p, const LsodaTables& tab, c
       status = PW_FAIL_HE_SOLVER;
       break;
     }
+    if (!ok) {   // helium.py:1007
+      // An `odeint` of the relax loop warned.  The reference does not check it and carries on with rows scipy
+      // left uninitialised (helium.py:736 has the same pattern; pw_helium.cuh): undefined from here on.  Stop,
+      // hand back the last completed pass, status PW_WARN_HE_RELAX.
+      status = PW_WARN_HE_RELAX;
+      for (int i = 0; i < nr; ++i) f[i] = w.prev[i];
+      break;
+    }
     if (it > 0) {  // the reference clamps only inside the relax loop (:1015-1016)
       for (int i = 0; i < nr; ++i) {
         if (f[i] < 0) f[i] = 1E-15;
@@ -155,7 +162,7 @@ PW_HD void he_ion_fraction_model(const HeIonParams& p, const LsodaTables& tab, c
       if (fabs(d) / sp < p.convergence) break;
     }
   }
-  if (status != PW_OK) {
+  if (status == PW_FAIL_HE_SOLVER) {
     const double nan_ = nan("");
     for (int i = 0; i < nr; ++i) f[i] = nan_;
   }

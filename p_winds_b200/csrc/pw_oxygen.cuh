@@ -114,7 +114,6 @@ PW_HD bool o_solve(const OParams& p, ORhs& rhs, const LsodaTables& tab, int nr, 
     if (s.call(rn[0], &y0, rn[k], yo) < 0) { ok = false; break; }
     f[k] = yo[0];
   }
-  for (int q = k; q < nr; ++q) f[q] = 0.0;
   *nfev += s.nfe;
   (void)ytmp;
   return ok;
@@ -188,6 +187,14 @@ PW_HD void o_ion_fraction_model(const OParams& p, const LsodaTables& tab, const 
       status = PW_FAIL_HE_SOLVER;
       break;
     }
+    if (!ok) {   // oxygen.py:455
+      // An `odeint` of the relax loop warned.  The reference does not check it and carries on with rows scipy
+      // left uninitialised (helium.py:736 has the same pattern; pw_helium.cuh): undefined from here on.  Stop,
+      // hand back the last completed pass, status PW_WARN_HE_RELAX.
+      status = PW_WARN_HE_RELAX;
+      for (int i = 0; i < nr; ++i) f[i] = w.prev[i];
+      break;
+    }
     clamp();
     if (it > 0) {
       double d = 0.0;
@@ -195,7 +202,7 @@ PW_HD void o_ion_fraction_model(const OParams& p, const LsodaTables& tab, const 
       if (fabs(d) / sp < p.convergence) break;  // :470-475
     }
   }
-  if (status != PW_OK) {
+  if (status == PW_FAIL_HE_SOLVER) {
     const double nan_ = nan("");
     for (int i = 0; i < nr; ++i) f[i] = nan_;
   } else if (out.rates) {

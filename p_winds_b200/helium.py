@@ -159,4 +159,9 @@ def ion_fraction(radius_profile, velocity, density, hydrogen_ion_fraction, plane
                                   [density_sonic_point], r, velocity, density, hydrogen_ion_fraction, opts)
     if int(o['status'].cpu()[0]) == 2:
         raise RuntimeError(STATUS_MESSAGES[2] if method == 'odeint' else STATUS_MESSAGES[1])
+    if int(o['status'].cpu()[0]) == 3:
+        # an `odeint` of the relax loop warned: the reference goes on with rows its solver never wrote (undefined
+        # result); the engine returns the last relax pass that completed
+        warnings.warn('odeint warned inside the relax loop: the fractions of the last completed pass are returned; '
+                      'the reference result is undefined for this model.', RuntimeWarning, stacklevel=2)
     return o['f_he_ion'][0].cpu().numpy()

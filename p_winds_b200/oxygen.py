@@ -1,6 +1,8 @@
 """O II fraction (reference: p_winds/oxygen.py), reference signatures; the work is done by
 k_oxygen (csrc/pw_oxygen.cuh) with the Radau IIA replica of csrc/pw_radau.cuh (the reference's
 default integrator for this species)."""
+import warnings
+
 import numpy as np
 
 from . import tools
@@ -65,6 +67,11 @@ def ion_fraction(radius_profile, velocity, density, hydrogen_ion_fraction, heliu
                                  helium_ion_fraction, opts, return_rates=return_rates is True)
     if int(o['status'].cpu()[0]) == 2:
         raise RuntimeError(STATUS_MESSAGES[2] if method == 'odeint' else STATUS_MESSAGES[1])
+    if int(o['status'].cpu()[0]) == 3:
+        # an `odeint` of the relax loop warned: the reference goes on with rows its solver never wrote (undefined
+        # result); the engine returns the last relax pass that completed
+        warnings.warn('odeint warned inside the relax loop: the fractions of the last completed pass are returned; '
+                      'the reference result is undefined for this model.', RuntimeWarning, stacklevel=2)
     f = o['f_o'][0].cpu().numpy()
     if return_rates is True:
         rr = o['rates'][0].cpu().numpy()
