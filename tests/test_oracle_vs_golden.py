@@ -138,7 +138,7 @@ def test_tight_grid_fixture_and_oracle(oracle, sed):
     assert len(d['T0']) == 100 and (d['status'] == 0).all()
     for i in (3, 40, 70, 99):
         s = oracle.Setup(sed, r=R, tidal=bool(d['tidal'][i]), i0=geo['i0'], r_map=geo['r_map'],
-                         h_tol=dict(rtol=1e-10, atol=1e-13), he_method='LSODA', he_tol=dict(rtol=1e-10, atol=1e-16))
+                         h_tol=dict(rtol=1e-12, atol=1e-15), he_method='LSODA', he_tol=dict(rtol=1e-10, atol=1e-16))
         o = oracle.forward_model(s, float(d['T0'][i]), float(d['mdot'][i]), float(d['h_fraction'][i]))
         assert o['status'] == 0
         for key in ('f_r', 'f_1', 'f_3', 'spectrum'):
